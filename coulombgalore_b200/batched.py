@@ -1,0 +1,114 @@
+"""Batched pair-interaction evaluator: the loop over pairs the reference leaves to its caller, run on a B200.
+
+Thin Python veneer over the C ABI (include/cg_b200.h).  Host buffers are numpy arrays; device buffers are anything
+exposing `data_ptr()` (torch CUDA tensors) -- PyTorch is only the allocator/stream provider here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import ENERGY, FIELD, FORCE, POTENTIAL, check, lib
+
+
+def _hp(a):
+    return None if a is None else a.ctypes.data
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _devptr(t):
+    if t is None:
+        return None
+    if not getattr(t, "is_cuda", False):
+        raise TypeError("device buffer expected (torch CUDA tensor)")
+    if str(t.dtype) != "torch.float64" or not t.is_contiguous():
+        raise TypeError("device buffers must be contiguous float64")
+    return t.data_ptr()
+
+
+class BatchedEvaluator:
+    def __init__(self, scheme, device=-1):
+        self.scheme = scheme
+        self.h = C.c_void_p()
+        check(lib.cg_create(C.byref(scheme.desc), device, C.byref(self.h)), "cg_create")
+        self.n = 0
+        self._keep = None
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            lib.cg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        check(lib.cg_set_stream(self.h, cuda_stream_ptr), "cg_set_stream", self.h)
+
+    def set_shard(self, rank, nranks):
+        check(lib.cg_set_shard(self.h, rank, nranks), "cg_set_shard", self.h)
+
+    # ---- host path ----
+    def set_system(self, x, y, z, q=None, mu=None, box=None, pbc=False):
+        x, y, z, q = _f64(x), _f64(y), _f64(z), _f64(q)
+        mx, my, mz = (None, None, None) if mu is None else [_f64(m) for m in mu]
+        b = None if box is None else np.ascontiguousarray(box, dtype=np.float64)
+        self.n = x.size
+        self._keep = (x, y, z, q, mx, my, mz, b)
+        check(lib.cg_set_system(self.h, self.n, _hp(x), _hp(y), _hp(z), _hp(q), _hp(mx), _hp(my), _hp(mz),
+                                None if b is None else b.ctypes.data_as(_capi._dp), int(bool(pbc))), "cg_set_system", self.h)
+
+    def eval(self, mode, what):
+        """-> dict(force (n,3), field (n,3), potential (n,), energy, pairs); entries not requested are None."""
+        n = self.n
+        f = np.empty((n, 3)) if what & FORCE else None
+        e = np.empty((n, 3)) if what & FIELD else None
+        p = np.empty(n) if what & POTENTIAL else None
+        u = C.c_double(0.0)
+        cnt = C.c_int64(0)
+        check(lib.cg_eval(self.h, mode, what, _hp(f), _hp(e), _hp(p), C.byref(u), C.byref(cnt)), "cg_eval", self.h)
+        return dict(force=f, field=e, potential=p, energy=u.value if what & ENERGY else None, pairs=cnt.value)
+
+    # ---- device path (zero copy) ----
+    def set_system_device(self, x, y, z, q=None, mu=None, box=None, pbc=False):
+        mx, my, mz = (None, None, None) if mu is None else mu
+        b = None if box is None else np.ascontiguousarray(box, dtype=np.float64)
+        self.n = x.numel()
+        self._keep = (x, y, z, q, mx, my, mz, b)
+        check(lib.cg_set_system_device(self.h, self.n, _devptr(x), _devptr(y), _devptr(z), _devptr(q), _devptr(mx),
+                                       _devptr(my), _devptr(mz), None if b is None else b.ctypes.data_as(_capi._dp),
+                                       int(bool(pbc))), "cg_set_system_device", self.h)
+
+    def eval_device(self, mode, what, force=None, field=None, potential=None, scalars=None):
+        """Asynchronous on the handle's stream; scalars (2 float64 on the device) receives U and the pair count."""
+        check(lib.cg_eval_device(self.h, mode, what, _devptr(force), _devptr(field), _devptr(potential), _devptr(scalars)),
+              "cg_eval_device", self.h)
+
+    def srf_device(self, q, out):
+        check(lib.cg_srf_device(self.h, q.numel(), _devptr(q), _devptr(out)), "cg_srf_device", self.h)
+
+    def generate_lattice_device(self, n, a, seed, x, y, z, q=None, mu=None):
+        mx, my, mz = (None, None, None) if mu is None else mu
+        check(lib.cg_generate_lattice_device(self.h, n, a, seed, _devptr(x), _devptr(y), _devptr(z), _devptr(q),
+                                             _devptr(mx), _devptr(my), _devptr(mz)), "cg_generate_lattice_device", self.h)
+
+    def timings(self):
+        ms = (C.c_double * 4)()
+        check(lib.cg_last_timings(self.h, ms), "cg_last_timings", self.h)
+        return dict(sort_ms=ms[0], pair_ms=ms[1], epilogue_ms=ms[2], step_ms=ms[3])
+
+    def counters(self):
+        c = (C.c_int64 * 8)()
+        check(lib.cg_last_counters(self.h, c), "cg_last_counters", self.h)
+        return dict(sorted_entries=c[0], cells=c[1], groups=c[2], pair_launches=c[3], launches=c[4], split=c[5], items=c[7])
+
+    def fp64_peak_probe(self):
+        t, ms = C.c_double(0), C.c_double(0)
+        check(lib.cg_fp64_peak_probe(self.h, C.byref(t), C.byref(ms)), "cg_fp64_peak_probe", self.h)
+        return t.value, ms.value

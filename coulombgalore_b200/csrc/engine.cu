@@ -1,0 +1,1020 @@
+// engine.cu -- host side of libcg_b200.so: the cg_handle, the spatial sort (cells + periodic ghost images),
+// the i-group table, kernel dispatch, reductions and the C ABI of include/cg_b200.h.
+//
+// Per evaluation ("step"):
+//   1. bin_count      one thread per particle: cell of the particle and of each of its periodic images that lies
+//                     within one cut-off of the box (ghost cells); integer atomics into the cell histogram
+//   2. scan           exclusive scan of the histogram -> cell_start (own 2-level scan kernels)
+//   3. row_groups     i-groups per primary cell row (<= 32 consecutive entries, never crossing a row)   + scan
+//   4. bin_scatter    keys (particle, image code) into cell order; cell_sort makes the order inside a cell
+//                     deterministic (ascending key), so results are bit-reproducible run to run
+//   5. gather         SoA inputs -> sorted AoS double4 {x,y,z,q}, double4 {mu,0}, float4 (relative, for the prefilter)
+//   6. pair_kernel    (pair_kernel.cuh)  7. combine (j-split only)  8. reduce_items -> U and pair count
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cg_b200.h"
+#include "coulombgalore/detail/descriptor.hpp"
+#include "kparams.cuh"
+
+namespace cgb {
+
+// functor tables, one translation unit each (pair_inst_*.cu)
+const FunctorEntry *entry_plain();
+const FunctorEntry *entry_plain_yukawa();
+const FunctorEntry *entry_reactionfield();
+const FunctorEntry *entry_poisson();
+const FunctorEntry *entry_poisson_yukawa();
+const FunctorEntry *entry_qpotential();
+const FunctorEntry *entry_qpotential3();
+const FunctorEntry *entry_fanourgakis();
+const FunctorEntry *entry_wolf();
+const FunctorEntry *entry_fennell();
+const FunctorEntry *entry_zerodipole();
+const FunctorEntry *entry_zahn();
+const FunctorEntry *entry_ewald();
+const FunctorEntry *entry_ewald_screened();
+const FunctorEntry *entry_ewaldt();
+const FunctorEntry *entry_spline();
+const FunctorEntry *entry_spline_yukawa();
+
+const FunctorEntry *functor_entry(int id) {
+    switch (id) {
+    case kFnPlain: return entry_plain();
+    case kFnPlainYukawa: return entry_plain_yukawa();
+    case kFnReactionField: return entry_reactionfield();
+    case kFnPoisson: return entry_poisson();
+    case kFnPoissonYukawa: return entry_poisson_yukawa();
+    case kFnQPotential: return entry_qpotential();
+    case kFnQPotential3: return entry_qpotential3();
+    case kFnFanourgakis: return entry_fanourgakis();
+    case kFnWolf: return entry_wolf();
+    case kFnFennell: return entry_fennell();
+    case kFnZeroDipole: return entry_zerodipole();
+    case kFnZahn: return entry_zahn();
+    case kFnEwald: return entry_ewald();
+    case kFnEwaldScreened: return entry_ewald_screened();
+    case kFnEwaldT: return entry_ewaldt();
+    case kFnSpline: return entry_spline();
+    case kFnSplineYukawa: return entry_spline_yukawa();
+    default: return nullptr;
+    }
+}
+
+// which functor instantiation serves a descriptor
+static int functor_for(const cg_scheme_desc &d) {
+    const bool core_yukawa = d.inverse_debye_length != 0.0;
+    switch (d.functor) {
+    case CG_PLAIN: return core_yukawa ? kFnPlainYukawa : kFnPlain;
+    case CG_REACTIONFIELD: return kFnReactionField;
+    case CG_POISSON: return core_yukawa ? kFnPoissonYukawa : kFnPoisson;
+    case CG_QPOTENTIAL:
+    case CG_QPOTENTIAL5: return d.order == 3 ? kFnQPotential3 : kFnQPotential;
+    case CG_FANOURGAKIS: return kFnFanourgakis;
+    case CG_WOLF: return kFnWolf;
+    case CG_FENNELL: return kFnFennell;
+    case CG_ZERODIPOLE: return kFnZeroDipole;
+    case CG_ZAHN: return kFnZahn;
+    case CG_EWALD: return d.zeta != 0.0 ? kFnEwaldScreened : kFnEwald;
+    case CG_EWALDT: return kFnEwaldT;
+    case CG_SPLINE: return core_yukawa ? kFnSplineYukawa : kFnSpline;
+    default: return -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sort / binning kernels
+// ---------------------------------------------------------------------------------------------------------------
+struct SortParams {
+    int n;
+    const double *x, *y, *z, *q, *mx, *my, *mz;
+    double lo[3];     // lower corner of the primary region (0 for periodic boxes, min coordinate for open ones)
+    double box[3];    // periodic lengths (or extent for open boundaries)
+    double gw[3];     // ghost width = ghost layers * cell size (0 for open boundaries)
+    double inv_cs[3];
+    int nprim[3], ghost[3], ntot[3];
+    int pbc;
+};
+
+// per dimension: up to three images (shift 0 always; +1 / -1 when the image falls into the ghost layer)
+__device__ __forceinline__ int images_1d(const SortParams &sp, int d, double v, int *shift, int *cell) {
+    int m = 0;
+    const int g = sp.ghost[d], np = sp.nprim[d];
+    int c = (int)floor(v * sp.inv_cs[d]);
+    c = c < 0 ? 0 : (c > np - 1 ? np - 1 : c);
+    shift[m] = 0;
+    cell[m++] = g + c;
+    if (sp.pbc && g > 0) {
+        if (v < sp.gw[d]) { // image at v + L lies in the upper ghost layer
+            int cc = (int)floor((v + sp.box[d]) * sp.inv_cs[d]) + g;
+            cc = cc < g + np ? g + np : (cc > sp.ntot[d] - 1 ? sp.ntot[d] - 1 : cc);
+            shift[m] = 1;
+            cell[m++] = cc;
+        }
+        if (v >= sp.box[d] - sp.gw[d]) { // image at v - L lies in the lower ghost layer
+            int cc = (int)floor((v - sp.box[d] + sp.gw[d]) * sp.inv_cs[d]);
+            cc = cc < 0 ? 0 : (cc > g - 1 ? g - 1 : cc);
+            shift[m] = -1;
+            cell[m++] = cc;
+        }
+    }
+    return m;
+}
+
+template <bool SCATTER>
+__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= sp.n) return;
+    int sx[3], cx[3], sy[3], cy[3], sz[3], cz[3];
+    const int mx = images_1d(sp, 0, sp.x[p] - sp.lo[0], sx, cx);
+    const int my = images_1d(sp, 1, sp.y[p] - sp.lo[1], sy, cy);
+    const int mz = images_1d(sp, 2, sp.z[p] - sp.lo[2], sz, cz);
+    for (int c = 0; c < mz; c++)
+        for (int b = 0; b < my; b++)
+            for (int a = 0; a < mx; a++) {
+                const int cell = (cz[c] * sp.ntot[1] + cy[b]) * sp.ntot[0] + cx[a];
+                const int slot = atomicAdd(&cell_count[cell], 1);
+                if (SCATTER) {
+                    const unsigned int code = (unsigned int)((sx[a] + 1) + 3 * (sy[b] + 1) + 9 * (sz[c] + 1));
+                    keys[cell_start[cell] + slot] = (unsigned int)p * 27u + code;
+                }
+            }
+}
+
+// make the order inside every cell deterministic: ascending key (cells hold a handful of entries)
+__global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int *keys) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    const int a = cell_start[c], b = cell_start[c + 1];
+    for (int i = a + 1; i < b; i++) {
+        const unsigned int k = keys[i];
+        int j = i - 1;
+        while (j >= a && keys[j] > k) {
+            keys[j + 1] = keys[j];
+            j--;
+        }
+        keys[j + 1] = k;
+    }
+}
+
+__global__ void gather_kernel(const __grid_constant__ SortParams sp, int n_sorted, const unsigned int *keys, double4 *pos,
+                              double4 *mu, float4 *pos32, int *orig) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_sorted) return;
+    const unsigned int key = keys[k];
+    const int p = (int)(key / 27u);
+    const int code = (int)(key - (unsigned int)p * 27u);
+    const int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
+    // stored coordinate = r_j + shift (the image), formed exactly as oracle/harness.hpp forms it
+    const double X = sp.x[p] + (double)sx * sp.box[0], Y = sp.y[p] + (double)sy * sp.box[1], Z = sp.z[p] + (double)sz * sp.box[2];
+    pos[k] = make_double4(X, Y, Z, sp.q ? sp.q[p] : 0.0);
+    if (mu) mu[k] = sp.mx ? make_double4(sp.mx[p], sp.my[p], sp.mz[p], 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
+    pos32[k] = make_float4((float)(X - (sp.lo[0] - sp.gw[0])), (float)(Y - (sp.lo[1] - sp.gw[1])), (float)(Z - (sp.lo[2] - sp.gw[2])), 0.0f);
+    orig[k] = p;
+}
+
+// i-groups: per primary cell row, ceil(count/32) groups
+__global__ void row_group_count_kernel(const __grid_constant__ SortParams sp, const int *cell_start, int *row_ngroups) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrows = sp.nprim[1] * sp.nprim[2];
+    if (r >= nrows) return;
+    const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
+    const int rowbase = ((rz + sp.ghost[2]) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
+    const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
+    row_ngroups[r] = (b - a + 31) / 32;
+}
+
+__global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, const int *cell_start, const int *row_gstart, int2 *groups) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nrows = sp.nprim[1] * sp.nprim[2];
+    if (r >= nrows) return;
+    const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
+    const int rowbase = ((rz + sp.ghost[2]) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
+    const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
+    int g = row_gstart[r];
+    for (int s = a; s < b; s += 32) groups[g++] = make_int2(s, min(32, b - s));
+}
+
+// ---- exclusive scan (ints): 4096 elements per block, recursive over block sums ----
+constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+
+__global__ void scan_tile_kernel(const int *in, int *out, int n, int *tile_sums) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+    int v[kScanItems], sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        v[k] = (base + k < n) ? in[base + k] : 0;
+        sum += v[k];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = (lane < kScanThreads / 32) ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += t;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = w; // inclusive over warps
+    }
+    __syncthreads();
+    int excl = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        if (base + k < n) out[base + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == kScanThreads - 1 && tile_sums) tile_sums[blockIdx.x] = excl;
+}
+
+__global__ void scan_add_kernel(int *out, int n, const int *tile_offsets) {
+    const int off = tile_offsets[blockIdx.x];
+    for (int k = threadIdx.x; k < kScanTile; k += kScanThreads)
+        if (blockIdx.x * kScanTile + k < n) out[blockIdx.x * kScanTile + k] += off;
+}
+
+// out[0..n) = exclusive scan of in[0..n).  `tmp` needs >= 4*(n/kScanTile+8) ints.
+static cudaError_t exclusive_scan(const int *in, int *out, int n, int *tmp, cudaStream_t st, int *launches) {
+    // out[n] (the total) is written afterwards by scan_total_kernel
+    const int tiles = (n + kScanTile) / kScanTile;
+    scan_tile_kernel<<<tiles, kScanThreads, 0, st>>>(in, out, n, tmp);
+    (*launches)++;
+    if (tiles > 1) {
+        int *tile_off = tmp + tiles;
+        cudaError_t e = exclusive_scan(tmp, tile_off, tiles, tile_off + tiles + 1, st, launches);
+        if (e != cudaSuccess) return e;
+        scan_add_kernel<<<tiles, kScanThreads, 0, st>>>(out, n, tile_off);
+        (*launches)++;
+    }
+    return cudaGetLastError();
+}
+
+__global__ void scan_total_kernel(const int *in, int *out, int n) { // out[n] = out[n-1] + in[n-1]
+    if (threadIdx.x == 0 && blockIdx.x == 0) out[n] = n > 0 ? out[n - 1] + in[n - 1] : 0;
+}
+
+// ---- bounding box for open boundaries ----
+__global__ void minmax_kernel(int n, const double *x, const double *y, const double *z, double *partial) {
+    __shared__ double s[6][256];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const double v[3] = {x[p], y[p], z[p]};
+        for (int d = 0; d < 3; d++) {
+            lo[d] = fmin(lo[d], v[d]);
+            hi[d] = fmax(hi[d], v[d]);
+        }
+    }
+    for (int d = 0; d < 3; d++) {
+        s[d][threadIdx.x] = lo[d];
+        s[3 + d][threadIdx.x] = hi[d];
+    }
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off)
+            for (int d = 0; d < 3; d++) {
+                s[d][threadIdx.x] = fmin(s[d][threadIdx.x], s[d][threadIdx.x + off]);
+                s[3 + d][threadIdx.x] = fmax(s[3 + d][threadIdx.x], s[3 + d][threadIdx.x + off]);
+            }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        for (int d = 0; d < 6; d++) partial[blockIdx.x * 6 + d] = s[d][0];
+}
+
+// ---- epilogue kernels ----
+__global__ void combine_kernel(int64_t len, int split, const double *part, double *out) { // out[k] = sum_s part[s][k]
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= len) return;
+    double s = 0.0;
+    for (int t = 0; t < split; t++) s += part[(int64_t)t * len + k];
+    out[k] = s;
+}
+
+// deterministic: fixed strided partial sums, then a fixed tree
+__global__ void reduce_items_kernel(int items, const double *item_energy, const unsigned long long *item_pairs, double *scalars) {
+    __shared__ double se[1024];
+    __shared__ unsigned long long sp[1024];
+    double e = 0.0;
+    unsigned long long c = 0;
+    for (int k = threadIdx.x; k < items; k += 1024) {
+        e += item_energy[k];
+        c += item_pairs[k];
+    }
+    se[threadIdx.x] = e;
+    sp[threadIdx.x] = c;
+    __syncthreads();
+    for (int off = 512; off > 0; off >>= 1) {
+        if ((int)threadIdx.x < off) {
+            se[threadIdx.x] += se[threadIdx.x + off];
+            sp[threadIdx.x] += sp[threadIdx.x + off];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        scalars[0] = 0.5 * se[0]; // U = 1/2 sum_i sum_j u_ij
+        scalars[1] = (double)sp[0];
+    }
+}
+
+// ---- synthetic system of SURVEY.md 8d, generated on the device ----
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+    z ^= z >> 30;
+    z *= 0xBF58476D1CE4E5B9ULL;
+    z ^= z >> 27;
+    z *= 0x94D049BB133111EBULL;
+    z ^= z >> 31;
+    return z;
+}
+__device__ __forceinline__ unsigned long long draw64(unsigned long long seed, unsigned long long k) {
+    return mix64(seed + (k + 1ULL) * 0x9E3779B97F4A7C15ULL);
+}
+__device__ __forceinline__ double unit53(unsigned long long d) { return (double)(d >> 11) * (1.0 / 9007199254740992.0); }
+
+__global__ void lattice_kernel(int n, double a, unsigned long long seed, double *x, double *y, double *z, double *q,
+                               double *mx, double *my, double *mz) {
+    const long long N = (long long)n * n * n;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= N) return;
+    const long long k = p % n, j = (p / n) % n, i = p / ((long long)n * n);
+    const unsigned long long b = 7ULL * (unsigned long long)p;
+    const double ux = unit53(draw64(seed, b + 0)), uy = unit53(draw64(seed, b + 1)), uz = unit53(draw64(seed, b + 2));
+    // no FMA contraction: the oracle generator (g++ -ffp-contract=off) must produce the same bits
+    if (x) x[p] = __dmul_rn(__dadd_rn(__dadd_rn((double)i, 0.5), __dmul_rn(0.5, __dadd_rn(ux, -0.5))), a);
+    if (y) y[p] = __dmul_rn(__dadd_rn(__dadd_rn((double)j, 0.5), __dmul_rn(0.5, __dadd_rn(uy, -0.5))), a);
+    if (z) z[p] = __dmul_rn(__dadd_rn(__dadd_rn((double)k, 0.5), __dmul_rn(0.5, __dadd_rn(uz, -0.5))), a);
+    if (q) q[p] = (draw64(seed, b + 3) & 1ULL) ? 1.0 : -1.0;
+    const double m0 = unit53(draw64(seed, b + 4)) - 0.5, m1 = unit53(draw64(seed, b + 5)) - 0.5, m2 = unit53(draw64(seed, b + 6)) - 0.5;
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(m0, m0), __dmul_rn(m1, m1)), __dmul_rn(m2, m2)));
+    if (mx) mx[p] = __ddiv_rn(m0, nrm);
+    if (my) my[p] = __ddiv_rn(m1, nrm);
+    if (mz) mz[p] = __ddiv_rn(m2, nrm);
+}
+
+// ---- FP64 pipe peak probe: 8 independent DFMA chains per thread ----
+__global__ void dfma_probe_kernel(int iters, double a, double b, double *sink) {
+    double v0 = threadIdx.x * 1e-9, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; i++) {
+        v0 = fma(v0, a, b);
+        v1 = fma(v1, a, b);
+        v2 = fma(v2, a, b);
+        v3 = fma(v3, a, b);
+        v4 = fma(v4, a, b);
+        v5 = fma(v5, a, b);
+        v6 = fma(v6, a, b);
+        v7 = fma(v7, a, b);
+    }
+    const double s = v0 + v1 + v2 + v3 + v4 + v5 + v6 + v7;
+    if (s == 123.456) sink[0] = s; // never true; keeps the chain alive
+}
+
+} // namespace cgb
+
+// =================================================================================================================
+// handle
+// =================================================================================================================
+using namespace cgb;
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct cg_handle {
+    int device = 0;
+    cg_scheme_desc desc;
+    std::vector<double> host_table; // packed spline tables
+    DevBuf<double> d_table;
+    int table_doubles = 0;
+    int functor = -1;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int precision = CG_FP64;
+    int shard_rank = 0, shard_n = 1;
+    std::string err;
+    // system
+    int64_t n = 0;
+    bool have_system = false, pbc = false, inputs_on_device = false;
+    bool has_q = false, has_mu = false;
+    double box[3] = {0, 0, 0};
+    const double *in[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // device SoA (own or caller's)
+    DevBuf<double> own_in[7];
+    // sorted system
+    DevBuf<int> cell_count, cell_start, scan_tmp, row_ngroups, row_gstart, orig;
+    DevBuf<unsigned int> keys;
+    DevBuf<double4> pos, mu;
+    DevBuf<float4> pos32;
+    DevBuf<int2> groups;
+    DevBuf<double> minmax_partial;
+    // outputs
+    DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
+    DevBuf<unsigned long long> item_pairs;
+    int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups
+    double *h_minmax = nullptr;  // pinned
+    double *h_scalars = nullptr; // pinned
+    double ms[4] = {0, 0, 0, 0};
+    int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static thread_local std::string g_create_error;
+
+#define CG_CUDA(h, call)                                                                                            \
+    do {                                                                                                            \
+        cudaError_t e__ = (call);                                                                                   \
+        if (e__ != cudaSuccess) {                                                                                   \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                                         \
+            return (e__ == cudaErrorMemoryAllocation) ? CG_ERR_ALLOC : CG_ERR_CUDA;                                 \
+        }                                                                                                           \
+    } while (0)
+
+extern "C" {
+
+const char *cg_version(void) { return "coulombgalore_b200 0.1 (sm_100a)"; }
+
+int cg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+const char *cg_last_error(const cg_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
+    if (!scheme || !out) return CG_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        g_create_error = "no CUDA device: this library has no CPU fallback";
+        return CG_ERR_NO_DEVICE;
+    }
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) return CG_ERR_NO_DEVICE;
+    }
+    if (device >= ndev) return CG_ERR_INVALID;
+    const int fn = functor_for(*scheme);
+    if (fn < 0 || !(scheme->cutoff > 0.0)) {
+        g_create_error = "unknown functor or non-positive cutoff in descriptor";
+        return CG_ERR_INVALID;
+    }
+    cg_handle *h = new cg_handle();
+    h->device = device;
+    h->desc = *scheme;
+    h->functor = fn;
+    if (cudaSetDevice(device) != cudaSuccess) {
+        delete h;
+        return CG_ERR_NO_DEVICE;
+    }
+    if (scheme->functor == CG_SPLINE) {
+        for (int k = 0; k < 4; k++) {
+            const int n = scheme->spline_knots[k];
+            if (n < 2 || n > CG_SPLINE_MAX_KNOTS || !scheme->spline_r2[k] || !scheme->spline_c[k]) {
+                g_create_error = "spline tables missing or too large";
+                delete h;
+                return CG_ERR_INVALID;
+            }
+        }
+        cgd::SplineSrf f;
+        h->host_table.resize((size_t)cgd::SplineSrf::packed_size(*scheme));
+        f.pack_from(*scheme, h->host_table.data());
+        h->table_doubles = f.total;
+        // the handle owns its own copy of the tables: re-point the descriptor at it
+        for (int k = 0; k < 4; k++) {
+            h->desc.spline_r2[k] = h->host_table.data() + f.koff[k];
+            h->desc.spline_c[k] = h->host_table.data() + f.coff[k];
+        }
+        if (h->d_table.ensure(h->host_table.size()) != cudaSuccess ||
+            cudaMemcpy(h->d_table.p, h->host_table.data(), h->host_table.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+            g_create_error = "cannot upload spline tables";
+            delete h;
+            return CG_ERR_CUDA;
+        }
+    }
+    bool ok = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&h->h_counts, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&h->h_minmax, 6 * 64 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&h->h_scalars, 2 * sizeof(double)) == cudaSuccess;
+    if (!ok) {
+        g_create_error = std::string("CUDA resource creation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete h;
+        return CG_ERR_CUDA;
+    }
+    h->stream = h->own_stream;
+    *out = h;
+    return CG_OK;
+}
+
+int cg_destroy(cg_handle *h) {
+    if (!h) return CG_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &b : h->own_in) b.release();
+    h->d_table.release();
+    h->cell_count.release();
+    h->cell_start.release();
+    h->scan_tmp.release();
+    h->row_ngroups.release();
+    h->row_gstart.release();
+    h->orig.release();
+    h->keys.release();
+    h->pos.release();
+    h->mu.release();
+    h->pos32.release();
+    h->groups.release();
+    h->minmax_partial.release();
+    h->out_force.release();
+    h->out_field.release();
+    h->out_pot.release();
+    h->part_force.release();
+    h->part_field.release();
+    h->part_pot.release();
+    h->item_energy.release();
+    h->scalars.release();
+    h->item_pairs.release();
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_minmax) cudaFreeHost(h->h_minmax);
+    if (h->h_scalars) cudaFreeHost(h->h_scalars);
+    for (auto &e : h->ev)
+        if (e) cudaEventDestroy(e);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return CG_OK;
+}
+
+int cg_set_stream(cg_handle *h, void *cuda_stream) {
+    if (!h) return CG_ERR_INVALID;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return CG_OK;
+}
+
+int cg_set_precision(cg_handle *h, int precision) {
+    if (!h || (precision != CG_FP64 && precision != CG_FP32)) return CG_ERR_INVALID;
+    if (precision == CG_FP32) {
+        h->err = "fp32 pair arithmetic is not built into this library version";
+        return CG_ERR_UNSUPPORTED;
+    }
+    h->precision = precision;
+    return CG_OK;
+}
+
+int cg_set_shard(cg_handle *h, int rank, int nranks) {
+    if (!h || nranks < 1 || rank < 0 || rank >= nranks) return CG_ERR_INVALID;
+    h->shard_rank = rank;
+    h->shard_n = nranks;
+    return CG_OK;
+}
+
+static int set_system_common(cg_handle *h, int64_t n, const double *box, int pbc) {
+    if (n < 0 || n > 150000000LL) {
+        h->err = "particle count out of range";
+        return CG_ERR_INVALID;
+    }
+    h->pbc = pbc != 0;
+    if (h->pbc) {
+        if (!box) return CG_ERR_INVALID;
+        for (int d = 0; d < 3; d++) {
+            if (!(box[d] > 0.0)) return CG_ERR_INVALID;
+            if (!(box[d] >= h->desc.cutoff)) {
+                h->err = "periodic box shorter than the cut-off is not supported (needs more than the nearest images)";
+                return CG_ERR_UNSUPPORTED;
+            }
+            h->box[d] = box[d];
+        }
+    }
+    h->n = n;
+    h->have_system = true;
+    return CG_OK;
+}
+
+int cg_set_system(cg_handle *h, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                  const double *mux, const double *muy, const double *muz, const double *box, int pbc) {
+    if (!h || (n > 0 && (!x || !y || !z))) return CG_ERR_INVALID;
+    if ((mux || muy || muz) && !(mux && muy && muz)) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    int rc = set_system_common(h, n, box, pbc);
+    if (rc != CG_OK) return rc;
+    const double *src[7] = {x, y, z, q, mux, muy, muz};
+    for (int k = 0; k < 7; k++) {
+        h->in[k] = nullptr;
+        if (src[k] && n > 0) {
+            CG_CUDA(h, h->own_in[k].ensure((size_t)n));
+            CG_CUDA(h, cudaMemcpyAsync(h->own_in[k].p, src[k], (size_t)n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            h->in[k] = h->own_in[k].p;
+        }
+    }
+    h->inputs_on_device = false;
+    return CG_OK;
+}
+
+int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                         const double *mux, const double *muy, const double *muz, const double *box, int pbc) {
+    if (!h || (n > 0 && (!x || !y || !z))) return CG_ERR_INVALID;
+    if ((mux || muy || muz) && !(mux && muy && muz)) return CG_ERR_INVALID;
+    int rc = set_system_common(h, n, box, pbc);
+    if (rc != CG_OK) return rc;
+    const double *src[7] = {x, y, z, q, mux, muy, muz};
+    for (int k = 0; k < 7; k++) h->in[k] = src[k];
+    h->inputs_on_device = true;
+    return CG_OK;
+}
+
+// the evaluation proper; outputs are device pointers (may be null)
+static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars) {
+    if (!h->have_system) {
+        h->err = "cg_eval before cg_set_system";
+        return CG_ERR_STATE;
+    }
+    if (mode < 0 || mode > 2 || (what & ~15) || what == 0) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->stream;
+    int launches = 0, pair_launches = 0;
+    CG_CUDA(h, cudaEventRecord(h->ev[0], st));
+    if (!d_scalars) {
+        CG_CUDA(h, h->scalars.ensure(2));
+        d_scalars = h->scalars.p;
+    }
+    const int n = (int)h->n;
+    if (n == 0) {
+        CG_CUDA(h, cudaMemsetAsync(d_scalars, 0, 2 * sizeof(double), st));
+        for (int k = 1; k < 4; k++) CG_CUDA(h, cudaEventRecord(h->ev[k], st));
+        return CG_OK;
+    }
+    const cg_scheme_desc &D = h->desc;
+    const double rc = D.cutoff;
+
+    // ---- 0. cell grid ----
+    SortParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.n = n;
+    sp.x = h->in[0];
+    sp.y = h->in[1];
+    sp.z = h->in[2];
+    sp.q = h->in[3];
+    sp.mx = h->in[4];
+    sp.my = h->in[5];
+    sp.mz = h->in[6];
+    sp.pbc = h->pbc ? 1 : 0;
+    double ext[3];
+    if (h->pbc) {
+        for (int d = 0; d < 3; d++) {
+            sp.lo[d] = 0.0;
+            ext[d] = h->box[d];
+        }
+    } else {
+        const int nb = 64;
+        CG_CUDA(h, h->minmax_partial.ensure(6 * nb));
+        minmax_kernel<<<nb, 256, 0, st>>>(n, sp.x, sp.y, sp.z, h->minmax_partial.p);
+        launches++;
+        CG_CUDA(h, cudaMemcpyAsync(h->h_minmax, h->minmax_partial.p, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CG_CUDA(h, cudaStreamSynchronize(st));
+        for (int d = 0; d < 3; d++) {
+            double lo = 1e300, hi = -1e300;
+            for (int b = 0; b < nb; b++) {
+                lo = std::min(lo, h->h_minmax[b * 6 + d]);
+                hi = std::max(hi, h->h_minmax[b * 6 + 3 + d]);
+            }
+            sp.lo[d] = lo;
+            ext[d] = std::max(hi - lo, 1e-9 * std::max(1.0, std::fabs(hi)));
+            ext[d] *= (1.0 + 1e-12);
+        }
+    }
+    // target cell edge: half the cut-off, but not so small that cells are nearly empty or the grid explodes
+    static const double cell_div = [] {
+        const char *e = std::getenv("CG_CELL_DIV");
+        const double v = e ? std::atof(e) : 2.0;
+        return (v >= 0.5 && v <= 8.0) ? v : 2.0;
+    }();
+    const double vol = ext[0] * ext[1] * ext[2];
+    // (an unbounded cut-off, i.e. Plain, still gets cells of ~32 particles: they only provide the sorted order)
+    double cs0 = std::min(rc / cell_div, std::cbrt(32.0 * vol / (double)n));
+    cs0 = std::max(cs0, std::cbrt(2.0 * vol / (double)n)); // >= ~2 particles per cell on average
+    for (;;) {
+        double ncell = 1.0;
+        for (int d = 0; d < 3; d++) {
+            int np = (int)std::min(4096.0, std::max(1.0, std::floor(ext[d] / cs0)));
+            sp.nprim[d] = np;
+            const double cs = ext[d] / np;
+            sp.box[d] = ext[d];
+            sp.inv_cs[d] = 1.0 / cs;
+            sp.ghost[d] = h->pbc ? (int)std::ceil(rc / cs - 1e-9) : 0;
+            sp.gw[d] = sp.ghost[d] * cs;
+            sp.ntot[d] = np + 2 * sp.ghost[d];
+            ncell *= sp.ntot[d];
+        }
+        if (ncell <= 48e6) break;
+        cs0 *= 1.26;
+    }
+    const int ncell = sp.ntot[0] * sp.ntot[1] * sp.ntot[2];
+    const int nrows_prim = sp.nprim[1] * sp.nprim[2];
+
+    // ---- 1-3. histogram, scan, groups ----
+    CG_CUDA(h, h->cell_count.ensure((size_t)ncell + 1));
+    CG_CUDA(h, h->cell_start.ensure((size_t)ncell + 2));
+    CG_CUDA(h, h->scan_tmp.ensure(4 * ((size_t)std::max(ncell, nrows_prim) / kScanTile + 8) + 64));
+    CG_CUDA(h, h->row_ngroups.ensure((size_t)nrows_prim + 1));
+    CG_CUDA(h, h->row_gstart.ensure((size_t)nrows_prim + 2));
+    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
+    const int nb_p = (n + 255) / 256;
+    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, nullptr, nullptr);
+    launches++;
+    CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, &launches));
+    scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell);
+    launches++;
+    row_group_count_kernel<<<(nrows_prim + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
+    launches++;
+    CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, &launches));
+    scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim);
+    launches++;
+    CG_CUDA(h, cudaMemcpyAsync(&h->h_counts[0], h->cell_start.p + ncell, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(h, cudaMemcpyAsync(&h->h_counts[1], h->row_gstart.p + nrows_prim, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(h, cudaStreamSynchronize(st));
+    const int n_sorted = h->h_counts[0], n_groups = h->h_counts[1];
+
+    // ---- 4-5. scatter, deterministic order, gather ----
+    CG_CUDA(h, h->keys.ensure((size_t)n_sorted));
+    CG_CUDA(h, h->pos.ensure((size_t)n_sorted));
+    const bool need_mu = mode != CG_MODE_ION;
+    if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)n_sorted));
+    CG_CUDA(h, h->pos32.ensure((size_t)n_sorted));
+    CG_CUDA(h, h->orig.ensure((size_t)n_sorted));
+    CG_CUDA(h, h->groups.ensure((size_t)n_groups + 1));
+    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
+    bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, h->cell_start.p, h->keys.p);
+    cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ncell, h->cell_start.p, h->keys.p);
+    gather_kernel<<<(n_sorted + 255) / 256, 256, 0, st>>>(sp, n_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p, h->orig.p);
+    row_group_emit_kernel<<<(nrows_prim + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
+    launches += 4;
+    CG_CUDA(h, cudaGetLastError());
+    CG_CUDA(h, cudaEventRecord(h->ev[1], st));
+
+    // ---- 6. pair kernel ----
+    const int g0 = (int)((int64_t)n_groups * h->shard_rank / h->shard_n), g1 = (int)((int64_t)n_groups * (h->shard_rank + 1) / h->shard_n);
+    const int ng = g1 - g0;
+    int device_sms = 148;
+    cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, h->device);
+    static const int split_env = [] {
+        const char *e = std::getenv("CG_SPLIT");
+        return e ? std::atoi(e) : 0;
+    }();
+    int split = 1;
+    const int want_items = device_sms * 2 * kWarpsPerCta * 2; // two waves of two CTAs per SM
+    if (ng > 0 && ng < want_items) split = std::min(64, (want_items + ng - 1) / ng);
+    if (split_env > 0) split = std::min(64, split_env);
+    const int items = ng * split;
+
+    // smallest instantiated (mode, what) superset
+    int ci = -1;
+    for (int k = 0; k < kNumCombos; k++) {
+        const Combo c = combo(k);
+        if (c.mode != mode || (c.what & what) != what) continue;
+        if (ci < 0 || __builtin_popcount(c.what) < __builtin_popcount(combo(ci).what)) ci = k;
+    }
+    if (ci < 0) return CG_ERR_INVALID;
+    const int cwhat = combo(ci).what;
+
+    KParams kp;
+    std::memset(&kp, 0, sizeof(kp));
+    kp.pos = h->pos.p;
+    kp.mu = need_mu ? h->mu.p : nullptr;
+    kp.pos32 = h->pos32.p;
+    kp.orig = h->orig.p;
+    kp.cell_start = h->cell_start.p;
+    kp.groups = h->groups.p;
+    kp.group_begin = g0;
+    kp.group_end = g1;
+    kp.split = split;
+    kp.nx = sp.ntot[0];
+    kp.ny = sp.ntot[1];
+    kp.nz = sp.ntot[2];
+    kp.inv_cs_x = (float)sp.inv_cs[0];
+    kp.inv_cs_y = (float)sp.inv_cs[1];
+    kp.inv_cs_z = (float)sp.inv_cs[2];
+    kp.cs_x = (float)(1.0 / sp.inv_cs[0]);
+    kp.cs_y = (float)(1.0 / sp.inv_cs[1]);
+    kp.cs_z = (float)(1.0 / sp.inv_cs[2]);
+    {
+        // fp32 prefilter margin: both relative coordinates are rounded to fp32 (half an ulp of the largest relative
+        // coordinate each), the difference and the squared norm add a few more roundings of magnitude ~ rc
+        double span = 0.0;
+        for (int d = 0; d < 3; d++) span = std::max(span, sp.ntot[d] / sp.inv_cs[d]);
+        const double e = std::ldexp(span, -23) + std::ldexp(std::min(rc, span), -22);
+        const double m = 2.0 * 1.7320508 * e * 1.05;
+        double rcm = std::min(rc + m, 1e15) * (1.0 + 3e-7);
+        kp.rc_m = (float)rcm;
+        kp.rc2_m = (float)(rcm * rcm * (1.0 + 6e-7));
+        const int nmax = std::max(sp.ntot[0], std::max(sp.ntot[1], sp.ntot[2]));
+        kp.slack = (float)(1e-4 + 1e-6 * nmax);
+    }
+    kp.rc2 = D.cutoff_squared;
+    kp.core.inverse_cutoff = D.inverse_cutoff;
+    kp.core.cutoff_squared = D.cutoff_squared;
+    kp.core.kappa = D.inverse_debye_length;
+    kp.n = n;
+    CG_CUDA(h, h->item_energy.ensure((size_t)std::max(items, 1)));
+    CG_CUDA(h, h->item_pairs.ensure((size_t)std::max(items, 1)));
+    kp.item_energy = h->item_energy.p;
+    kp.item_pairs = h->item_pairs.p;
+    // outputs the instantiated combo writes; extra ones go nowhere (null)
+    double *o_force = (what & CG_FORCE) ? d_force : nullptr, *o_field = (what & CG_FIELD) ? d_field : nullptr,
+           *o_pot = (what & CG_POTENTIAL) ? d_pot : nullptr;
+    if (split > 1) {
+        // per-slice partial buffers; with a shard, particles of other ranks are never written: clear them first
+        const bool clear = h->shard_n > 1;
+        if (o_force) {
+            CG_CUDA(h, h->part_force.ensure((size_t)split * n * 3));
+            if (clear) CG_CUDA(h, cudaMemsetAsync(h->part_force.p, 0, (size_t)split * n * 3 * sizeof(double), st));
+            kp.force = h->part_force.p;
+        }
+        if (o_field) {
+            CG_CUDA(h, h->part_field.ensure((size_t)split * n * 3));
+            if (clear) CG_CUDA(h, cudaMemsetAsync(h->part_field.p, 0, (size_t)split * n * 3 * sizeof(double), st));
+            kp.field = h->part_field.p;
+        }
+        if (o_pot) {
+            CG_CUDA(h, h->part_pot.ensure((size_t)split * n));
+            if (clear) CG_CUDA(h, cudaMemsetAsync(h->part_pot.p, 0, (size_t)split * n * sizeof(double), st));
+            kp.potential = h->part_pot.p;
+        }
+    } else {
+        kp.force = o_force;
+        kp.field = o_field;
+        kp.potential = o_pot;
+    }
+    (void)cwhat;
+    const FunctorEntry *fe = functor_entry(h->functor);
+    if (!fe) return CG_ERR_INVALID;
+    if (items > 0) {
+        CG_CUDA(h, fe->pair[ci](kp, D, h->d_table.p, h->table_doubles, items, st));
+        pair_launches++;
+        launches++;
+    }
+    CG_CUDA(h, cudaEventRecord(h->ev[2], st));
+
+    // ---- 7-8. epilogue ----
+    if (split > 1 && items > 0) {
+        if (o_force) {
+            combine_kernel<<<(unsigned)(((int64_t)3 * n + 255) / 256), 256, 0, st>>>((int64_t)3 * n, split, h->part_force.p, o_force);
+            launches++;
+        }
+        if (o_field) {
+            combine_kernel<<<(unsigned)(((int64_t)3 * n + 255) / 256), 256, 0, st>>>((int64_t)3 * n, split, h->part_field.p, o_field);
+            launches++;
+        }
+        if (o_pot) {
+            combine_kernel<<<(unsigned)(((int64_t)n + 255) / 256), 256, 0, st>>>((int64_t)n, split, h->part_pot.p, o_pot);
+            launches++;
+        }
+    }
+    reduce_items_kernel<<<1, 1024, 0, st>>>(items, h->item_energy.p, h->item_pairs.p, d_scalars);
+    launches++;
+    CG_CUDA(h, cudaGetLastError());
+    CG_CUDA(h, cudaEventRecord(h->ev[3], st));
+    h->counters[0] = n_sorted;
+    h->counters[1] = ncell;
+    h->counters[2] = n_groups;
+    h->counters[3] = pair_launches;
+    h->counters[4] = launches;
+    h->counters[5] = split;
+    h->counters[6] = 0;
+    h->counters[7] = items;
+    return CG_OK;
+}
+
+int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *scalars) {
+    if (!h) return CG_ERR_INVALID;
+    return eval_device_impl(h, mode, what, force, field, potential, scalars);
+}
+
+int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
+    if (!h) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const size_t n = (size_t)h->n;
+    double *df = nullptr, *de = nullptr, *dp = nullptr;
+    if ((what & CG_FORCE) && force) {
+        CG_CUDA(h, h->out_force.ensure(3 * n + 1));
+        df = h->out_force.p;
+    }
+    if ((what & CG_FIELD) && field) {
+        CG_CUDA(h, h->out_field.ensure(3 * n + 1));
+        de = h->out_field.p;
+    }
+    if ((what & CG_POTENTIAL) && potential) {
+        CG_CUDA(h, h->out_pot.ensure(n + 1));
+        dp = h->out_pot.p;
+    }
+    CG_CUDA(h, h->scalars.ensure(2));
+    if (h->shard_n > 1) { // particles outside the shard are not written by the kernels
+        if (df) CG_CUDA(h, cudaMemsetAsync(df, 0, 3 * n * sizeof(double), h->stream));
+        if (de) CG_CUDA(h, cudaMemsetAsync(de, 0, 3 * n * sizeof(double), h->stream));
+        if (dp) CG_CUDA(h, cudaMemsetAsync(dp, 0, n * sizeof(double), h->stream));
+    }
+    // outputs without a destination stay null: the kernel computes but does not store them
+    const int rc = eval_device_impl(h, mode, what, df, de, dp, h->scalars.p);
+    if (rc != CG_OK) return rc;
+    cudaStream_t st = h->stream;
+    if (df) CG_CUDA(h, cudaMemcpyAsync(force, df, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (de) CG_CUDA(h, cudaMemcpyAsync(field, de, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (dp) CG_CUDA(h, cudaMemcpyAsync(potential, dp, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(h, cudaStreamSynchronize(st));
+    if (energy) *energy = h->h_scalars[0];
+    if (pairs) *pairs = (int64_t)(h->h_scalars[1] + 0.5);
+    return CG_OK;
+}
+
+int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out) {
+    if (!h || n < 0 || (n > 0 && (!q || !out))) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const FunctorEntry *fe = functor_entry(h->functor);
+    if (!fe) return CG_ERR_INVALID;
+    CG_CUDA(h, fe->srf(h->desc, h->d_table.p, h->table_doubles, n, q, out, h->stream));
+    return CG_OK;
+}
+
+int cg_last_timings(cg_handle *h, double ms[4]) {
+    if (!h || !ms) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CG_CUDA(h, cudaEventSynchronize(h->ev[3]));
+    float a = 0, b = 0, c = 0, d = 0;
+    CG_CUDA(h, cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    CG_CUDA(h, cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    CG_CUDA(h, cudaEventElapsedTime(&c, h->ev[2], h->ev[3]));
+    CG_CUDA(h, cudaEventElapsedTime(&d, h->ev[0], h->ev[3]));
+    ms[0] = a;
+    ms[1] = b;
+    ms[2] = c;
+    ms[3] = d;
+    return CG_OK;
+}
+
+int cg_last_counters(cg_handle *h, int64_t c[8]) {
+    if (!h || !c) return CG_ERR_INVALID;
+    for (int k = 0; k < 8; k++) c[k] = h->counters[k];
+    return CG_OK;
+}
+
+int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z, double *q,
+                               double *mux, double *muy, double *muz) {
+    if (!h || n <= 0) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    const long long N = (long long)n * n * n;
+    lattice_kernel<<<(unsigned)((N + 255) / 256), 256, 0, h->stream>>>(n, a, seed, x, y, z, q, mux, muy, muz);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+int cg_fp64_peak_probe(cg_handle *h, double *tflops, double *ms_out) {
+    if (!h || !tflops) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    CG_CUDA(h, h->scalars.ensure(2));
+    const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+    cudaStream_t st = h->stream;
+    dfma_probe_kernel<<<blocks, threads, 0, st>>>(1024, 0.999999, 1e-9, h->scalars.p); // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CG_CUDA(h, cudaEventRecord(h->ev[0], st));
+        dfma_probe_kernel<<<blocks, threads, 0, st>>>(iters, 0.999999, 1e-9, h->scalars.p);
+        CG_CUDA(h, cudaEventRecord(h->ev[1], st));
+        CG_CUDA(h, cudaEventSynchronize(h->ev[1]));
+        float ms = 0;
+        CG_CUDA(h, cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]));
+        best = std::min(best, ms);
+    }
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * (double)threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return CG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,91 @@
+// kparams.cuh -- parameter blocks shared by the host engine and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "coulombgalore/detail/pair.hpp"
+#include "coulombgalore/detail/srf.hpp"
+
+namespace cgb {
+
+namespace cgd = CoulombGalore::detail;
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kThreads = kWarpsPerCta * 32;
+constexpr int kQueueCap = 64; // per-lane deferred-pair queue depth (entries); flush is forced above kQueueCap-32
+
+// Spatially sorted system.  With periodic boundaries the arrays also hold the periodic images that lie within one
+// cut-off of the box ("ghost" entries, coordinates already shifted), so the pair kernel never applies a minimum
+// image: d = r_i - r_j on the stored coordinates.
+struct KParams {
+    const double4 *pos;   // x, y, z, charge            [n_sorted]
+    const double4 *mu;    // mu_x, mu_y, mu_z, 0        [n_sorted]  (may be null when no dipoles are needed)
+    const float4 *pos32;  // position relative to the grid origin in fp32, w unused   [n_sorted]
+    const int *orig;      // original particle index of a sorted entry               [n_sorted]
+    const int *cell_start; // first sorted entry of each cell, x fastest             [ncell + 1]
+    const int2 *groups;   // i-groups: (first sorted entry, count <= 32); a group never crosses a cell row
+    int group_begin, group_end; // shard of groups this launch evaluates
+    int split;            // j-split factor: work item = (group, s), s in [0, split)
+    int nx, ny, nz;       // cells per dimension (ghost layers included)
+    float inv_cs_x, inv_cs_y, inv_cs_z, cs_x, cs_y, cs_z;
+    float rc_m, rc2_m;    // cut-off plus fp32 rounding margin (conservative prefilter), and its square
+    float slack;          // slack in cell units for fp32 cell-range rounding
+    double rc2;           // exact gate: r2 < cutoff_squared (strict, reference core.hpp:354 etc.)
+    cgd::CoreParams core;
+    int n;                // number of (original) particles
+    // outputs, indexed by original particle index; with split > 1 they are [split][n] partial buffers
+    double *force, *field, *potential;
+    double *item_energy;              // [items] sum_j u_ij over the item's pairs (not yet halved)
+    unsigned long long *item_pairs;   // [items]
+};
+
+typedef cudaError_t (*pair_launch_fn)(const KParams &p, const cg_scheme_desc &desc, const double *dev_table,
+                                      int table_doubles, int items, cudaStream_t stream);
+typedef cudaError_t (*srf_launch_fn)(const cg_scheme_desc &desc, const double *dev_table, int table_doubles, int64_t n,
+                                     const double *q, double *out, cudaStream_t stream);
+
+// the (mode, what) combinations that are instantiated; a request maps to the smallest superset
+struct Combo {
+    int mode, what;
+};
+constexpr int kNumCombos = 8;
+__host__ __device__ constexpr Combo combo(int i) {
+    return i == 0   ? Combo{cgd::kModeIon, 2}
+           : i == 1 ? Combo{cgd::kModeIon, 3}
+           : i == 2 ? Combo{cgd::kModeIon, 15}
+           : i == 3 ? Combo{cgd::kModeDipole, 7}
+           : i == 4 ? Combo{cgd::kModeDipole, 15}
+           : i == 5 ? Combo{cgd::kModeMultipole, 3}
+           : i == 6 ? Combo{cgd::kModeMultipole, 15}
+                    : Combo{cgd::kModeIon, 1};
+}
+
+struct FunctorEntry {
+    pair_launch_fn pair[kNumCombos];
+    srf_launch_fn srf;
+};
+
+// one per functor family, defined in pair_inst_*.cu
+enum FunctorId {
+    kFnPlain = 0,
+    kFnPlainYukawa,
+    kFnReactionField,
+    kFnPoisson,
+    kFnPoissonYukawa,
+    kFnQPotential,  // run-time order
+    kFnQPotential3, // compile-time order 3 (BASELINE config 1)
+    kFnFanourgakis,
+    kFnWolf,
+    kFnFennell,
+    kFnZeroDipole,
+    kFnZahn,
+    kFnEwald,
+    kFnEwaldScreened,
+    kFnEwaldT,
+    kFnSpline,
+    kFnSplineYukawa,
+    kNumFunctors
+};
+const FunctorEntry *functor_entry(int id);
+
+} // namespace cgb

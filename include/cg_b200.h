@@ -1,0 +1,186 @@
+/*
+ * cg_b200.h -- C ABI of the B200 batched pair-interaction engine (libcg_b200.so).
+ *
+ * The reference (mlund/coulombgalore) is a header-only C++ library whose public surface is the scheme classes
+ * (reference include/coulombgalore/core.hpp:110-244 `SchemeBase`, :251-843 `EnergyImplementation<T>`); every call
+ * evaluates ONE pair on the CPU and the caller owns the loop over pairs.  This ABI is the boundary behind which
+ * that loop now runs on the GPU: plain pointers and sizes, int status codes, no C++ or torch types.
+ *
+ *   reference call (one pair)                                   batched replacement (all pairs within the cut-off)
+ *   ----------------------------------------------------------  ---------------------------------------------------
+ *   T::T(cutoff, ...)             e.g. wolf.hpp:44              cg_scheme_wolf(...) / include/coulombgalore/wolf.hpp
+ *   pot.ion_potential(z,r)        core.hpp:268                  cg_eval(mode=CG_MODE_ION,       what=CG_POTENTIAL)
+ *   pot.ion_field(z,r)            core.hpp:352                  cg_eval(mode=CG_MODE_ION,       what=CG_FIELD)
+ *   pot.ion_ion_energy(zA,zB,r)   core.hpp:501                  cg_eval(mode=CG_MODE_ION,       what=CG_ENERGY)
+ *   pot.ion_ion_force(zA,zB,r)    core.hpp:630                  cg_eval(mode=CG_MODE_ION,       what=CG_FORCE)
+ *   pot.dipole_potential(mu,r)    core.hpp:294                  cg_eval(mode=CG_MODE_DIPOLE,    what=CG_POTENTIAL)
+ *   pot.dipole_field(mu,r)        core.hpp:380                  cg_eval(mode=CG_MODE_DIPOLE,    what=CG_FIELD)
+ *   pot.dipole_dipole_energy      core.hpp:543                  cg_eval(mode=CG_MODE_DIPOLE,    what=CG_ENERGY)
+ *   pot.dipole_dipole_force       core.hpp:677                  cg_eval(mode=CG_MODE_DIPOLE,    what=CG_FORCE)
+ *   pot.multipole_field           core.hpp:457                  cg_eval(mode=CG_MODE_MULTIPOLE, what=CG_FIELD)
+ *   pot.multipole_multipole_energy core.hpp:581                 cg_eval(mode=CG_MODE_MULTIPOLE, what=CG_ENERGY)
+ *   pot.multipole_multipole_force core.hpp:737                  cg_eval(mode=CG_MODE_MULTIPOLE, what=CG_FORCE)
+ *   pot.short_range_function*(q)  core.hpp:181-184              cg_srf_device(...) (per-functor parity probe)
+ *
+ * Batched semantics (identical to oracle/harness.hpp): for every particle i, sum over j != i with
+ * |d| < cutoff, d = r_i - r_j (minimum image when pbc): potential/field use d; the ion force on i is
+ * ion_ion_force(z_j, z_i, d); the dipole force on i is dipole_dipole_force(mu_i, mu_j, -d); multipole energy and
+ * force are the reference functions called with A = i, B = j, r = r_j - r_i and zero quadrupoles; U = 1/2 sum u_ij.
+ *
+ * All entry points return CG_OK (0) or a negative cg_status; none throws.  A handle owns its device buffers and one
+ * CUDA stream; it is not safe to call one handle from two threads at once, separate handles are independent.
+ * There is NO CPU fallback: without a CUDA device cg_create returns CG_ERR_NO_DEVICE.
+ */
+#ifndef CG_B200_H
+#define CG_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cg_status {
+    CG_OK = 0,
+    CG_ERR_INVALID = -1,   /* bad argument / scheme parameters rejected (mirrors the reference ctor throws) */
+    CG_ERR_NO_DEVICE = -2, /* no CUDA device / driver */
+    CG_ERR_CUDA = -3,      /* a CUDA call failed; see cg_last_error */
+    CG_ERR_ALLOC = -4,
+    CG_ERR_UNSUPPORTED = -5, /* valid request outside what the kernels cover (e.g. pbc box shorter than cutoff) */
+    CG_ERR_STATE = -6        /* e.g. cg_eval before cg_set_system */
+} cg_status;
+
+/* same order as the reference's `enum class Scheme` (core.hpp:56-70) */
+typedef enum cg_scheme_id {
+    CG_PLAIN = 0,
+    CG_EWALD,
+    CG_EWALDT,
+    CG_REACTIONFIELD,
+    CG_WOLF,
+    CG_POISSON,
+    CG_QPOTENTIAL,
+    CG_FANOURGAKIS,
+    CG_ZERODIPOLE,
+    CG_ZAHN,
+    CG_FENNELL,
+    CG_QPOTENTIAL5,
+    CG_SPLINE
+} cg_scheme_id;
+
+#define CG_MAX_POISSON_C 12
+#define CG_SPLINE_MAX_KNOTS 64 /* per table; the reference default utol=1e-3 needs <= 9 */
+
+/*
+ * POD scheme descriptor: what SURVEY.md 8b calls the "scheme -> device parameter export".  The reference keeps
+ * these constants in private members (wolf.hpp:35, poisson.hpp:64-70, ewald.hpp:115-117, splined.hpp:323-325);
+ * the new header classes (the headers under include/coulombgalore/) expose them through `descriptor()`, and the cg_scheme_*
+ * functions below fill the same struct for C / ctypes callers.  Every constant is computed with the expression the
+ * reference constructor uses.
+ */
+typedef struct cg_scheme_desc {
+    int32_t functor;  /* cg_scheme_id of the S(q) functor that is evaluated (CG_SPLINE for tabulated schemes) */
+    int32_t scheme;   /* value of the reference's public `scheme` member (Splined copies the wrapped id) */
+    int32_t order;    /* qPotential: order */
+    int32_t C, D;     /* Poisson */
+    int32_t yukawa_map; /* Poisson: use_yukawa_screening (poisson.hpp:95-102) */
+    int32_t shifted;  /* ReactionField */
+    int32_t reserved0;
+    double cutoff, inverse_cutoff, cutoff_squared; /* core.hpp:116-117,151 */
+    double debye_length, inverse_debye_length;     /* core.hpp:118,152 (kappa of the core formulas) */
+    double eta, zeta;        /* erfc family: alpha*cutoff ; Ewald: cutoff/debye_length (0 when unscreened) */
+    double erfc_eta;         /* std::erfc(eta) */
+    double exp_eta2;         /* std::exp(-eta*eta) */
+    double F0;               /* EwaldTruncated scaling (ewald_truncated.hpp:59) */
+    double rf_a, rf_b;       /* ReactionField: (epsRF-epsr)/(2epsRF+epsr), 3epsRF/(2epsRF+epsr)*shifted */
+    double eps_rf, eps_r;    /* ReactionField constructor arguments (kept for the literal host evaluation) */
+    double reduced_kappa, yukawa_denom, binomCDC;  /* Poisson (poisson.hpp:92-107) */
+    double poisson_w[CG_MAX_POISSON_C];            /* binomial(D-1+c,c)*(C-c)/C, c = 0..C-1 */
+    double self_energy_prefactor[2], self_field_prefactor[2], T0, chi; /* O(N) terms, core.hpp:112-121 */
+    /* CG_SPLINE: four independent tables (S, S', S'', S'''), knots ascending in q, 6 coefficients per interval */
+    int32_t spline_knots[4];
+    const double *spline_r2[4];
+    const double *spline_c[4];
+} cg_scheme_desc;
+
+/* Constructors mirroring the reference constructors; they validate like the reference does. */
+int cg_scheme_plain(double debye_length, cg_scheme_desc *out);                                  /* plain.hpp:37 */
+int cg_scheme_reactionfield(double cutoff, double epsRF, double epsr, int shifted, cg_scheme_desc *out); /* reactionfield.hpp:47 */
+int cg_scheme_poisson(double cutoff, int C, int D, double debye_length, cg_scheme_desc *out);   /* poisson.hpp:79 */
+int cg_scheme_qpotential(double cutoff, int order, cg_scheme_desc *out);                        /* qpotential.hpp:253 */
+int cg_scheme_qpotential5(double cutoff, cg_scheme_desc *out);                                  /* qpotential.hpp:205, order 5 */
+int cg_scheme_fanourgakis(double cutoff, cg_scheme_desc *out);                                  /* fanourgakis.hpp:39 */
+int cg_scheme_fennell(double cutoff, double alpha, cg_scheme_desc *out);                        /* fennell.hpp:44 */
+int cg_scheme_zerodipole(double cutoff, double alpha, cg_scheme_desc *out);                     /* zerodipole.hpp:44 */
+int cg_scheme_zahn(double cutoff, double alpha, cg_scheme_desc *out);                           /* zahn.hpp:45 */
+int cg_scheme_wolf(double cutoff, double alpha, cg_scheme_desc *out);                           /* wolf.hpp:44 */
+int cg_scheme_ewald(double cutoff, double alpha, double eps_sur, double debye_length, cg_scheme_desc *out); /* ewald.hpp:129 */
+int cg_scheme_ewaldt(double cutoff, double alpha, double eps_sur, double debye_length, cg_scheme_desc *out); /* ewald_truncated.hpp:47 */
+/*
+ * Splined().spline<T>(...) (splined.hpp:340-367).  `inner` is the analytic scheme; the four tables are generated on
+ * the host with the reference's Andrea algorithm (utol<=0 -> 1e-3).  The tables live in `storage`, which the caller
+ * provides: at least cg_spline_storage_doubles() doubles, alive until cg_create has copied them.
+ */
+int64_t cg_spline_storage_doubles(void);
+int cg_scheme_splined(const cg_scheme_desc *inner, double utol, double *storage, cg_scheme_desc *out);
+/* Same, but with tables supplied by the caller (parity runs feed the oracle's tables to both sides) */
+int cg_scheme_splined_tables(const cg_scheme_desc *inner, const int32_t n_knots[4], const double *const r2[4],
+                             const double *const c[4], cg_scheme_desc *out);
+
+/* host evaluation of S..S''' from a descriptor (same code path as the header classes): out[k*n+i] */
+int cg_srf_host(const cg_scheme_desc *d, int64_t n, const double *q, double *out);
+
+typedef enum cg_mode { CG_MODE_ION = 0, CG_MODE_DIPOLE = 1, CG_MODE_MULTIPOLE = 2 } cg_mode;
+enum cg_what { CG_ENERGY = 1, CG_FORCE = 2, CG_FIELD = 4, CG_POTENTIAL = 8 };
+enum cg_precision { CG_FP64 = 0, CG_FP32 = 1 }; /* CG_FP32: fp32 pair arithmetic, fp64 positions/accumulators */
+
+typedef struct cg_handle cg_handle;
+
+int cg_device_count(void);
+/* device < 0 -> current device */
+int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out);
+int cg_destroy(cg_handle *h);
+const char *cg_last_error(const cg_handle *h); /* h may be NULL: last error of cg_create on this thread */
+const char *cg_version(void);
+
+/* run on a caller-owned CUDA stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL -> own stream */
+int cg_set_stream(cg_handle *h, void *cuda_stream);
+int cg_set_precision(cg_handle *h, int precision);
+/* evaluate only the i-particles of shard `rank` out of `nranks` (contiguous blocks of the spatially sorted order);
+ * every rank still needs all N particles as j.  Default 0 of 1. */
+int cg_set_shard(cg_handle *h, int rank, int nranks);
+
+/* Positions (and charges / dipoles, any of which may be NULL = all zero) as SoA buffers.
+ * box[3]: periodic box lengths when pbc != 0 (positions must lie in [0, box)); ignored when pbc == 0 (open). */
+int cg_set_system(cg_handle *h, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                  const double *mux, const double *muy, const double *muz, const double *box, int pbc);
+/* same with DEVICE pointers: zero-copy, the buffers must stay valid and unchanged until the next cg_eval returns */
+int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                         const double *mux, const double *muy, const double *muz, const double *box, int pbc);
+
+/* Evaluate.  HOST output buffers, any may be NULL: force[3n], field[3n] (AoS xyz per particle), potential[n],
+ * *energy (total U), *pairs (ordered in-cutoff pair count).  Blocks until the results are in the buffers. */
+int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy,
+            int64_t *pairs);
+/* Same with DEVICE output buffers; scalars[0] = U, scalars[1] = pair count (as double), on the device.
+ * Asynchronous on the handle's stream. */
+int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,
+                   double *scalars);
+
+/* per-functor probe: S..S''' evaluated by the device functor, q and out are DEVICE pointers, out[k*n+i] */
+int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out);
+
+/* timings of the last evaluation in milliseconds (CUDA events on the handle's stream):
+ * ms[0] binning+sort+reorder, ms[1] pair kernel(s), ms[2] reductions/epilogue, ms[3] whole step */
+int cg_last_timings(cg_handle *h, double ms[4]);
+/* counters of the last evaluation: [0] sorted entries incl. periodic images, [1] cells, [2] i-groups,
+ * [3] pair-kernel launches, [4] total kernel launches, [5] j-split factor, [6] candidate tests (if counted) */
+int cg_last_counters(cg_handle *h, int64_t c[8]);
+
+/* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
+int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,
+                               double *q, double *mux, double *muy, double *muz);
+/* FP64-pipe peak probe: a register-resident DFMA chain; returns measured TFLOP/s (2 flops per DFMA) */
+int cg_fp64_peak_probe(cg_handle *h, double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,169 @@
+// coulombgalore/detail/pair.hpp -- the pair-interaction formulas of reference core.hpp:268-779, restated once for
+// host and device on raw doubles.
+//
+// Every formula of the reference is of the form  (geometry) x (radial factor built from S..S''' and kappa r) x
+// exp(-kappa r).  `radial_terms` evaluates the radial factors once per pair:
+//     angcor = S (1 + kr) - q S'                                  (core.hpp:596, 754;  potential/field of an ion)
+//     unicor = (S kr - 2 q S') kr / 3 + q^2 S'' / 3               (core.hpp:597, 755)
+//     totcor = angcor + unicor                                    (the dipole "A" factor, core.hpp:393)
+//     r3corr = angcor kr^2 - 2 q S' (1+kr) kr + q^2 S'' (1+3kr) - q^3 S'''     (core.hpp:696-697, 757-758)
+// and the per-mode functions below combine them with the geometry exactly as the reference does, with the
+// divisions replaced by multiplications with 1/r (one rsqrt per pair).  YUK=false removes every kappa term at
+// compile time (kappa = 0 gives bit-identical values to evaluating them: exp(-0) = 1, kr = 0).
+#pragma once
+#include "hd.hpp"
+#include "specfun.hpp"
+
+namespace CoulombGalore {
+namespace detail {
+
+enum { kWhatEnergy = 1, kWhatForce = 2, kWhatField = 4, kWhatPotential = 8 };
+enum { kModeIon = 0, kModeDipole = 1, kModeMultipole = 2 };
+
+struct CoreParams {
+    double inverse_cutoff, cutoff_squared, kappa; // core.hpp:116-118
+};
+
+// highest S-derivative a (mode, what) combination needs
+constexpr int derivatives_needed(int mode, int what) {
+    return mode == kModeIon ? ((what & (kWhatForce | kWhatField)) ? 1 : 0)
+                            : ((what & kWhatForce) ? 3 : ((what & (kWhatField | kWhatEnergy)) ? 2 : 1));
+}
+
+struct Radial {
+    double rinv, r1, q, s0, ek, angcor, unicor, totcor, r3corr;
+};
+
+template <class F, bool YUK, int ND> CG_HD Radial radial_terms(const F &f, const CoreParams &cp, double r2, const double *tab) {
+    Radial R;
+    R.rinv = rsqrt_pos(r2);
+    R.r1 = r2 * R.rinv;
+    R.q = R.r1 * cp.inverse_cutoff;
+    double s[4] = {0.0, 0.0, 0.0, 0.0};
+    f.template eval<ND>(R.q, s, tab);
+    R.s0 = s[0];
+    const double qs1 = R.q * s[1];
+    const double q2s2 = (ND >= 2) ? (R.q * R.q) * s[2] : 0.0;
+    const double q3s3 = (ND >= 3) ? (R.q * R.q) * (R.q * s[3]) : 0.0;
+    if (YUK) {
+        const double kr = cp.kappa * R.r1;
+        R.ek = exp_any(-kr);
+        R.angcor = s[0] * (1.0 + kr) - qs1;
+        R.unicor = (s[0] * kr - 2.0 * qs1) * kr * (1.0 / 3.0) + q2s2 * (1.0 / 3.0);
+        R.totcor = R.angcor + R.unicor;
+        R.r3corr = R.angcor * kr * kr - qs1 * 2.0 * (1.0 + kr) * kr + q2s2 * (1.0 + 3.0 * kr) - q3s3;
+    } else {
+        R.ek = 1.0;
+        R.angcor = s[0] - qs1;
+        R.unicor = q2s2 * (1.0 / 3.0);
+        R.totcor = R.angcor + R.unicor;
+        R.r3corr = q2s2 - q3s3;
+    }
+    return R;
+}
+
+// per-particle accumulators; members that a (mode, what) instantiation never touches stay dead and cost nothing
+struct Accum {
+    double U = 0.0, Fx = 0.0, Fy = 0.0, Fz = 0.0, Ex = 0.0, Ey = 0.0, Ez = 0.0, phi = 0.0;
+};
+
+// One in-cutoff ordered pair (i <- j), d = r_i - r_j, r2 = |d|^2 < cutoff^2 already established by the caller.
+// Conventions: SURVEY.md 8b / oracle/harness.hpp.
+template <class F, bool YUK, int MODE, int WHAT>
+CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const D3 &d, double r2, double zi,
+                           double zj, const D3 &mui, const D3 &muj, Accum &acc) {
+    constexpr int ND = derivatives_needed(MODE, WHAT);
+    const Radial R = radial_terms<F, YUK, ND>(f, cp, r2, tab);
+    const double rinv2 = R.rinv * R.rinv;
+    const double rinv3 = rinv2 * R.rinv;
+    const double ek3 = R.ek * rinv3; // exp(-kr) / r^3
+
+    if (MODE == kModeIon) {
+        // ion_potential core.hpp:268-280, ion_field :352-365, ion_ion_energy :501, ion_ion_force :630
+        if (WHAT & (kWhatPotential | kWhatEnergy)) {
+            const double p = zj * R.rinv * R.s0 * R.ek;
+            if (WHAT & kWhatPotential) acc.phi += p;
+            if (WHAT & kWhatEnergy) acc.U += zi * p;
+        }
+        if (WHAT & (kWhatField | kWhatForce)) {
+            const double c = zj * ek3 * R.angcor;
+            if (WHAT & kWhatField) {
+                acc.Ex += c * d.x;
+                acc.Ey += c * d.y;
+                acc.Ez += c * d.z;
+            }
+            if (WHAT & kWhatForce) {
+                const double cf = zi * c;
+                acc.Fx += cf * d.x;
+                acc.Fy += cf * d.y;
+                acc.Fz += cf * d.z;
+            }
+        }
+        return;
+    }
+
+    const double mjd = dot(muj, d);
+    if (MODE == kModeDipole) {
+        // dipole_potential :294-307, dipole_field :380-399, dipole_dipole_energy :543-546, dipole_dipole_force :677-702
+        if (WHAT & kWhatPotential) acc.phi += mjd * ek3 * R.angcor;
+        if (WHAT & (kWhatField | kWhatEnergy)) {
+            const double cd = 3.0 * mjd * rinv2 * R.totcor * ek3; // coefficient of d
+            const double cm = -R.angcor * ek3;                    // coefficient of mu_j  (B - A = -angcor)
+            const double ex = cd * d.x + cm * muj.x, ey = cd * d.y + cm * muj.y, ez = cd * d.z + cm * muj.z;
+            if (WHAT & kWhatField) {
+                acc.Ex += ex;
+                acc.Ey += ey;
+                acc.Ez += ez;
+            }
+            if (WHAT & kWhatEnergy) acc.U -= mui.x * ex + mui.y * ey + mui.z * ez;
+        }
+        if (WHAT & kWhatForce) {
+            const double mid = dot(mui, d), mm = dot(mui, muj);
+            const double ab = mid * mjd * rinv2;
+            const double t3 = 3.0 * R.totcor;
+            const double e5 = ek3 * rinv2; // exp(-kr)/r^5
+            const double cd = -(t3 * (5.0 * ab - mm) + ab * R.r3corr) * e5;
+            const double ci = t3 * mjd * e5, cj = t3 * mid * e5;
+            acc.Fx += cd * d.x + ci * mui.x + cj * muj.x;
+            acc.Fy += cd * d.y + ci * mui.y + cj * muj.y;
+            acc.Fz += cd * d.z + ci * mui.z + cj * muj.z;
+        }
+        return;
+    }
+
+    // MODE == kModeMultipole: potential = ion_potential + dipole_potential, field = multipole_field :457-486 (quad = 0),
+    // energy = multipole_multipole_energy :581-615, force = multipole_multipole_force :737-779, both with A = i,
+    // B = j, r = r_j - r_i = -d and zero quadrupoles.
+    if (WHAT & kWhatPotential) acc.phi += zj * R.rinv * R.s0 * R.ek + mjd * ek3 * R.angcor;
+    if (WHAT & kWhatField) {
+        const double cd = (zj * R.angcor + 3.0 * mjd * rinv2 * R.totcor) * ek3;
+        const double cm = -R.angcor * ek3;
+        acc.Ex += cd * d.x + cm * muj.x;
+        acc.Ey += cd * d.y + cm * muj.y;
+        acc.Ez += cd * d.z + cm * muj.z;
+    }
+    if (WHAT & (kWhatEnergy | kWhatForce)) {
+        const double mid = dot(mui, d), mm = dot(mui, muj);
+        const double ab = mid * mjd * rinv2;
+        if (WHAT & kWhatEnergy) {
+            const double ion_ion = zi * zj * R.s0 * r2;
+            const double ion_dipole = (zi * mjd - zj * mid) * R.angcor;
+            const double dipole_dipole = -(3.0 * ab - mm) * R.totcor - mm * R.unicor;
+            acc.U += (ion_ion + ion_dipole + dipole_dipole) * ek3;
+        }
+        if (WHAT & kWhatForce) {
+            const double t3 = 3.0 * R.totcor;
+            const double e4 = R.ek * rinv2 * rinv2; // exp(-kr)/r^4
+            const double ar = R.angcor * R.r1;
+            const double cd = (-zi * zj * ar + R.rinv * (t3 * (zi * mjd + zj * mid) - t3 * (5.0 * ab - mm) - ab * R.r3corr)) * e4;
+            const double ci = (-zj * ar + t3 * mjd * R.rinv) * e4;
+            const double cj = (-zi * ar + t3 * mid * R.rinv) * e4;
+            acc.Fx += cd * d.x + ci * mui.x + cj * muj.x;
+            acc.Fy += cd * d.y + ci * mui.y + cj * muj.y;
+            acc.Fz += cd * d.z + ci * mui.z + cj * muj.z;
+        }
+    }
+}
+
+} // namespace detail
+} // namespace CoulombGalore

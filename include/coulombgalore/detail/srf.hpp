@@ -1,0 +1,315 @@
+// coulombgalore/detail/srf.hpp -- short-range-function functors S(q), S'(q), S''(q), S'''(q), q = r/R_c.
+//
+// One POD functor per truncation scheme, constructed from a cg_scheme_desc and usable on the host (scheme classes)
+// and inside the sm_100a pair kernels (passed by value as a __grid_constant__ kernel parameter, so every member is
+// a constant-bank operand).  `eval<ND>(q, s, tab)` fills s[0..ND]; sub-expressions shared between the derivatives
+// (exp(-eta^2 q^2), erfc, powers of q) are evaluated once, where the reference re-evaluates them in each of its
+// four virtual functions.  Constants that depend only on the scheme parameters are hoisted into the descriptor
+// with the same libm calls and arguments the reference uses, so hoisting changes no value.
+//
+// Reference formulas: plain.hpp:47-50, reactionfield.hpp:60-73, poisson.hpp:119-220, qpotential.hpp:50-192,
+// fanourgakis.hpp:49-61, wolf.hpp:60-71, fennell.hpp:59-73, zerodipole.hpp:61-80, zahn.hpp:60-76,
+// ewald.hpp:175-195, ewald_truncated.hpp:71-82, splined.hpp:167-176.
+#pragma once
+#include "../../cg_b200.h"
+#include "hd.hpp"
+#include "specfun.hpp"
+
+namespace CoulombGalore {
+namespace detail {
+
+// 2/sqrt(pi); the reference forms it as 2/(2*sqrt(atan(1))) (e.g. wolf.hpp:36), equal to within one ulp
+constexpr double kTwoOverSqrtPi = 1.1283791670955125739;
+
+// ---------------------------------------------------------------------------------------------------------------
+struct PlainSrf { // plain.hpp:47-50
+    static constexpr bool kHasTable = false;
+    CG_HD PlainSrf() {}
+    CG_HD explicit PlainSrf(const cg_scheme_desc &) {}
+    template <int ND> CG_HD void eval(double, double *s, const double * = nullptr) const {
+        s[0] = 1.0;
+        if (ND >= 1) s[1] = 0.0;
+        if (ND >= 2) s[2] = 0.0;
+        if (ND >= 3) s[3] = 0.0;
+    }
+};
+
+struct ReactionFieldSrf { // reactionfield.hpp:60-73: S = 1 + a q^3 - b q
+    static constexpr bool kHasTable = false;
+    double a, b;
+    CG_HD ReactionFieldSrf() : a(0), b(0) {}
+    CG_HD explicit ReactionFieldSrf(const cg_scheme_desc &d) : a(d.rf_a), b(d.rf_b) {}
+    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+        const double aq = a * q, aq2 = aq * q;
+        s[0] = 1.0 + (aq2 - b) * q;
+        if (ND >= 1) s[1] = 3.0 * aq2 - b;
+        if (ND >= 2) s[2] = 6.0 * aq;
+        if (ND >= 3) s[3] = 6.0 * a;
+    }
+};
+
+struct FanourgakisSrf { // fanourgakis.hpp:49-61
+    static constexpr bool kHasTable = false;
+    CG_HD FanourgakisSrf() {}
+    CG_HD explicit FanourgakisSrf(const cg_scheme_desc &) {}
+    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+        const double q2 = q * q, a = 1.0 - q, a2 = a * a;
+        s[0] = (a2 * a2) * (1.0 + q * (2.25 + q * (3.0 + 2.5 * q)));
+        if (ND >= 1) s[1] = -1.75 + (q2 * q2) * (26.25 + q * (-42.0 + 17.5 * q));
+        if (ND >= 2) s[2] = 105.0 * (q2 * q) * a2;
+        if (ND >= 3) s[3] = 525.0 * q2 * (q - 0.6) * (q - 1.0);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// qPotential: S = prod_{n=1}^{P} (1 - q^n) = (1-q)^P prod_{n=2}^{P} g_n,  g_n = sum_{k<n} q^k  (qpotential.hpp:50-61).
+// The factored form is kept (all g_n are positive, no cancellation as q -> 1); derivatives by Leibniz' rule over
+// the factors with the recurrence g_n = 1 + q g_{n-1}, O(P) work instead of the reference's O(P^2) powi loops.
+// ORDER > 0: compile-time order (fully unrolled); ORDER == 0: run-time order.
+template <int ND> CG_HD void jet_mul(double *c, const double *g) { // c <- c * g as Taylor jets up to order ND
+    if (ND >= 3) c[3] = c[3] * g[0] + 3.0 * (c[2] * g[1] + c[1] * g[2]) + c[0] * g[3];
+    if (ND >= 2) c[2] = c[2] * g[0] + 2.0 * c[1] * g[1] + c[0] * g[2];
+    if (ND >= 1) c[1] = c[1] * g[0] + c[0] * g[1];
+    c[0] = c[0] * g[0];
+}
+
+template <int ORDER> struct QPotentialSrf {
+    static constexpr bool kHasTable = false;
+    int order;
+    CG_HD QPotentialSrf() : order(ORDER) {}
+    CG_HD explicit QPotentialSrf(const cg_scheme_desc &d) : order(d.order) {}
+    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+        const int P = ORDER > 0 ? ORDER : order;
+        double g[4] = {1.0, 0.0, 0.0, 0.0}; // jet of g_1
+        double c[4] = {1.0, 0.0, 0.0, 0.0}; // jet of prod g_n
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+        for (int n = 2; n <= P; n++) {
+            if (ND >= 3) g[3] = 3.0 * g[2] + q * g[3];
+            if (ND >= 2) g[2] = 2.0 * g[1] + q * g[2];
+            if (ND >= 1) g[1] = g[0] + q * g[1];
+            g[0] = 1.0 + q * g[0];
+            jet_mul<ND>(c, g);
+        }
+        // jet of (1-q)^P
+        const double a = 1.0 - q;
+        double d[4];
+        double ap = (P > 3) ? powi(a, P - 3) : 1.0; // a^(max(P-3,0))
+        d[3] = (P >= 3) ? -(double)(P * (P - 1) * (P - 2)) * ap : 0.0;
+        if (P >= 3) ap *= a;
+        d[2] = (P >= 2) ? (double)(P * (P - 1)) * ap : 0.0;
+        if (P >= 2) ap *= a;
+        d[1] = (P >= 1) ? -(double)P * ap : 0.0;
+        if (P >= 1) ap *= a;
+        d[0] = ap;
+        jet_mul<ND>(c, d);
+        s[0] = c[0];
+        if (ND >= 1) s[1] = c[1];
+        if (ND >= 2) s[2] = c[2];
+        if (ND >= 3) s[3] = c[3];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// erfc family.  x = eta q, E = exp(-x^2), k1 = 2 eta / sqrt(pi); c = erfc(eta), e = exp(-eta^2), c2 = c + k1 e.
+enum ErfcKind { kWolf, kFennell, kZeroDipole, kZahn, kEwaldT, kEwaldPlain };
+
+template <int KIND> struct ErfcFamilySrf {
+    static constexpr bool kHasTable = false;
+    double eta, eta2, k1, c, e, c2, invF0;
+    CG_HD ErfcFamilySrf() : eta(0), eta2(0), k1(0), c(0), e(0), c2(0), invF0(1) {}
+    CG_HD explicit ErfcFamilySrf(const cg_scheme_desc &d)
+        : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), c(d.erfc_eta), e(d.exp_eta2),
+          c2(d.erfc_eta + d.eta * kTwoOverSqrtPi * d.exp_eta2), invF0(KIND == kEwaldT ? 1.0 / d.F0 : 1.0) {}
+    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+        const double x = eta * q;
+        double E, ec;
+        erfc_and_gauss(x, ec, E); // ec = erfc(x), E = exp(-x^2)
+        const double k1E = k1 * E;
+        const double g2 = 2.0 * eta2 * q * k1E;                    // 4 eta^3 q E / sqrt(pi)
+        const double g3 = 2.0 * eta2 * k1E * (1.0 - 2.0 * x * x);  // 4 eta^3 (1 - 2 x^2) E / sqrt(pi)
+        if (KIND == kWolf) { // wolf.hpp:60-71
+            s[0] = ec - q * c;
+            if (ND >= 1) s[1] = -k1E - c;
+            if (ND >= 2) s[2] = g2;
+            if (ND >= 3) s[3] = g3;
+        } else if (KIND == kFennell) { // fennell.hpp:59-73
+            s[0] = ec - q * c + (q - 1.0) * q * c2;
+            if (ND >= 1) s[1] = -k1E + 2.0 * q * c2 - (c2 + c);
+            if (ND >= 2) s[2] = g2 + 2.0 * c2;
+            if (ND >= 3) s[3] = g3;
+        } else if (KIND == kZeroDipole) { // zerodipole.hpp:61-80
+            const double q2 = q * q;
+            s[0] = ec - q * c + 0.5 * (q2 - 1.0) * q * c2;
+            if (ND >= 1) s[1] = -k1E + 1.5 * q2 * c2 - (0.5 * c2 + c);
+            if (ND >= 2) s[2] = g2 + 3.0 * q * c2;
+            if (ND >= 3) s[3] = g3 + 3.0 * c2;
+        } else if (KIND == kZahn) { // zahn.hpp:60-76
+            s[0] = ec - (q - 1.0) * q * c2;
+            if (ND >= 1) s[1] = -k1E - (2.0 * q - 1.0) * c2;
+            if (ND >= 2) s[2] = g2 - 2.0 * c2;
+            if (ND >= 3) s[3] = g3;
+        } else if (KIND == kEwaldT) { // ewald_truncated.hpp:71-82
+            s[0] = (ec - c - (1.0 - q) * k1 * e) * invF0;
+            if (ND >= 1) s[1] = -(k1E - k1 * e) * invF0;
+            if (ND >= 2) s[2] = g2 * invF0;
+            if (ND >= 3) s[3] = g3 * invF0;
+        } else { // Ewald without screening, ewald.hpp:175-195 with zeta = 0
+            s[0] = ec;
+            if (ND >= 1) s[1] = -k1E;
+            if (ND >= 2) s[2] = g2;
+            if (ND >= 3) s[3] = g3;
+        }
+    }
+};
+
+// Ewald with Debye screening (zeta = R_c / lambda_D > 0), ewald.hpp:175-195.
+//   S = 1/2 [ erfc(x+) e^{2 zeta q} + erfc(x-) ],  x+- = eta q +- zeta/(2 eta)
+// Because x+^2 - x-^2 = 2 zeta q, erfc(x+) e^{2 zeta q} = erfcx(x+) exp(-x-^2): one Gaussian serves both terms and
+// the product never overflows.
+struct EwaldScreenedSrf {
+    static constexpr bool kHasTable = false;
+    double eta, eta2, k1, zeta, zeta2, zeta3, half_z_over_eta, z_over_eta, z2_over_eta2;
+    CG_HD EwaldScreenedSrf() : eta(0), eta2(0), k1(0), zeta(0), zeta2(0), zeta3(0), half_z_over_eta(0), z_over_eta(0), z2_over_eta2(0) {}
+    CG_HD explicit EwaldScreenedSrf(const cg_scheme_desc &d)
+        : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), zeta(d.zeta), zeta2(d.zeta * d.zeta),
+          zeta3(d.zeta * d.zeta * d.zeta), half_z_over_eta(d.zeta / (2.0 * d.eta)), z_over_eta(d.zeta / d.eta),
+          z2_over_eta2((d.zeta * d.zeta) / (d.eta * d.eta)) {}
+    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+        const double xq = eta * q;
+        const double xm = xq - half_z_over_eta, xp = xq + half_z_over_eta;
+        double ecm, Em; // erfc(x-), exp(-x-^2)
+        erfc_and_gauss(xm, ecm, Em);
+        const double P = erfc_times_exp(xp, 2.0 * zeta * q, Em); // erfc(x+) exp(2 zeta q)
+        s[0] = 0.5 * (P + ecm);
+        if (ND >= 1) s[1] = -k1 * Em + zeta * P;
+        if (ND >= 2) s[2] = 2.0 * k1 * eta * (xq - z_over_eta) * Em + 2.0 * zeta2 * P;
+        if (ND >= 3) s[3] = 2.0 * k1 * eta2 * (1.0 - 2.0 * (xq - z_over_eta) * xm - z2_over_eta2) * Em + 4.0 * zeta3 * P;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Poisson (poisson.hpp:119-220), run-time C and D.  q~ = q, or (1 - e^{2 kappa* q}) * yukawa_denom when screened.
+struct PoissonSrf {
+    static constexpr bool kHasTable = false;
+    int C, D, yukawa;
+    double rk, denom, binomCDC;
+    double w[CG_MAX_POISSON_C];
+    CG_HD PoissonSrf() : C(1), D(-1), yukawa(0), rk(0), denom(0), binomCDC(0) {}
+    CG_HD explicit PoissonSrf(const cg_scheme_desc &d)
+        : C(d.C), D(d.D), yukawa(d.yukawa_map), rk(d.reduced_kappa), denom(d.yukawa_denom), binomCDC(d.binomCDC) {
+        for (int i = 0; i < CG_MAX_POISSON_C; i++) w[i] = d.poisson_w[i];
+    }
+    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+        if (D == -C) { // poisson.hpp:120-122 etc.
+            s[0] = 1.0;
+            if (ND >= 1) s[1] = 0.0;
+            if (ND >= 2) s[2] = 0.0;
+            if (ND >= 3) s[3] = 0.0;
+            return;
+        }
+        double qp = q, d1 = 1.0, d2 = 0.0, d3 = 0.0;
+        if (yukawa) { // :126, :147-149, :174-176, :204-207
+            const double ex = exp_any(2.0 * rk * q);
+            qp = (1.0 - ex) * denom;
+            d1 = -2.0 * rk * ex * denom;
+            d2 = 2.0 * rk * d1;
+            d3 = 2.0 * rk * d2;
+        }
+        if (D == 0 && C == 1) { // :128-130, :141-143: the derivatives are returned as zero
+            s[0] = 1.0 - qp;
+            if (ND >= 1) s[1] = 0.0;
+            if (ND >= 2) s[2] = 0.0;
+            if (ND >= 3) s[3] = 0.0;
+            return;
+        }
+        // tmp1 = sum_c w_c qp^c, tmp2 = d tmp1 / d qp  (Horner)
+        double t1 = 0.0, t2 = 0.0;
+        for (int c = C - 1; c >= 0; c--) {
+            t2 = t2 * qp + t1;
+            t1 = t1 * qp + w[c];
+        }
+        const double a = 1.0 - qp;
+        const double aD = powi(a, D);
+        s[0] = aD * a * t1;
+        if (ND >= 1) {
+            const double dS = -(double)(D + 1) * aD * t1 + aD * a * t2;
+            s[1] = dS * d1;
+            if (ND >= 2) {
+                const double d2S = binomCDC * powi(a, D - 1) * powi(qp, C - 1);
+                // the reference adds the chain-rule terms only inside `if (use_yukawa_screening)`; d2 = d3 = 0 otherwise
+                s[2] = d2S * d1 * d1 + dS * d2;
+                if (ND >= 3) {
+                    const double d3S = binomCDC * powi(a, D - 2) * powi(qp, C - 2) * ((2.0 - (double)(C + D)) * qp + (double)C - 1.0);
+                    s[3] = d3S * d1 * d1 * d1 + 3.0 * d2S * d1 * d2 + dS * d3;
+                }
+            }
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Splined (splined.hpp:321-386): four independent Andrea tables; eval = lower_bound over the knots, then a quintic
+// Horner in dz = q - knot (splined.hpp:167-176).  Packed layout in `tab` (global memory on the device, staged to
+// shared memory by the kernels; a host pointer for the scheme classes):
+//   for k in 0..3:  knots[k][0..n_k)  at tab + koff[k],   coefficients[k][6*(n_k-1)]  at tab + coff[k]
+struct SplineSrf {
+    static constexpr bool kHasTable = true;
+    int n[4], koff[4], coff[4], total;
+    const double *tab;
+    CG_HD SplineSrf() : total(0), tab(nullptr) {
+        for (int k = 0; k < 4; k++) n[k] = koff[k] = coff[k] = 0;
+    }
+    // layout only (tab is attached afterwards: the device copy for kernels, pack_from() on the host)
+    inline explicit SplineSrf(const cg_scheme_desc &d) : total(0), tab(nullptr) {
+        int t = 0;
+        for (int k = 0; k < 4; k++) {
+            n[k] = d.spline_knots[k];
+            koff[k] = t;
+            t += n[k];
+            coff[k] = t;
+            t += 6 * (n[k] - 1);
+        }
+        total = t;
+    }
+    // number of doubles of the packed table
+    static inline int packed_size(const cg_scheme_desc &d) {
+        int t = 0;
+        for (int k = 0; k < 4; k++) t += d.spline_knots[k] + 6 * (d.spline_knots[k] - 1);
+        return t;
+    }
+    // host-side packing; `dst` must hold packed_size(d) doubles
+    inline void pack_from(const cg_scheme_desc &d, double *dst) {
+        int t = 0;
+        for (int k = 0; k < 4; k++) {
+            n[k] = d.spline_knots[k];
+            koff[k] = t;
+            for (int i = 0; i < n[k]; i++) dst[t++] = d.spline_r2[k][i];
+            coff[k] = t;
+            for (int i = 0; i < 6 * (n[k] - 1); i++) dst[t++] = d.spline_c[k][i];
+        }
+        total = t;
+        tab = dst;
+    }
+    CG_HD double table(int k, double q, const double *t) const {
+        const double *kn = t + koff[k];
+        // std::lower_bound(...) - begin - 1  ==  (#knots strictly below q) - 1; q on an interior knot -> lower interval
+        int pos = -1;
+        for (int i = 0; i < n[k]; i++) pos += (kn[i] < q) ? 1 : 0;
+        pos = pos < 0 ? 0 : (pos > n[k] - 2 ? n[k] - 2 : pos); // q == 0 asserts in the reference; clamp instead
+        const double dz = q - kn[pos];
+        const double *c = t + coff[k] + 6 * pos;
+        return c[0] + dz * (c[1] + dz * (c[2] + dz * (c[3] + dz * (c[4] + dz * (c[5])))));
+    }
+    template <int ND> CG_HD void eval(double q, double *s, const double *t = nullptr) const {
+        const double *p = t ? t : tab;
+        s[0] = table(0, q, p);
+        if (ND >= 1) s[1] = table(1, q, p);
+        if (ND >= 2) s[2] = table(2, q, p);
+        if (ND >= 3) s[3] = table(3, q, p);
+    }
+};
+
+} // namespace detail
+} // namespace CoulombGalore

@@ -1,0 +1,83 @@
+"""Parity helpers shared by the GPU tests, smoke() and bench.py: scheme zoo, tolerance norms.
+
+fp64 bar: per-particle vectors  |delta|_2 <= TOL * max(|ref|_2, sum_j |term_ij|_2);  scalars |delta| <= TOL * sum |terms|;
+whole arrays |delta|_F / |ref|_F <= TOL;  in-cutoff ordered pair counts identical.  TOL = 1e-12 (BASELINE.json north_star).
+"""
+import numpy as np
+
+import coulombgalore_b200 as cg
+from oracle import oracle as O
+
+TOL = 1e-12
+INF = float("inf")
+
+
+def zoo():
+    """name -> (product scheme factory, oracle params): every scheme of the reference, incl. the core-Yukawa variants."""
+    return {
+        "plain": (lambda: cg.Plain(), O.params(O.PLAIN)),
+        "plain_yukawa": (lambda: cg.Plain(23.0), O.params(O.PLAIN, debye_length=23.0)),
+        "reactionfield": (lambda: cg.ReactionField(12, 80, 1, False), O.params(O.REACTIONFIELD, cutoff=12, eps_rf=80, eps_r=1, shifted=False)),
+        "reactionfield_shifted": (lambda: cg.ReactionField(12, 80, 1, True), O.params(O.REACTIONFIELD, cutoff=12, eps_rf=80, eps_r=1, shifted=True)),
+        "poisson43": (lambda: cg.Poisson(12, 4, 3), O.params(O.POISSON, cutoff=12, C_=4, D=3)),
+        "poisson33_yukawa": (lambda: cg.Poisson(12, 3, 3, 30.0), O.params(O.POISSON, cutoff=12, C_=3, D=3, debye_length=30.0)),
+        "poisson10": (lambda: cg.Poisson(12, 1, 0), O.params(O.POISSON, cutoff=12, C_=1, D=0)),
+        "poisson1m1": (lambda: cg.Poisson(12, 1, -1), O.params(O.POISSON, cutoff=12, C_=1, D=-1)),
+        "qpotential3": (lambda: cg.qPotential(14, 3), O.params(O.QPOTENTIAL, cutoff=14, order=3)),
+        "qpotential4": (lambda: cg.qPotential(12, 4), O.params(O.QPOTENTIAL, cutoff=12, order=4)),
+        "qpotential5_fixed": (lambda: cg.qPotentialFixedOrder5(12), O.params(O.QPOTENTIAL5, cutoff=12)),
+        "fanourgakis": (lambda: cg.Fanourgakis(12), O.params(O.FANOURGAKIS, cutoff=12)),
+        "wolf": (lambda: cg.Wolf(12, 0.25), O.params(O.WOLF, cutoff=12, alpha=0.25)),
+        "fennell": (lambda: cg.Fennell(12, 0.25), O.params(O.FENNELL, cutoff=12, alpha=0.25)),
+        "zerodipole": (lambda: cg.ZeroDipole(12, 0.25), O.params(O.ZERODIPOLE, cutoff=12, alpha=0.25)),
+        "zahn": (lambda: cg.Zahn(12, 0.25), O.params(O.ZAHN, cutoff=12, alpha=0.25)),
+        "ewald": (lambda: cg.Ewald(10, 0.3), O.params(O.EWALD, cutoff=10, alpha=0.3)),
+        "ewald_screened": (lambda: cg.Ewald(10, 0.3, INF, 30.0), O.params(O.EWALD, cutoff=10, alpha=0.3, debye_length=30.0)),
+        "ewaldt": (lambda: cg.EwaldTruncated(12, 0.25), O.params(O.EWALDT, cutoff=12, alpha=0.25)),
+    }
+
+
+def splined_pair(name, kind):
+    """Splined wrapper of a zoo scheme: the oracle generates the tables, both sides evaluate the same tables."""
+    mk, p = zoo()[name]
+    ps = O.Params.from_buffer_copy(p)
+    ps.splined = 1
+    osch = O.Scheme(ps, kind)
+    pot = cg.Splined().spline_from_tables(mk(), osch.spline_tables())
+    return pot, osch
+
+
+def compare(gpu, ref, what, tol=TOL):
+    """-> dict of worst normalised errors (each must be <= 1 to pass at `tol`)."""
+    out = {}
+    for key, skey, bit in (("force", "force_scale", cg.FORCE), ("field", "field_scale", cg.FIELD)):
+        if what & bit:
+            g, r, s = gpu[key], ref[key], ref[skey]
+            dn = np.linalg.norm(g - r, axis=1)
+            den = np.maximum(np.linalg.norm(r, axis=1), s)
+            den = np.where(den > 0, den, 1.0)
+            out[key + "_particle"] = float(np.max(dn / den) / tol)
+            nr = np.linalg.norm(r)
+            out[key + "_array"] = float(np.linalg.norm(g - r) / (nr if nr > 0 else 1.0) / tol)
+    if what & cg.POTENTIAL:
+        g, r, s = gpu["potential"], ref["potential"], ref["potential_scale"]
+        den = np.where(s > 0, s, 1.0)
+        out["potential_particle"] = float(np.max(np.abs(g - r) / den) / tol)
+    if what & cg.ENERGY:
+        den = ref["energy_abs"] if ref["energy_abs"] > 0 else 1.0
+        out["energy"] = float(abs(gpu["energy"] - ref["energy"]) / den / tol)
+    out["pairs_equal"] = 0.0 if gpu["pairs"] == ref["pairs"] else float("inf")
+    return out
+
+
+def run_case(pot, osch, x, y, z, q, mu, box, pbc, mode, what, shard=None):
+    ev = cg.BatchedEvaluator(pot)
+    if shard:
+        ev.set_shard(*shard)
+    ev.set_system(x, y, z, q, mu, box, pbc)
+    g = ev.eval(mode, what)
+    g["counters"] = ev.counters()
+    g["timings"] = ev.timings()
+    ev.close()
+    r = osch.batched(x, y, z, q, mu, box, pbc, mode, what)
+    return g, r

@@ -1,0 +1,85 @@
+"""GPU parity: the CUDA path through the C ABI against the CPU oracle on identical seeded inputs."""
+import numpy as np
+import pytest
+
+import coulombgalore_b200 as cg
+from oracle import oracle as O
+
+from parity import TOL, compare, run_case, splined_pair, zoo
+
+pytestmark = pytest.mark.gpu
+
+ALL = cg.ENERGY | cg.FORCE | cg.FIELD | cg.POTENTIAL
+
+
+def lattice(n, a, seed, kind):
+    return O.generate(n, a, seed, kind)
+
+
+def assert_parity(errs):
+    bad = {k: v for k, v in errs.items() if not (v <= 1.0)}
+    assert not bad, "parity beyond %.0e (normalised errors, must be <= 1): %r" % (TOL, errs)
+
+
+def test_config1_qpotential_all_pairs_open(oracle_kind):
+    """BASELINE config 1: qPotential(14, 3), N = 16^3, a = 1.75, open box, ion-ion energy + force."""
+    x, y, z, q, mu = lattice(16, 1.75, 1001, oracle_kind)
+    mk, p = zoo()["qpotential3"]
+    g, r = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, None, [28.0] * 3, False, cg.MODE_ION, cg.ENERGY | cg.FORCE)
+    assert r["pairs"] == 4631758
+    assert_parity(compare(g, r, cg.ENERGY | cg.FORCE))
+
+
+@pytest.mark.parametrize("name", ["wolf", "fennell"])
+def test_config2_small_cell_list_pbc(name, oracle_kind):
+    """BASELINE config 2 at a size the oracle finishes in seconds: Wolf/Fennell(12, 0.25), a = 3, periodic, forces."""
+    x, y, z, q, mu = lattice(24, 3.0, 1002, oracle_kind)
+    mk, p = zoo()[name]
+    g, r = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, None, [72.0] * 3, True, cg.MODE_ION, cg.FORCE)
+    assert_parity(compare(g, r, cg.FORCE))
+
+
+def test_config3_small_reactionfield_dipoles(oracle_kind):
+    x, y, z, q, mu = lattice(20, 3.0, 1003, oracle_kind)
+    mk, p = zoo()["reactionfield"]
+    w = cg.ENERGY | cg.FIELD | cg.FORCE
+    g, r = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, None, mu, [60.0] * 3, True, cg.MODE_DIPOLE, w)
+    assert_parity(compare(g, r, w))
+
+
+def test_config4_small_ewald_screened_multipole(oracle_kind):
+    x, y, z, q, mu = lattice(20, 3.0, 1004, oracle_kind)
+    mk, p = zoo()["ewald_screened"]
+    w = cg.ENERGY | cg.FORCE
+    g, r = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, [60.0] * 3, True, cg.MODE_MULTIPOLE, w)
+    assert_parity(compare(g, r, w))
+
+
+def test_config5_small_splined_poisson_multipole(oracle_kind):
+    x, y, z, q, mu = lattice(20, 3.0, 1005, oracle_kind)
+    pot, osch = splined_pair("poisson43", oracle_kind)
+    w = cg.ENERGY | cg.FORCE
+    g, r = run_case(pot, osch, x, y, z, q, mu, [60.0] * 3, True, cg.MODE_MULTIPOLE, w)
+    assert_parity(compare(g, r, w))
+
+
+@pytest.mark.parametrize("name", sorted(zoo().keys()))
+@pytest.mark.parametrize("mode", [cg.MODE_ION, cg.MODE_DIPOLE, cg.MODE_MULTIPOLE])
+def test_every_scheme_every_mode(name, mode, oracle_kind):
+    """Every scheme x {ion, dipole, multipole} x {energy, force, field, potential} at n = 16 (SURVEY.md 8d extras)."""
+    mk, p = zoo()[name]
+    pot = mk()
+    pbc = pot.cutoff < 1e10  # Plain has no cut-off: open boundaries only
+    x, y, z, q, mu = lattice(16 if pbc else 10, 3.0, 77 + mode, oracle_kind)
+    L = 48.0
+    g, r = run_case(pot, O.Scheme(p, oracle_kind), x, y, z, q, mu, [L] * 3, pbc, mode, ALL)
+    assert_parity(compare(g, r, ALL))
+
+
+@pytest.mark.parametrize("name", ["wolf", "ewald_screened", "qpotential3", "plain_yukawa", "reactionfield"])
+def test_splined_schemes(name, oracle_kind):
+    pot, osch = splined_pair(name, oracle_kind)
+    pbc = pot.cutoff < 1e10
+    x, y, z, q, mu = lattice(16 if pbc else 10, 3.0, 99, oracle_kind)
+    g, r = run_case(pot, osch, x, y, z, q, mu, [48.0] * 3, pbc, cg.MODE_MULTIPOLE, ALL)
+    assert_parity(compare(g, r, ALL))
