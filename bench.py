@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- pair interactions/s (fp64) of the B200 batched CoulombGalore engine.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): Wolf(12, 0.25) and Fennell(12, 0.25) ion-ion forces, N = 100^3 = 1 000 000 charges
+on the jittered lattice of SURVEY.md 8d (a = 3, L = 300, periodic, seed 1002), cell list under R_c = 12, fp64.
+One STEP = one Wolf evaluation + one Fennell evaluation of all per-particle forces: spatial sort, pair kernel and
+reductions each time (positions are treated as new every step).  The unit of work is one ordered in-cutoff pair
+(i <- j); `value` = pairs evaluated by all ranks per second with the inputs resident in HBM; `e2e` is the same metric
+through the host-buffer C ABI (cg_set_system + cg_eval: H2D of positions/charges and D2H of forces inside the timing).
+
+N > 1: every rank owns N/R particles, the step all-gathers the SoA inputs over NCCL, then each rank
+sorts and evaluates its contiguous block of i-groups.  Total work is fixed -> "scaling": "strong".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CFG = dict(n_side=100, a=3.0, seed=1002, cutoff=12.0, alpha=0.25)
+F_ALG = {"wolf": 33.0, "fennell": 39.0}  # algorithmic flops per ordered in-cutoff pair, SURVEY.md 8d / appendix D
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: 148 SMs x 64 DFMA/clk x 2 x 1.965 GHz
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-side", type=int, default=CFG["n_side"], help="lattice sites per edge (default: the BASELINE config)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_rate(kind, n_side, target_seconds, nthreads=0):
+    """The reference's own classes looped over the same pairs on the host cores (oracle/harness.hpp), on a bounded
+    sample of i-particles; -> (pairs/s, cores, sample description, kind string)."""
+    from oracle import oracle as O
+    x, y, z, q, _ = O.generate(n_side, CFG["a"], CFG["seed"], kind)
+    L = n_side * CFG["a"]
+    cores = nthreads or (os.cpu_count() or 1)
+    schemes = [O.Scheme(O.params(O.WOLF, cutoff=CFG["cutoff"], alpha=CFG["alpha"]), kind),
+               O.Scheme(O.params(O.FENNELL, cutoff=CFG["cutoff"], alpha=CFG["alpha"]), kind)]
+    N = x.size
+
+    def run(m):
+        t0 = time.perf_counter()
+        pairs = 0
+        for s in schemes:
+            r = s.batched(x, y, z, q, None, [L] * 3, True, O.MODE_ION, O.FORCE, 0, m, cores, scales=False)
+            pairs += r["pairs"]
+        return pairs, time.perf_counter() - t0
+
+    m = min(N, 16384)
+    pairs, dt = run(m)  # probe (includes the serial CPU cell-list build for all N particles)
+    m2 = int(min(N, max(m, m * target_seconds / max(dt, 1e-3))))
+    if m2 > m:
+        pairs, dt = run(m2)
+        m = m2
+    return pairs / dt, cores, "first %d of %d i-particles, Wolf + Fennell force, %.1f s incl. cell-list build" % (m, N, dt), schemes[0].kind
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    n_side = args.n_side
+    N = n_side ** 3
+    workload = ("configs[1]: Wolf(12,0.25) + Fennell(12,0.25) ion-ion forces, cell list, N=%d^3=%d charges, a=3, periodic, "
+                "R_c=12, fp64; step = one Wolf + one Fennell evaluation incl. spatial sort" % (n_side, N))
+    config = {"workload": workload, "n_particles": N, "cutoff": CFG["cutoff"], "l2_policy": "L2 flushed (512 MiB write) before every timed step",
+              "parallelism": "i-group sharding x%d, NCCL all-gather of SoA inputs" % world if world > 1 else "single GPU"}
+
+    from oracle import oracle as O
+    okind = "ref" if O.available("ref") else "port"
+
+    # ------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        per_step = []
+        sample = kind = ""
+        cores = 0
+        for s in range(args.warmup + args.steps):
+            rate, cores, sample, kind = cpu_reference_rate(okind, n_side, 4.0)
+            if s >= args.warmup:
+                per_step.append(rate)
+        v = statistics.mean(per_step)
+        line = {"impl": "reference", "metric": "pair interactions/s (fp64)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference" if kind == "reference" else "port",
+                                 "sample": sample},
+                "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    import numpy as np
+    import torch
+
+    import coulombgalore_b200 as cg
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    pots = {"wolf": cg.Wolf(CFG["cutoff"], CFG["alpha"]), "fennell": cg.Fennell(CFG["cutoff"], CFG["alpha"])}
+    evs = {k: cg.BatchedEvaluator(p, local) for k, p in pots.items()}
+    # a dedicated (non-default) stream: everything timed below is enqueued on it, and the CUDA events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    for ev in evs.values():
+        ev.set_stream(stream.cuda_stream)
+        ev.set_shard(rank, world)
+    L = n_side * CFG["a"]
+    box = [L, L, L]
+
+    # synthetic inputs generated on the device by the SURVEY.md 8d rule (bit-identical to the oracle generator)
+    full = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
+    evs["wolf"].generate_lattice_device(n_side, CFG["a"], CFG["seed"], full[0], full[1], full[2], full[3])
+    torch.cuda.synchronize()
+    lo, hi = N * rank // world, N * (rank + 1) // world
+    owned = [t[lo:hi].clone() for t in full]  # this rank's particles
+    if world > 1:
+        counts = [N * (r + 1) // world - N * r // world for r in range(world)]
+        even = len(set(counts)) == 1
+    gathered = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)] if world > 1 else full
+    force = torch.empty((N, 3), dtype=torch.float64, device=dev)
+    scal = {k: torch.zeros(2, dtype=torch.float64, device=dev) for k in evs}
+    flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        launches = 0
+        if world > 1:
+            for k in range(4):  # the exchange step: positions + charges of every rank
+                if even:
+                    dist.all_gather_into_tensor(gathered[k], owned[k])
+                else:
+                    parts = list(gathered[k].split(counts))
+                    dist.all_gather(parts, owned[k])
+        for name, ev in evs.items():
+            ev.set_system_device(gathered[0], gathered[1], gathered[2], gathered[3], None, box, True)
+            ev.eval_device(cg.MODE_ION, cg.FORCE, force=force, scalars=scal[name])
+            launches += ev.counters()["launches"]
+        return launches
+
+    # ---- device-resident timing ----
+    pair_ms = {k: [] for k in evs}
+    sort_ms = {k: [] for k in evs}
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_steps = []
+    launches = 0
+    e0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    for s in range(args.steps):
+        flush_buf.fill_(s & 0xFF)  # evict L2 between timed iterations (untimed)
+        e0[s].record()
+        launches += step_device()
+        e1[s].record()
+        e1[s].synchronize()
+        for k, ev in evs.items():
+            t = ev.timings()
+            pair_ms[k].append(t["pair_ms"])
+            sort_ms[k].append(t["sort_ms"])
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_steps = [e0[s].elapsed_time(e1[s]) for s in range(args.steps)]
+    total_ms = torch.tensor([sum(t_steps)], dtype=torch.float64, device=dev)
+    pairs_rank = torch.tensor([float(sum(scal[k][1].item() for k in evs))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pairs_rank, op=dist.ReduceOp.SUM)
+    ms_per_step = total_ms.item() / args.steps
+    pairs_per_step = pairs_rank.item()
+    value = pairs_per_step / (ms_per_step * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI ----
+    e2e = None
+    if not args.no_e2e:
+        host = [t.cpu().numpy() for t in full]  # cg_set_system copies from these host buffers every step
+        hx = [torch.from_numpy(a).pin_memory().numpy() for a in host]
+        evh = {k: cg.BatchedEvaluator(p, local) for k, p in pots.items()}
+        for ev in evh.values():
+            ev.set_shard(rank, world)
+
+        def step_host():
+            p = 0
+            for ev in evh.values():
+                ev.set_system(hx[0], hx[1], hx[2], hx[3], None, box, True)
+                p += ev.eval(cg.MODE_ION, cg.FORCE)["pairs"]
+            return p
+
+        step_host()
+        barrier()
+        t0 = time.perf_counter()
+        pe = 0
+        ksteps = max(1, min(args.steps, 5))
+        for _ in range(ksteps):
+            pe += step_host()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        pe_t = torch.tensor([float(pe)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(pe_t, op=dist.ReduceOp.SUM)
+        e2e = {"value": pe_t.item() / dt.item(), "unit": "pairs/s", "h2d_bytes_per_step": 2 * 4 * 8 * N,
+               "d2h_bytes_per_step": 2 * (3 * 8 * N + 16), "steps": ksteps,
+               "note": "cg_set_system + cg_eval with pinned host buffers; every rank uploads all N particles"}
+        for ev in evh.values():
+            ev.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (pair_kernel): FP64 pipe, measured live with CUDA events ----
+    peak_tf, _ = evs["wolf"].fp64_peak_probe()
+    pk = {}
+    for k in evs:
+        ms = statistics.mean(pair_ms[k])
+        pr = scal[k][1].item()
+        pk[k] = {"pair_kernel_ms": ms, "sort_ms": statistics.mean(sort_ms[k]), "pairs_per_launch": pr,
+                 "pairs_per_s_kernel": pr / (ms * 1e-3), "tflops_alg": pr * F_ALG[k] / (ms * 1e-3) / 1e12}
+    ach = sum(scal[k][1].item() * F_ALG[k] for k in evs) / (sum(statistics.mean(pair_ms[k]) for k in evs) * 1e-3) / 1e12
+    alg_bytes = (N // world) * (32 + 24) + N * 32  # per launch: own i read + force write, all j read once
+    hbm_peak = None
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        pass
+    kms = statistics.mean(pair_ms["wolf"])
+    roofline = {"bound": "fp64", "kernel": "pair_kernel (Wolf + Fennell launches)", "achieved": ach, "peak": peak_tf,
+                "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
+                "peak_source": "measured here: register-resident DFMA chain (cg_fp64_peak_probe); MEASURED_PEAKS.json has no fp64 entry",
+                "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": ach / NOMINAL_FP64_TFLOPS,
+                "flops_per_pair": F_ALG, "traffic": None,
+                "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9,
+                        "peak_gbs": hbm_peak, "frac": (alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
+                        "note": "shown only to establish that the path is not HBM-bound"},
+                "per_scheme": pk}
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        rate, cores, sample, kind = cpu_reference_rate(okind, n_side, 12.0)
+        cpu = {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "reference" if kind == "reference" else "port", "sample": sample}
+
+    line = {"metric": "pair interactions/s (fp64)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": config, "pairs_per_step": pairs_per_step, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "counters": evs["wolf"].counters()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

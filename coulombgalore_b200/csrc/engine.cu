@@ -22,6 +22,7 @@
 
 #include "cg_b200.h"
 #include "coulombgalore/detail/descriptor.hpp"
+#include "coulombgalore/detail/erfc_table.hpp"
 #include "kparams.cuh"
 
 namespace cgb {
@@ -176,7 +177,9 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int n_sorte
     const double X = sp.x[p] + (double)sx * sp.box[0], Y = sp.y[p] + (double)sy * sp.box[1], Z = sp.z[p] + (double)sz * sp.box[2];
     pos[k] = make_double4(X, Y, Z, sp.q ? sp.q[p] : 0.0);
     if (mu) mu[k] = sp.mx ? make_double4(sp.mx[p], sp.my[p], sp.mz[p], 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
-    pos32[k] = make_float4((float)(X - (sp.lo[0] - sp.gw[0])), (float)(Y - (sp.lo[1] - sp.gw[1])), (float)(Z - (sp.lo[2] - sp.gw[2])), 0.0f);
+    const float fx = (float)(X - (sp.lo[0] - sp.gw[0])), fy = (float)(Y - (sp.lo[1] - sp.gw[1])), fz = (float)(Z - (sp.lo[2] - sp.gw[2]));
+    // w = |c|^2 of the ROUNDED coordinates (formed in fp64, rounded once): the prefilter expands |c - x_i|^2 around it
+    pos32[k] = make_float4(fx, fy, fz, (float)((double)fx * fx + (double)fy * fy + (double)fz * fz));
     orig[k] = p;
 }
 
@@ -413,8 +416,9 @@ struct cg_handle {
     int device = 0;
     cg_scheme_desc desc;
     std::vector<double> host_table; // packed spline tables
-    DevBuf<double> d_table;
+    DevBuf<double> d_table;      // packed spline tables (Splined schemes)
     int table_doubles = 0;
+    DevBuf<double> d_erfc_table; // erfc/exp table of specfun.hpp (erfc-family schemes)
     int functor = -1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -518,6 +522,18 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
             return CG_ERR_CUDA;
         }
     }
+    {
+        const FunctorEntry *fe = functor_entry(fn);
+        if (fe && fe->table_kind == cgd::kTableErfc) {
+            const std::vector<double> t = cgd::make_erfc_table();
+            if (h->d_erfc_table.ensure(t.size()) != cudaSuccess ||
+                cudaMemcpy(h->d_erfc_table.p, t.data(), t.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+                g_create_error = "cannot upload the erfc table";
+                delete h;
+                return CG_ERR_CUDA;
+            }
+        }
+    }
     bool ok = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_counts, 4 * sizeof(int)) == cudaSuccess;
@@ -539,6 +555,7 @@ int cg_destroy(cg_handle *h) {
     cudaStreamSynchronize(h->stream);
     for (auto &b : h->own_in) b.release();
     h->d_table.release();
+    h->d_erfc_table.release();
     h->cell_count.release();
     h->cell_start.release();
     h->scan_tmp.release();
@@ -822,15 +839,23 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     kp.cs_y = (float)(1.0 / sp.inv_cs[1]);
     kp.cs_z = (float)(1.0 / sp.inv_cs[2]);
     {
-        // fp32 prefilter margin: both relative coordinates are rounded to fp32 (half an ulp of the largest relative
-        // coordinate each), the difference and the squared norm add a few more roundings of magnitude ~ rc
+        // Prefilter margins.  The kernel tests  |c|^2 - 2 c.x_i < rc2_m - |x_i|^2  in fp32 on coordinates relative to
+        // the grid origin (|c|, |x_i| <= S = sqrt(3) * span).  Error budget of the test, in units of length^2:
+        //   * three FFMA roundings of partial sums <= 3 S^2, the rounding of |c|^2 and of the right-hand side:
+        //     <= 12 * 2^-24 * S^2;
+        //   * both positions are rounded to fp32 (<= 2^-24 span per component each): |r - r32| <= sqrt(3) 2^-23 span,
+        //     i.e. <= 2 rc sqrt(3) 2^-23 span (+ second order) in r^2.
+        // rc2_m adds both (x1.1) to the exact squared cut-off, so every true neighbour passes; false positives are
+        // removed by the exact FP64 gate in phase 2.
         double span = 0.0;
         for (int d = 0; d < 3; d++) span = std::max(span, sp.ntot[d] / sp.inv_cs[d]);
-        const double e = std::ldexp(span, -23) + std::ldexp(std::min(rc, span), -22);
-        const double m = 2.0 * 1.7320508 * e * 1.05;
-        double rcm = std::min(rc + m, 1e15) * (1.0 + 3e-7);
+        const double S2 = 3.0 * span * span;
+        const double rcl = std::min(rc, 1e150);
+        const double e_pos = 1.7320508 * std::ldexp(span, -23);
+        const double margin = 1.1 * (12.0 * std::ldexp(S2, -24) + 2.0 * rcl * e_pos + e_pos * e_pos);
+        kp.rc2_m = rcl * rcl + margin;
+        const double rcm = std::min(std::sqrt(kp.rc2_m), 1e15) * (1.0 + 3e-7);
         kp.rc_m = (float)rcm;
-        kp.rc2_m = (float)(rcm * rcm * (1.0 + 6e-7));
         const int nmax = std::max(sp.ntot[0], std::max(sp.ntot[1], sp.ntot[2]));
         kp.slack = (float)(1e-4 + 1e-6 * nmax);
     }
@@ -872,8 +897,17 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     (void)cwhat;
     const FunctorEntry *fe = functor_entry(h->functor);
     if (!fe) return CG_ERR_INVALID;
+    const double *dev_table = nullptr;
+    int table_doubles = 0;
+    if (fe->table_kind == cgd::kTableSpline) {
+        dev_table = h->d_table.p;
+        table_doubles = h->table_doubles;
+    } else if (fe->table_kind == cgd::kTableErfc) {
+        dev_table = h->d_erfc_table.p;
+        table_doubles = 2 * cgd::kErfcTableEntries;
+    }
     if (items > 0) {
-        CG_CUDA(h, fe->pair[ci](kp, D, h->d_table.p, h->table_doubles, items, st));
+        CG_CUDA(h, fe->pair[ci](kp, D, dev_table, table_doubles, items, st));
         pair_launches++;
         launches++;
     }
@@ -956,7 +990,9 @@ int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out) {
     cudaSetDevice(h->device);
     const FunctorEntry *fe = functor_entry(h->functor);
     if (!fe) return CG_ERR_INVALID;
-    CG_CUDA(h, fe->srf(h->desc, h->d_table.p, h->table_doubles, n, q, out, h->stream));
+    const bool erfc_tab = fe->table_kind == cgd::kTableErfc;
+    CG_CUDA(h, fe->srf(h->desc, erfc_tab ? h->d_erfc_table.p : h->d_table.p, erfc_tab ? 2 * cgd::kErfcTableEntries : h->table_doubles, n, q,
+                       out, h->stream));
     return CG_OK;
 }
 

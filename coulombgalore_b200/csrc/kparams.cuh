@@ -12,7 +12,7 @@ namespace cgd = CoulombGalore::detail;
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kQueueCap = 64; // per-lane deferred-pair queue depth (entries); flush is forced above kQueueCap-32
+constexpr int kSlots = 48; // candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase
 
 // Spatially sorted system.  With periodic boundaries the arrays also hold the periodic images that lie within one
 // cut-off of the box ("ghost" entries, coordinates already shifted), so the pair kernel never applies a minimum
@@ -20,7 +20,7 @@ constexpr int kQueueCap = 64; // per-lane deferred-pair queue depth (entries); f
 struct KParams {
     const double4 *pos;   // x, y, z, charge            [n_sorted]
     const double4 *mu;    // mu_x, mu_y, mu_z, 0        [n_sorted]  (may be null when no dipoles are needed)
-    const float4 *pos32;  // position relative to the grid origin in fp32, w unused   [n_sorted]
+    const float4 *pos32;  // position relative to the grid origin in fp32, w = |xyz|^2   [n_sorted]
     const int *orig;      // original particle index of a sorted entry               [n_sorted]
     const int *cell_start; // first sorted entry of each cell, x fastest             [ncell + 1]
     const int2 *groups;   // i-groups: (first sorted entry, count <= 32); a group never crosses a cell row
@@ -28,7 +28,8 @@ struct KParams {
     int split;            // j-split factor: work item = (group, s), s in [0, split)
     int nx, ny, nz;       // cells per dimension (ghost layers included)
     float inv_cs_x, inv_cs_y, inv_cs_z, cs_x, cs_y, cs_z;
-    float rc_m, rc2_m;    // cut-off plus fp32 rounding margin (conservative prefilter), and its square
+    float rc_m;           // cut-off plus fp32 rounding margin, for the candidate cell ranges
+    double rc2_m;         // squared cut-off plus the rounding margin of the three-FFMA prefilter test
     float slack;          // slack in cell units for fp32 cell-range rounding
     double rc2;           // exact gate: r2 < cutoff_squared (strict, reference core.hpp:354 etc.)
     cgd::CoreParams core;
@@ -63,6 +64,7 @@ __host__ __device__ constexpr Combo combo(int i) {
 struct FunctorEntry {
     pair_launch_fn pair[kNumCombos];
     srf_launch_fn srf;
+    int table_kind; // cgd::kTableNone / kTableSpline / kTableErfc: which table the engine must pass
 };
 
 // one per functor family, defined in pair_inst_*.cu

@@ -1,17 +1,85 @@
 // coulombgalore/detail/specfun.hpp -- the transcendental functions of the pair path.
 //
 // Host: glibc libm, exactly the calls the reference makes (std::erfc, std::exp, std::sqrt).
-// Device: CUDA's double-precision erfc/erfcx/exp/rsqrt (<= 2-5 ulp), far inside the 1e-12 parity budget.
+//
+// Device (sm_100a): the FP64 pipe issues one warp instruction every two cycles, so the pair kernels are bound by
+// the NUMBER of FP64 instructions per pair.  CUDA's libm erfc + exp cost ~85 FP64 instructions plus ~70 constant
+// moves per call; the versions below cost 28 FP64 instructions and one 16-byte shared-memory load for BOTH
+// erfc(x) and exp(-x^2):
+//   * a table {erfc(x_k), exp(-x_k^2)} at x_k = k/128, k < 1024 (16 KB, staged in shared memory by the kernels,
+//     built on the host with glibc -- include/coulombgalore/detail/erfc_table.hpp);
+//   * exp(-x^2) = exp(-x_k^2) exp(-w), w = (x - x_k)(x + x_k), |w| <= 1/16: degree-7 Taylor polynomial;
+//   * erfc(x) = erfc(x_k) - 2/sqrt(pi) exp(-x_k^2) I,  I = int_0^d exp(-2 x_k t - t^2) dt, d = x - x_k, by the
+//     two-point Hermite (osculatory) rule  I = d/2 (f0+f1) + d^2/10 (f0'-f1') + d^3/120 (f0''+f1'') + d^7 f^(6)/100800,
+//     whose end-point values all follow from the exp(-w) just computed: f1 = e, f' = -(2 x_k + 2 t) f, ...
+// Measured against mpmath (tests/test_specfun.py): <= 2 ulp for x < 4, <= 4e-15 relative for x < 6, i.e. three to
+// four orders inside the 1e-12 parity budget.  Arguments outside [0, 8) take CUDA's erfc/exp (a rarely taken branch).
 #pragma once
 #include "hd.hpp"
 
 namespace CoulombGalore {
 namespace detail {
 
+constexpr int kErfcTableEntries = 1024;      // x_k = k / 128, x < 8
+constexpr double kErfcTableInvStep = 128.0;
+constexpr double kErfcTableStep = 1.0 / 128.0;
+
+#ifdef __CUDA_ARCH__
+// 1/sqrt(x), x > 0 normal: MUFU.RSQ64H seed (2^-22) + one third-order (Halley) step -> full double precision
+__device__ __forceinline__ double rsqrt_device(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
+// ec = erfc(x), E = exp(-x^2) from the shared-memory table `tab` (interleaved {erfc(x_k), exp(-x_k^2)})
+__device__ __forceinline__ void erfc_gauss_table(double x, const double *tab, double &ec, double &E) {
+    const double magic = 6755399441055744.0; // 2^52 + 2^51: the low word of (x*128 + magic) is round(x*128)
+    const double t = fma(x, kErfcTableInvStep, magic);
+    const int k = __double2loint(t);
+    if ((unsigned)k < (unsigned)kErfcTableEntries) {
+        const double kf = t - magic;
+        const double d = fma(kf, -kErfcTableStep, x); // x - x_k, exact
+        const double xk = kf * kErfcTableStep;
+        double2 T; // the table lives in shared memory: address it as such (a generic load would cost an aperture check)
+        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(T.x), "=d"(T.y) : "r"((unsigned)__cvta_generic_to_shared(tab) + 16u * (unsigned)k));
+        const double w = d * (x + xk);
+        double e = fma(w, -1.0 / 5040.0, 1.0 / 720.0);
+        e = fma(e, w, -1.0 / 120.0);
+        e = fma(e, w, 1.0 / 24.0);
+        e = fma(e, w, -1.0 / 6.0);
+        e = fma(e, w, 0.5);
+        e = fma(e, w, -1.0);
+        e = fma(e, w, 1.0); // exp(-w)
+        E = T.y * e;
+        const double a0 = 1.0 + e;
+        const double a1 = fma(x, e, -xk);
+        const double a2 = fma(fma(2.0 * x, x, -1.0), e, fma(2.0 * xk, xk, -1.0));
+        const double I = d * fma(d, fma(d * (1.0 / 60.0), a2, 0.2 * a1), 0.5 * a0);
+        ec = fma(-1.1283791670955125739 * T.y, I, T.x);
+    } else { // negative or huge argument
+        E = exp(-x * x);
+        ec = erfc(x);
+    }
+}
+#endif
+
+// a double from a table that lives in shared memory on the device (plain memory on the host)
+CG_HD double table_load(const double *p) {
+#ifdef __CUDA_ARCH__
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
+#else
+    return *p;
+#endif
+}
+
 // 1/sqrt(x) for x > 0
 CG_HD double rsqrt_pos(double x) {
 #ifdef __CUDA_ARCH__
-    return rsqrt(x);
+    return rsqrt_device(x);
 #else
     return 1.0 / std::sqrt(x);
 #endif
@@ -26,25 +94,14 @@ CG_HD double exp_any(double y) {
 #endif
 }
 
-// ec = erfc(x), E = exp(-x^2); x may be negative (screened Ewald at small q)
-CG_HD void erfc_and_gauss(double x, double &ec, double &E) {
+// ec = erfc(x), E = exp(-x^2); `tab` is the device erfc table (ignored on the host)
+CG_HD void erfc_and_gauss(double x, double &ec, double &E, const double *tab) {
 #ifdef __CUDA_ARCH__
-    E = exp(-x * x);
-    ec = erfc(x);
+    erfc_gauss_table(x, tab, ec, E); // the kernels always stage the table
 #else
+    (void)tab;
     E = std::exp(-x * x);
     ec = std::erfc(x);
-#endif
-}
-
-// erfc(xp) * exp(a) where exp(a) = exp(xp^2) * Em, i.e. erfcx(xp) * Em (Em = exp(-xm^2), xp^2 - xm^2 = a)
-CG_HD double erfc_times_exp(double xp, double a, double Em) {
-#ifdef __CUDA_ARCH__
-    (void)a;
-    return erfcx(xp) * Em;
-#else
-    (void)Em;
-    return std::erfc(xp) * std::exp(a);
 #endif
 }
 

@@ -18,12 +18,16 @@
 namespace CoulombGalore {
 namespace detail {
 
+// what `tab` points to in eval(): nothing, the packed Andrea tables of a Splined scheme, or the erfc/exp table of
+// specfun.hpp (device only; the host evaluates libm directly)
+enum { kTableNone = 0, kTableSpline = 1, kTableErfc = 2 };
+
 // 2/sqrt(pi); the reference forms it as 2/(2*sqrt(atan(1))) (e.g. wolf.hpp:36), equal to within one ulp
 constexpr double kTwoOverSqrtPi = 1.1283791670955125739;
 
 // ---------------------------------------------------------------------------------------------------------------
 struct PlainSrf { // plain.hpp:47-50
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableNone;
     CG_HD PlainSrf() {}
     CG_HD explicit PlainSrf(const cg_scheme_desc &) {}
     template <int ND> CG_HD void eval(double, double *s, const double * = nullptr) const {
@@ -35,7 +39,7 @@ struct PlainSrf { // plain.hpp:47-50
 };
 
 struct ReactionFieldSrf { // reactionfield.hpp:60-73: S = 1 + a q^3 - b q
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableNone;
     double a, b;
     CG_HD ReactionFieldSrf() : a(0), b(0) {}
     CG_HD explicit ReactionFieldSrf(const cg_scheme_desc &d) : a(d.rf_a), b(d.rf_b) {}
@@ -49,7 +53,7 @@ struct ReactionFieldSrf { // reactionfield.hpp:60-73: S = 1 + a q^3 - b q
 };
 
 struct FanourgakisSrf { // fanourgakis.hpp:49-61
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableNone;
     CG_HD FanourgakisSrf() {}
     CG_HD explicit FanourgakisSrf(const cg_scheme_desc &) {}
     template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
@@ -74,7 +78,7 @@ template <int ND> CG_HD void jet_mul(double *c, const double *g) { // c <- c * g
 }
 
 template <int ORDER> struct QPotentialSrf {
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableNone;
     int order;
     CG_HD QPotentialSrf() : order(ORDER) {}
     CG_HD explicit QPotentialSrf(const cg_scheme_desc &d) : order(d.order) {}
@@ -116,16 +120,16 @@ template <int ORDER> struct QPotentialSrf {
 enum ErfcKind { kWolf, kFennell, kZeroDipole, kZahn, kEwaldT, kEwaldPlain };
 
 template <int KIND> struct ErfcFamilySrf {
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableErfc;
     double eta, eta2, k1, c, e, c2, invF0;
     CG_HD ErfcFamilySrf() : eta(0), eta2(0), k1(0), c(0), e(0), c2(0), invF0(1) {}
     CG_HD explicit ErfcFamilySrf(const cg_scheme_desc &d)
         : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), c(d.erfc_eta), e(d.exp_eta2),
           c2(d.erfc_eta + d.eta * kTwoOverSqrtPi * d.exp_eta2), invF0(KIND == kEwaldT ? 1.0 / d.F0 : 1.0) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+    template <int ND> CG_HD void eval(double q, double *s, const double *tab = nullptr) const {
         const double x = eta * q;
         double E, ec;
-        erfc_and_gauss(x, ec, E); // ec = erfc(x), E = exp(-x^2)
+        erfc_and_gauss(x, ec, E, tab); // ec = erfc(x), E = exp(-x^2)
         const double k1E = k1 * E;
         const double g2 = 2.0 * eta2 * q * k1E;                    // 4 eta^3 q E / sqrt(pi)
         const double g3 = 2.0 * eta2 * k1E * (1.0 - 2.0 * x * x);  // 4 eta^3 (1 - 2 x^2) E / sqrt(pi)
@@ -166,22 +170,22 @@ template <int KIND> struct ErfcFamilySrf {
 
 // Ewald with Debye screening (zeta = R_c / lambda_D > 0), ewald.hpp:175-195.
 //   S = 1/2 [ erfc(x+) e^{2 zeta q} + erfc(x-) ],  x+- = eta q +- zeta/(2 eta)
-// Because x+^2 - x-^2 = 2 zeta q, erfc(x+) e^{2 zeta q} = erfcx(x+) exp(-x-^2): one Gaussian serves both terms and
-// the product never overflows.
 struct EwaldScreenedSrf {
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableErfc;
     double eta, eta2, k1, zeta, zeta2, zeta3, half_z_over_eta, z_over_eta, z2_over_eta2;
     CG_HD EwaldScreenedSrf() : eta(0), eta2(0), k1(0), zeta(0), zeta2(0), zeta3(0), half_z_over_eta(0), z_over_eta(0), z2_over_eta2(0) {}
     CG_HD explicit EwaldScreenedSrf(const cg_scheme_desc &d)
         : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), zeta(d.zeta), zeta2(d.zeta * d.zeta),
           zeta3(d.zeta * d.zeta * d.zeta), half_z_over_eta(d.zeta / (2.0 * d.eta)), z_over_eta(d.zeta / d.eta),
           z2_over_eta2((d.zeta * d.zeta) / (d.eta * d.eta)) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+    template <int ND> CG_HD void eval(double q, double *s, const double *tab = nullptr) const {
         const double xq = eta * q;
         const double xm = xq - half_z_over_eta, xp = xq + half_z_over_eta;
-        double ecm, Em; // erfc(x-), exp(-x-^2)
-        erfc_and_gauss(xm, ecm, Em);
-        const double P = erfc_times_exp(xp, 2.0 * zeta * q, Em); // erfc(x+) exp(2 zeta q)
+        double ecm, Em, ecp, Ep; // erfc(x-), exp(-x-^2), erfc(x+)
+        erfc_and_gauss(xm, ecm, Em, tab);
+        erfc_and_gauss(xp, ecp, Ep, tab);
+        (void)Ep;
+        const double P = ecp * exp_any(2.0 * zeta * q); // erfc(x+) exp(2 zeta q), as the reference forms it
         s[0] = 0.5 * (P + ecm);
         if (ND >= 1) s[1] = -k1 * Em + zeta * P;
         if (ND >= 2) s[2] = 2.0 * k1 * eta * (xq - z_over_eta) * Em + 2.0 * zeta2 * P;
@@ -192,7 +196,7 @@ struct EwaldScreenedSrf {
 // ---------------------------------------------------------------------------------------------------------------
 // Poisson (poisson.hpp:119-220), run-time C and D.  q~ = q, or (1 - e^{2 kappa* q}) * yukawa_denom when screened.
 struct PoissonSrf {
-    static constexpr bool kHasTable = false;
+    static constexpr int kTable = kTableNone;
     int C, D, yukawa;
     double rk, denom, binomCDC;
     double w[CG_MAX_POISSON_C];
@@ -255,7 +259,7 @@ struct PoissonSrf {
 // shared memory by the kernels; a host pointer for the scheme classes):
 //   for k in 0..3:  knots[k][0..n_k)  at tab + koff[k],   coefficients[k][6*(n_k-1)]  at tab + coff[k]
 struct SplineSrf {
-    static constexpr bool kHasTable = true;
+    static constexpr int kTable = kTableSpline;
     int n[4], koff[4], coff[4], total;
     const double *tab;
     CG_HD SplineSrf() : total(0), tab(nullptr) {
@@ -296,14 +300,18 @@ struct SplineSrf {
         const double *kn = t + koff[k];
         // std::lower_bound(...) - begin - 1  ==  (#knots strictly below q) - 1; q on an interior knot -> lower interval
         int pos = -1;
-        for (int i = 0; i < n[k]; i++) pos += (kn[i] < q) ? 1 : 0;
+        for (int i = 0; i < n[k]; i++) pos += (table_load(kn + i) < q) ? 1 : 0;
         pos = pos < 0 ? 0 : (pos > n[k] - 2 ? n[k] - 2 : pos); // q == 0 asserts in the reference; clamp instead
-        const double dz = q - kn[pos];
+        const double dz = q - table_load(kn + pos);
         const double *c = t + coff[k] + 6 * pos;
-        return c[0] + dz * (c[1] + dz * (c[2] + dz * (c[3] + dz * (c[4] + dz * (c[5])))));
+        return table_load(c) + dz * (table_load(c + 1) + dz * (table_load(c + 2) + dz * (table_load(c + 3) + dz * (table_load(c + 4) + dz * (table_load(c + 5))))));
     }
     template <int ND> CG_HD void eval(double q, double *s, const double *t = nullptr) const {
+#ifdef __CUDA_ARCH__
+        const double *p = t; // staged in shared memory by the kernels
+#else
         const double *p = t ? t : tab;
+#endif
         s[0] = table(0, q, p);
         if (ND >= 1) s[1] = table(1, q, p);
         if (ND >= 2) s[2] = table(2, q, p);
