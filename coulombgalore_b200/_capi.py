@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcg_b200.so")
+# CG_B200_LIB: tuning builds (make LIB=... EXTRA_NVFLAGS=-D...); the default is the in-tree library
+LIB_PATH = os.environ.get("CG_B200_LIB") or os.path.join(HERE, "libcg_b200.so")
 
 CG_OK = 0
 STATUS = {0: "CG_OK", -1: "CG_ERR_INVALID", -2: "CG_ERR_NO_DEVICE", -3: "CG_ERR_CUDA", -4: "CG_ERR_ALLOC",

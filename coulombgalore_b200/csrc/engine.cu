@@ -860,6 +860,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.slack = (float)(1e-4 + 1e-6 * nmax);
     }
     kp.rc2 = D.cutoff_squared;
+    kp.rc2_safe = D.cutoff_squared < 1e30 ? 0.25 * D.cutoff_squared : 1.0; // Plain: any moderate value is in range
     kp.core.inverse_cutoff = D.inverse_cutoff;
     kp.core.cutoff_squared = D.cutoff_squared;
     kp.core.kappa = D.inverse_debye_length;

@@ -12,7 +12,7 @@ namespace cgd = CoulombGalore::detail;
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kSlots = 48; // candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase
+constexpr int kSlots = 40; // candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase
 
 // Spatially sorted system.  With periodic boundaries the arrays also hold the periodic images that lie within one
 // cut-off of the box ("ghost" entries, coordinates already shifted), so the pair kernel never applies a minimum
@@ -32,6 +32,7 @@ struct KParams {
     double rc2_m;         // squared cut-off plus the rounding margin of the three-FFMA prefilter test
     float slack;          // slack in cell units for fp32 cell-range rounding
     double rc2;           // exact gate: r2 < cutoff_squared (strict, reference core.hpp:354 etc.)
+    double rc2_safe;      // cutoff_squared / 4 (1 for Plain): the r2 fed to the branch-free arithmetic for rejected pairs
     cgd::CoreParams core;
     int n;                // number of (original) particles
     // outputs, indexed by original particle index; with split > 1 they are [split][n] partial buffers

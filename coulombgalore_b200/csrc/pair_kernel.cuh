@@ -11,8 +11,8 @@
 //     lane, then 32 broadcast LDS.128).  Each lane tests every candidate against its own particle with three FFMAs,
 //           |c|^2 - 2 c.x_i  <  rc^2 + margin - |x_i|^2      (|c|^2 is precomputed by the sort, margin covers fp32 rounding)
 //     and records the outcome as one bit of a 32-bit mask per batch -- a conservative prefilter, so the FP64 pipe
-//     never sees the ~80 % of candidates that are out of range.  Masks of up to kSlots batches are parked in shared
-//     memory (deferred evaluation);
+//     never sees the ~80 % of candidates that are out of range.  Non-empty masks of up to kSlots batches are parked
+//     in a per-lane list in shared memory (deferred evaluation);
 //   * PHASE 2 (FP64 pipe): every lane walks the set bits of its own masks.  All lanes hold work until the lane
 //     with the fewest hits runs dry, so the expensive FP64 pair arithmetic runs with (nearly) all lanes busy instead
 //     of at the ~15-25 % in-cut-off hit rate a branch-per-candidate loop would give.  The evaluation re-tests the
@@ -26,14 +26,26 @@ namespace cgb {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// one 256-bit read-only load (LDG.E.ENL2.256 on sm_100a): a sorted entry is one 32-byte sector
+// one 256-bit load of a sorted entry (one 32-byte sector); LDG.E...256 on sm_100a.  CG_GATHER selects the cache
+// policy for tuning runs: 0 = non-coherent path (default), 1 = L1-allocating with evict_last, 2 = two 128-bit loads.
+#ifndef CG_GATHER
+#define CG_GATHER 0
+#endif
 __device__ __forceinline__ double4 ldg256(const double4 *p) {
     double4 v;
+#if CG_GATHER == 0
     asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+#elif CG_GATHER == 1
+    asm volatile("ld.global.L1::evict_last.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+#else
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p)), b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    v = make_double4(a.x, a.y, b.x, b.y);
+#endif
     return v;
 }
 
-template <int MODE> constexpr int min_blocks_per_sm() { return MODE == cgd::kModeIon ? 3 : 2; }
+template <int MODE> constexpr int min_blocks_per_sm() { return 2; }
+template <int MODE> constexpr int pairs_in_flight() { return MODE == cgd::kModeIon ? 2 : 1; }
 
 template <class F, bool YUK, int MODE, int WHAT>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<MODE>())
@@ -44,8 +56,9 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     const int table_bytes = (table_doubles * 8 + 15) & ~15;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float4 *stage = reinterpret_cast<float4 *>(smem_raw + table_bytes) + warp * 32;
-    unsigned int *masks = reinterpret_cast<unsigned int *>(smem_raw + table_bytes + kWarpsPerCta * 32 * sizeof(float4)) + warp * (kSlots * 32);
-    int *j0s = reinterpret_cast<int *>(smem_raw + table_bytes + kWarpsPerCta * (32 * sizeof(float4) + kSlots * 32 * sizeof(unsigned int))) + warp * kSlots;
+    // per-lane lists of (hit mask, first candidate index) of the batches in which the lane had at least one hit
+    uint2 *hits = reinterpret_cast<uint2 *>(smem_raw + table_bytes + kWarpsPerCta * 32 * sizeof(float4)) + warp * (kSlots * 32) + lane;
+    constexpr int kIlp = pairs_in_flight<MODE>();
     const double *tab = nullptr;
     if constexpr (F::kTable != cgd::kTableNone) { // Splined: the four Andrea tables; erfc family: the erfc/exp table
         for (int k = threadIdx.x; k < table_doubles; k += kThreads) s_table[k] = dev_table[k];
@@ -100,7 +113,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
 
     while (more) {
         // ================= PHASE 1: prefilter up to kSlots batches of 32 candidates into bit masks =================
-        int nb = 0, cnt = 0;
+        int nb = 0, cnt = 0, qn = 0;
         while (nb < kSlots) {
             while (cur_j >= cur_end) { // next run
                 if (have == 0) {       // next 32 rows
@@ -164,34 +177,71 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             }
             const unsigned rel_self = (unsigned)(i - j0); // the lane's own entry is not a neighbour
             if (rel_self < 32u) m &= ~(1u << rel_self);
-            masks[nb * 32 + lane] = m;
-            if (lane == 0) j0s[nb] = j0;
+            if (m != 0u) hits[(qn++) * 32] = make_uint2(m, (unsigned)j0);
             cnt += __popc(m);
             nb++;
         }
         __syncwarp();
-        // ================= PHASE 2: evaluate the recorded pairs in FP64, one per lane per iteration =================
+        // ================= PHASE 2: evaluate the recorded pairs in FP64 =================
+        // kIlp independent pairs per lane and iteration, the gathers of the NEXT iteration already in flight, and no
+        // branch inside the arithmetic (the exact gate becomes a select): the FP64 dependency chains of the
+        // pairs interleave and the L2/L1 latency of the gather hides behind them.
+        // The lane's cursor: `cur` = unvisited hits of the current list entry, `base` = its first candidate index.
+        // The next entry is fetched as soon as the current one is exhausted, i.e. one pop ahead of its first use,
+        // so the shared-memory latency hides behind the pair arithmetic; pop() itself is straight-line code.
         int slot = 0;
-        unsigned cur = nb > 0 ? masks[lane] : 0u;
-        while (__any_sync(full, cnt > 0)) {
-            if (cnt > 0) {
-                cnt--;
-                while (cur == 0u) cur = masks[(++slot) * 32 + lane];
-                const int t = __ffs(cur) - 1;
-                cur &= cur - 1;
-                const int j = j0s[slot] + t;
-                const double4 pj = ldg256(p.pos + j);
-                const cgd::D3 d = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
+        unsigned cur = 0u;
+        int base = 0;
+        if (qn > 0) {
+            const uint2 e0 = hits[0];
+            cur = e0.x;
+            base = (int)e0.y;
+        }
+        auto pop = [&]() -> int { // next recorded neighbour of this lane, or -1
+            const bool has = cnt > 0;
+            const int j = has ? base + (__ffs(cur) - 1) : -1;
+            cur &= cur - 1u; // (0 stays 0)
+            cnt -= has ? 1 : 0;
+            if (cur == 0u && cnt > 0) {
+                const uint2 e = hits[(++slot) * 32];
+                cur = e.x;
+                base = (int)e.y;
+            }
+            return j;
+        };
+        int jc[kIlp];
+        double4 pc[kIlp], mc[kIlp];
+#pragma unroll
+        for (int u = 0; u < kIlp; u++) {
+            jc[u] = pop();
+            pc[u] = ldg256(p.pos + (jc[u] >= 0 ? jc[u] : i));
+            if constexpr (MODE != cgd::kModeIon) mc[u] = ldg256(p.mu + (jc[u] >= 0 ? jc[u] : i));
+        }
+        while (__any_sync(full, jc[0] >= 0)) {
+            int jn[kIlp];
+            double4 pn[kIlp], mn[kIlp];
+#pragma unroll
+            for (int u = 0; u < kIlp; u++) {
+                jn[u] = pop();
+                pn[u] = ldg256(p.pos + (jn[u] >= 0 ? jn[u] : i));
+                if constexpr (MODE != cgd::kModeIon) mn[u] = ldg256(p.mu + (jn[u] >= 0 ? jn[u] : i));
+            }
+#pragma unroll
+            for (int u = 0; u < kIlp; u++) {
+                const cgd::D3 d = {pi.x - pc[u].x, pi.y - pc[u].y, pi.z - pc[u].z};
                 const double r2 = d.x * d.x + d.y * d.y + d.z * d.z;
-                if (r2 < p.rc2) { // the exact, strict reference gate
-                    npairs++;
-                    cgd::D3 muj = {0.0, 0.0, 0.0};
-                    if constexpr (MODE != cgd::kModeIon) {
-                        const double4 mj = ldg256(p.mu + j);
-                        muj = {mj.x, mj.y, mj.z};
-                    }
-                    cgd::pair_accumulate<F, YUK, MODE, WHAT>(f, p.core, tab, d, r2, pi.w, pj.w, mui, muj, acc);
-                }
+                const bool pass = jc[u] >= 0 && r2 < p.rc2; // the exact, strict reference gate
+                npairs += pass ? 1u : 0u;
+                const double r2s = pass ? r2 : p.rc2_safe; // harmless in-range argument for rejected / absent pairs
+                cgd::D3 muj = {0.0, 0.0, 0.0};
+                if constexpr (MODE != cgd::kModeIon) muj = {mc[u].x, mc[u].y, mc[u].z};
+                cgd::pair_accumulate<F, YUK, MODE, WHAT>(f, p.core, tab, d, r2s, pi.w, pc[u].w, mui, muj, acc, pass);
+            }
+#pragma unroll
+            for (int u = 0; u < kIlp; u++) {
+                jc[u] = jn[u];
+                pc[u] = pn[u];
+                if constexpr (MODE != cgd::kModeIon) mc[u] = mn[u];
             }
         }
         __syncwarp();
@@ -234,7 +284,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
 
 inline size_t pair_smem_bytes(int table_doubles) {
     const int table_bytes = (table_doubles * 8 + 15) & ~15;
-    return (size_t)table_bytes + kWarpsPerCta * (32 * sizeof(float4) + kSlots * 32 * sizeof(unsigned int) + kSlots * sizeof(int));
+    return (size_t)table_bytes + kWarpsPerCta * (32 * sizeof(float4) + kSlots * 32 * sizeof(uint2));
 }
 
 template <class F, bool YUK, int MODE, int WHAT>

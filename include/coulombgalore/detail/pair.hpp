@@ -69,19 +69,21 @@ struct Accum {
 
 // One in-cutoff ordered pair (i <- j), d = r_i - r_j, r2 = |d|^2 < cutoff^2 already established by the caller.
 // Conventions: SURVEY.md 8b / oracle/harness.hpp.
+// `pass` = the pair is inside the cut-off.  The kernels evaluate branch-free (r2 must then be a harmless in-range
+// value when !pass): every contribution carries a scalar factor that is zeroed by a select.
 template <class F, bool YUK, int MODE, int WHAT>
 CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const D3 &d, double r2, double zi,
-                           double zj, const D3 &mui, const D3 &muj, Accum &acc) {
+                           double zj, const D3 &mui, const D3 &muj, Accum &acc, bool pass = true) {
     constexpr int ND = derivatives_needed(MODE, WHAT);
-    const Radial R = radial_terms<F, YUK, ND>(f, cp, r2, tab);
+    Radial R = radial_terms<F, YUK, ND>(f, cp, r2, tab);
     const double rinv2 = R.rinv * R.rinv;
     const double rinv3 = rinv2 * R.rinv;
-    const double ek3 = R.ek * rinv3; // exp(-kr) / r^3
+    const double ek3 = pass ? R.ek * rinv3 : 0.0; // exp(-kr) / r^3
 
     if (MODE == kModeIon) {
         // ion_potential core.hpp:268-280, ion_field :352-365, ion_ion_energy :501, ion_ion_force :630
         if (WHAT & (kWhatPotential | kWhatEnergy)) {
-            const double p = zj * R.rinv * R.s0 * R.ek;
+            const double p = pass ? zj * R.rinv * R.s0 * R.ek : 0.0;
             if (WHAT & kWhatPotential) acc.phi += p;
             if (WHAT & kWhatEnergy) acc.U += zi * p;
         }
@@ -134,7 +136,7 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, 
     // MODE == kModeMultipole: potential = ion_potential + dipole_potential, field = multipole_field :457-486 (quad = 0),
     // energy = multipole_multipole_energy :581-615, force = multipole_multipole_force :737-779, both with A = i,
     // B = j, r = r_j - r_i = -d and zero quadrupoles.
-    if (WHAT & kWhatPotential) acc.phi += zj * R.rinv * R.s0 * R.ek + mjd * ek3 * R.angcor;
+    if (WHAT & kWhatPotential) acc.phi += (pass ? zj * R.rinv * R.s0 * R.ek : 0.0) + mjd * ek3 * R.angcor;
     if (WHAT & kWhatField) {
         const double cd = (zj * R.angcor + 3.0 * mjd * rinv2 * R.totcor) * ek3;
         const double cm = -R.angcor * ek3;
@@ -153,7 +155,7 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, 
         }
         if (WHAT & kWhatForce) {
             const double t3 = 3.0 * R.totcor;
-            const double e4 = R.ek * rinv2 * rinv2; // exp(-kr)/r^4
+            const double e4 = ek3 * R.rinv; // exp(-kr)/r^4
             const double ar = R.angcor * R.r1;
             const double cd = (-zi * zj * ar + R.rinv * (t3 * (zi * mjd + zj * mid) - t3 * (5.0 * ab - mm) - ab * R.r3corr)) * e4;
             const double ci = (-zj * ar + t3 * mjd * R.rinv) * e4;

@@ -182,8 +182,8 @@ struct EwaldScreenedSrf {
         const double xq = eta * q;
         const double xm = xq - half_z_over_eta, xp = xq + half_z_over_eta;
         double ecm, Em, ecp, Ep; // erfc(x-), exp(-x-^2), erfc(x+)
-        erfc_and_gauss(xm, ecm, Em, tab);
-        erfc_and_gauss(xp, ecp, Ep, tab);
+        erfc_and_gauss<true>(xm, ecm, Em, tab);
+        erfc_and_gauss<false>(xp, ecp, Ep, tab);
         (void)Ep;
         const double P = ecp * exp_any(2.0 * zeta * q); // erfc(x+) exp(2 zeta q), as the reference forms it
         s[0] = 0.5 * (P + ecm);

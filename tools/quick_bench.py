@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Kernel-level timing of the BASELINE configs on one GPU (tuning aid; the judged numbers come from bench.py).
+usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,3,4,5s}  (5s = config 5 at n=128)"""
+import os, sys, statistics
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import coulombgalore_b200 as cg
+
+INF = float("inf")
+CONFIGS = {
+    "1": dict(pot=lambda: cg.qPotential(14, 3), n=16, a=1.75, seed=1001, pbc=False, mode=cg.MODE_ION, what=cg.ENERGY | cg.FORCE, falg=42),
+    "2w": dict(pot=lambda: cg.Wolf(12, 0.25), n=100, a=3.0, seed=1002, pbc=True, mode=cg.MODE_ION, what=cg.FORCE, falg=33),
+    "2f": dict(pot=lambda: cg.Fennell(12, 0.25), n=100, a=3.0, seed=1002, pbc=True, mode=cg.MODE_ION, what=cg.FORCE, falg=39),
+    "3": dict(pot=lambda: cg.ReactionField(12, 80, 1, False), n=64, a=3.0, seed=1003, pbc=True, mode=cg.MODE_DIPOLE, what=cg.ENERGY | cg.FIELD | cg.FORCE, falg=101),
+    "4s": dict(pot=lambda: cg.Ewald(10, 0.3, INF, 30.0), n=100, a=3.0, seed=1004, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=133),
+    "5s": dict(pot=lambda: cg.Splined().spline(cg.Poisson, 12, 4, 3), n=128, a=3.0, seed=1005, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=153),
+}
+
+def main():
+    names = sys.argv[1:] or ["1", "2w", "2f", "3", "4s", "5s"]
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream()
+    torch.cuda.set_stream(st)
+    for nm in names:
+        c = CONFIGS[nm]
+        N = c["n"] ** 3
+        ev = cg.BatchedEvaluator(c["pot"]())
+        ev.set_stream(st.cuda_stream)
+        arr = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(7)]
+        ev.generate_lattice_device(c["n"], c["a"], c["seed"], arr[0], arr[1], arr[2], arr[3], (arr[4], arr[5], arr[6]))
+        L = c["n"] * c["a"]
+        need_mu = c["mode"] != cg.MODE_ION
+        need_q = c["mode"] != cg.MODE_DIPOLE
+        ev.set_system_device(arr[0], arr[1], arr[2], arr[3] if need_q else None, (arr[4], arr[5], arr[6]) if need_mu else None, [L] * 3, c["pbc"])
+        f = torch.empty((N, 3), dtype=torch.float64, device=dev)
+        e = torch.empty((N, 3), dtype=torch.float64, device=dev)
+        sc = torch.zeros(2, dtype=torch.float64, device=dev)
+        pm, sm = [], []
+        for it in range(8):
+            ev.eval_device(c["mode"], c["what"], force=f, field=e if c["what"] & cg.FIELD else None, scalars=sc)
+            t = ev.timings()
+            if it >= 3:
+                pm.append(t["pair_ms"]); sm.append(t["sort_ms"])
+        pairs = sc[1].item()
+        p = statistics.median(pm)
+        cn = ev.counters()
+        print("cfg %-3s N=%8d pairs=%.4g  pair_kernel %.3f ms  sort %.3f ms  -> %.3e pairs/s  %.2f TF(F_alg=%d) %.1f%% of 37.2  [entries %d groups %d split %d]" %
+              (nm, N, pairs, p, statistics.median(sm), pairs / p * 1e3, pairs * c["falg"] / p * 1e3 / 1e12, c["falg"], 100 * pairs * c["falg"] / p * 1e3 / 37.2e12, cn["sorted_entries"], cn["groups"], cn["split"]), flush=True)
+        ev.close()
+
+if __name__ == "__main__":
+    main()
