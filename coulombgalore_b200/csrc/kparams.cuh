@@ -10,9 +10,22 @@ namespace cgb {
 
 namespace cgd = CoulombGalore::detail;
 
-constexpr int kWarpsPerCta = 8;
+// launch shape (overridable for tuning builds: make EXTRA_NVFLAGS="-DCG_WARPS=.. -DCG_MINB=.. -DCG_ILP=.. -DCG_SLOTS=..")
+#ifndef CG_WARPS
+#define CG_WARPS 8
+#endif
+#ifndef CG_MINB
+#define CG_MINB 2
+#endif
+#ifndef CG_ILP
+#define CG_ILP 2
+#endif
+#ifndef CG_SLOTS
+#define CG_SLOTS 40
+#endif
+constexpr int kWarpsPerCta = CG_WARPS;
 constexpr int kThreads = kWarpsPerCta * 32;
-constexpr int kSlots = 40; // candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase
+constexpr int kSlots = CG_SLOTS; // candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase
 
 // Spatially sorted system.  With periodic boundaries the arrays also hold the periodic images that lie within one
 // cut-off of the box ("ghost" entries, coordinates already shifted), so the pair kernel never applies a minimum

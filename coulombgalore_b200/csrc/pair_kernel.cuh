@@ -44,8 +44,8 @@ __device__ __forceinline__ double4 ldg256(const double4 *p) {
     return v;
 }
 
-template <int MODE> constexpr int min_blocks_per_sm() { return 2; }
-template <int MODE> constexpr int pairs_in_flight() { return MODE == cgd::kModeIon ? 2 : 1; }
+template <int MODE> constexpr int min_blocks_per_sm() { return CG_MINB; }
+template <int MODE> constexpr int pairs_in_flight() { return MODE == cgd::kModeIon ? CG_ILP : 1; }
 
 template <class F, bool YUK, int MODE, int WHAT>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<MODE>())
