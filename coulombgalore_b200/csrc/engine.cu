@@ -166,9 +166,14 @@ __global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int 
 }
 
 __global__ void gather_kernel(const __grid_constant__ SortParams sp, int n_sorted, const unsigned int *keys, double4 *pos,
-                              double4 *mu, float4 *pos32, int *orig) {
+                              double4 *mu, float4 *pos32, int *orig, double far) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_sorted) return;
+    if (k > n_sorted) return;
+    if (k == n_sorted) { // dummy entry far outside the system: chargeless, momentless, beyond every cut-off
+        pos[k] = make_double4(far, far, far, 0.0);
+        if (mu) mu[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+        return;
+    }
     const unsigned int key = keys[k];
     const int p = (int)(key / 27u);
     const int code = (int)(key - (unsigned int)p * 27u);
@@ -778,16 +783,26 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
 
     // ---- 4-5. scatter, deterministic order, gather ----
     CG_CUDA(h, h->keys.ensure((size_t)n_sorted));
-    CG_CUDA(h, h->pos.ensure((size_t)n_sorted));
+    CG_CUDA(h, h->pos.ensure((size_t)n_sorted + 1));
     const bool need_mu = mode != CG_MODE_ION;
-    if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)n_sorted));
+    if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)n_sorted + 1));
     CG_CUDA(h, h->pos32.ensure((size_t)n_sorted));
     CG_CUDA(h, h->orig.ensure((size_t)n_sorted));
     CG_CUDA(h, h->groups.ensure((size_t)n_groups + 1));
     CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
     bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, h->cell_start.p, h->keys.p);
     cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ncell, h->cell_start.p, h->keys.p);
-    gather_kernel<<<(n_sorted + 255) / 256, 256, 0, st>>>(sp, n_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p, h->orig.p);
+    double far_coord;
+    {
+        double span = 0.0, lo = 0.0;
+        for (int d = 0; d < 3; d++) {
+            span = std::max(span, sp.ntot[d] / sp.inv_cs[d]);
+            lo = std::min(lo, sp.lo[d] - sp.gw[d]);
+        }
+        far_coord = lo - 4.0 * span - 4.0 * std::min(rc, 1e9) - 1.0;
+    }
+    gather_kernel<<<(n_sorted + 256) / 256, 256, 0, st>>>(sp, n_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p, h->orig.p,
+                                                       far_coord);
     row_group_emit_kernel<<<(nrows_prim + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
     launches += 4;
     CG_CUDA(h, cudaGetLastError());
@@ -860,11 +875,11 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.slack = (float)(1e-4 + 1e-6 * nmax);
     }
     kp.rc2 = D.cutoff_squared;
-    kp.rc2_safe = D.cutoff_squared < 1e30 ? 0.25 * D.cutoff_squared : 1.0; // Plain: any moderate value is in range
     kp.core.inverse_cutoff = D.inverse_cutoff;
     kp.core.cutoff_squared = D.cutoff_squared;
     kp.core.kappa = D.inverse_debye_length;
     kp.n = n;
+    kp.dummy = n_sorted;
     CG_CUDA(h, h->item_energy.ensure((size_t)std::max(items, 1)));
     CG_CUDA(h, h->item_pairs.ensure((size_t)std::max(items, 1)));
     kp.item_energy = h->item_energy.p;

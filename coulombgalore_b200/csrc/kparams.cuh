@@ -31,8 +31,8 @@ constexpr int kSlots = CG_SLOTS; // candidate batches (of 32) whose per-lane hit
 // cut-off of the box ("ghost" entries, coordinates already shifted), so the pair kernel never applies a minimum
 // image: d = r_i - r_j on the stored coordinates.
 struct KParams {
-    const double4 *pos;   // x, y, z, charge            [n_sorted]
-    const double4 *mu;    // mu_x, mu_y, mu_z, 0        [n_sorted]  (may be null when no dipoles are needed)
+    const double4 *pos;   // x, y, z, charge            [n_sorted + 1]
+    const double4 *mu;    // mu_x, mu_y, mu_z, 0        [n_sorted + 1]  (may be null when no dipoles are needed)
     const float4 *pos32;  // position relative to the grid origin in fp32, w = |xyz|^2   [n_sorted]
     const int *orig;      // original particle index of a sorted entry               [n_sorted]
     const int *cell_start; // first sorted entry of each cell, x fastest             [ncell + 1]
@@ -45,9 +45,9 @@ struct KParams {
     double rc2_m;         // squared cut-off plus the rounding margin of the three-FFMA prefilter test
     float slack;          // slack in cell units for fp32 cell-range rounding
     double rc2;           // exact gate: r2 < cutoff_squared (strict, reference core.hpp:354 etc.)
-    double rc2_safe;      // cutoff_squared / 4 (1 for Plain): the r2 fed to the branch-free arithmetic for rejected pairs
     cgd::CoreParams core;
     int n;                // number of (original) particles
+    int dummy;            // index of the far-away dummy entry appended to pos/mu (gathered by lanes that ran dry)
     // outputs, indexed by original particle index; with split > 1 they are [split][n] partial buffers
     double *force, *field, *potential;
     double *item_energy;              // [items] sum_j u_ij over the item's pairs (not yet halved)

@@ -20,6 +20,8 @@
 //     (sorted order keeps the neighbourhood resident) and accumulates into the lane's registers: no atomics, no
 //     cross-lane reduction for per-particle outputs; energies/pair counts are reduced once per item.
 #pragma once
+#include <type_traits>
+
 #include "kparams.cuh"
 
 namespace cgb {
@@ -104,65 +106,74 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     cgd::Accum acc;
     unsigned int npairs = 0;
 
-    // iterator over the candidate runs (all warp-uniform except jb/je, which hold one row's run per lane)
+    // ---- iterator over the candidate batches (warp-uniform; jb/je hold one cell row's run per lane) ----
     int row_next = 0;       // next chunk of 32 rows to expand
     unsigned have = 0;      // lanes whose run of the current chunk is still unvisited
     int jb = 0, je = 0;     // this lane's run in the current chunk
     int cur_j = 0, cur_end = 0;
-    bool more = true;
-
-    while (more) {
-        // ================= PHASE 1: prefilter up to kSlots batches of 32 candidates into bit masks =================
-        int nb = 0, cnt = 0, qn = 0;
-        while (nb < kSlots) {
-            while (cur_j >= cur_end) { // next run
-                if (have == 0) {       // next 32 rows
-                    if (row_next >= nrows) {
-                        more = false;
-                        break;
-                    }
-                    const int rr = row_next + lane;
-                    row_next += 32;
-                    jb = je = 0;
-                    if (rr < nrows) {
-                        const int rzi = rr / nyr;
-                        const int ry = cy0 + (rr - rzi * nyr), rz = cz0 + rzi;
-                        const float ylo = (float)ry * p.cs_y, zlo = (float)rz * p.cs_z;
-                        const float dy = fmaxf(0.0f, fmaxf(ylo - ymax, ymin - (ylo + p.cs_y)));
-                        const float dz = fmaxf(0.0f, fmaxf(zlo - zmax, zmin - (zlo + p.cs_z)));
-                        const float w2 = rcm * rcm - (dy * dy + dz * dz);
-                        if (w2 > 0.0f) { // rows farther than the cut-off from the box in the y-z plane hold no neighbour
-                            const float w = sqrtf(w2);
-                            const int cxa = clampi((int)floorf((xmin - w) * p.inv_cs_x - p.slack), 0, p.nx - 1);
-                            const int cxb = clampi((int)floorf((xmax + w) * p.inv_cs_x + p.slack), 0, p.nx - 1);
-                            const int rowbase = (rz * p.ny + ry) * p.nx;
-                            jb = p.cell_start[rowbase + cxa];
-                            je = p.cell_start[rowbase + cxb + 1];
-                            if (split > 1) { // j-split: this slice's share of the run
-                                const long long len = je - jb;
-                                const int a = jb + (int)(len * slice / split), b = jb + (int)(len * (slice + 1) / split);
-                                jb = a;
-                                je = b;
-                            }
+    auto next_batch = [&](int &j0, int &n) -> bool {
+        while (cur_j >= cur_end) { // next run
+            if (have == 0) {       // next 32 rows
+                if (row_next >= nrows) return false;
+                const int rr = row_next + lane;
+                row_next += 32;
+                jb = je = 0;
+                if (rr < nrows) {
+                    const int rzi = rr / nyr;
+                    const int ry = cy0 + (rr - rzi * nyr), rz = cz0 + rzi;
+                    const float ylo = (float)ry * p.cs_y, zlo = (float)rz * p.cs_z;
+                    const float dy = fmaxf(0.0f, fmaxf(ylo - ymax, ymin - (ylo + p.cs_y)));
+                    const float dz = fmaxf(0.0f, fmaxf(zlo - zmax, zmin - (zlo + p.cs_z)));
+                    const float w2 = rcm * rcm - (dy * dy + dz * dz);
+                    if (w2 > 0.0f) { // rows farther than the cut-off from the box in the y-z plane hold no neighbour
+                        const float w = sqrtf(w2);
+                        const int cxa = clampi((int)floorf((xmin - w) * p.inv_cs_x - p.slack), 0, p.nx - 1);
+                        const int cxb = clampi((int)floorf((xmax + w) * p.inv_cs_x + p.slack), 0, p.nx - 1);
+                        const int rowbase = (rz * p.ny + ry) * p.nx;
+                        jb = p.cell_start[rowbase + cxa];
+                        je = p.cell_start[rowbase + cxb + 1];
+                        if (split > 1) { // j-split: this slice's share of the run
+                            const long long len = je - jb;
+                            const int a = jb + (int)(len * slice / split), b = jb + (int)(len * (slice + 1) / split);
+                            jb = a;
+                            je = b;
                         }
                     }
-                    have = __ballot_sync(full, je > jb);
-                    continue;
                 }
-                const int l = __ffs(have) - 1;
-                have &= have - 1;
-                cur_j = __shfl_sync(full, jb, l);
-                cur_end = __shfl_sync(full, je, l);
+                have = __ballot_sync(full, je > jb);
+                continue;
             }
-            if (!more) break;
-            const int j0 = cur_j;
-            const int n = min(32, cur_end - j0);
-            cur_j += 32;
-            float4 c = make_float4(0.0f, 0.0f, 0.0f, INFINITY); // sentinel: |c|^2 = inf never passes
-            if (lane < n) c = p.pos32[j0 + lane];
+            const int l = __ffs(have) - 1;
+            have &= have - 1;
+            cur_j = __shfl_sync(full, jb, l);
+            cur_end = __shfl_sync(full, je, l);
+        }
+        j0 = cur_j;
+        n = min(32, cur_end - cur_j);
+        cur_j += 32;
+        return true;
+    };
+    const float4 sentinel = make_float4(0.0f, 0.0f, 0.0f, INFINITY); // |c|^2 = inf never passes
+    // software pipeline: the coordinates of the NEXT batch are in flight while the current one is tested
+    int nj0 = 0, nn = 0;
+    bool nvalid = next_batch(nj0, nn);
+    float4 cpre = sentinel;
+    if (nvalid && lane < nn) cpre = p.pos32[nj0 + lane];
+
+    while (nvalid) {
+        // ================= PHASE 1: prefilter up to kSlots batches of 32 candidates into bit masks =================
+        int nb = 0, cnt = 0, qn = 0;
+        while (nb < kSlots && nvalid) {
+            const int j0 = nj0, n = nn;
+            const float4 c = cpre;
+            nvalid = next_batch(nj0, nn);
+            cpre = sentinel;
+            if (nvalid && lane < nn) cpre = p.pos32[nj0 + lane];
             __syncwarp();
             stage[lane] = c;
             __syncwarp();
+            // candidate t0+u lands in bit t0 + 7 - u: the sign bit of (v - thr) is funnel-shifted into the mask
+            // (one ALU instruction per test; NaN from the inf sentinel has a clear sign bit, i.e. does not pass)
             unsigned m = 0;
 #pragma unroll 1
             for (int t0 = 0; t0 < n; t0 += 8) {
@@ -171,24 +182,24 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                 for (int u = 0; u < 8; u++) {
                     const float4 cj = stage[t0 + u];
                     const float v = fmaf(m2z, cj.z, fmaf(m2y, cj.y, fmaf(m2x, cj.x, cj.w)));
-                    if (v < thr) m8 |= 1u << u;
+                    m8 = __funnelshift_l(__float_as_uint(v - thr), m8, 1);
                 }
                 m |= m8 << t0;
             }
             const unsigned rel_self = (unsigned)(i - j0); // the lane's own entry is not a neighbour
-            if (rel_self < 32u) m &= ~(1u << rel_self);
+            if (rel_self < 32u) m &= ~(1u << (rel_self ^ 7u));
             if (m != 0u) hits[(qn++) * 32] = make_uint2(m, (unsigned)j0);
             cnt += __popc(m);
             nb++;
         }
         __syncwarp();
         // ================= PHASE 2: evaluate the recorded pairs in FP64 =================
-        // kIlp independent pairs per lane and iteration, the gathers of the NEXT iteration already in flight, and no
-        // branch inside the arithmetic (the exact gate becomes a select): the FP64 dependency chains of the
-        // pairs interleave and the L2/L1 latency of the gather hides behind them.
+        // kIlp independent pairs per lane and step, the gathers of the NEXT step already in flight (two register
+        // sets used in ping-pong), and no branch inside the arithmetic (the exact gate becomes a select).
         // The lane's cursor: `cur` = unvisited hits of the current list entry, `base` = its first candidate index.
-        // The next entry is fetched as soon as the current one is exhausted, i.e. one pop ahead of its first use,
-        // so the shared-memory latency hides behind the pair arithmetic; pop() itself is straight-line code.
+        // The next entry is fetched as soon as the current one is exhausted, one pop ahead of its first use, so the
+        // shared-memory latency hides behind the pair arithmetic; pop() itself is straight-line code.  A lane that
+        // has run dry gathers the far-away dummy entry p.dummy (finite arithmetic, contribution zeroed).
         int slot = 0;
         unsigned cur = 0u;
         int base = 0;
@@ -197,10 +208,11 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             cur = e0.x;
             base = (int)e0.y;
         }
-        auto pop = [&]() -> int { // next recorded neighbour of this lane, or -1
-            const bool has = cnt > 0;
-            const int j = has ? base + (__ffs(cur) - 1) : -1;
-            cur &= cur - 1u; // (0 stays 0)
+        auto pop = [&](bool &has) -> int {
+            has = cnt > 0;
+            const int b = 31 - __clz((int)cur); // highest set bit (-1 when empty)
+            const int j = has ? base + (b ^ 7) : p.dummy;
+            cur &= ~(has ? (1u << b) : 0u);
             cnt -= has ? 1 : 0;
             if (cur == 0u && cnt > 0) {
                 const uint2 e = hits[(++slot) * 32];
@@ -209,40 +221,40 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             }
             return j;
         };
-        int jc[kIlp];
-        double4 pc[kIlp], mc[kIlp];
-#pragma unroll
-        for (int u = 0; u < kIlp; u++) {
-            jc[u] = pop();
-            pc[u] = ldg256(p.pos + (jc[u] >= 0 ? jc[u] : i));
-            if constexpr (MODE != cgd::kModeIon) mc[u] = ldg256(p.mu + (jc[u] >= 0 ? jc[u] : i));
-        }
-        while (__any_sync(full, jc[0] >= 0)) {
-            int jn[kIlp];
-            double4 pn[kIlp], mn[kIlp];
+        bool hh[2][kIlp];
+        double4 pp[2][kIlp], mm[2][kIlp];
+        auto fetch = [&](auto S) {
+            constexpr int s = decltype(S)::value;
 #pragma unroll
             for (int u = 0; u < kIlp; u++) {
-                jn[u] = pop();
-                pn[u] = ldg256(p.pos + (jn[u] >= 0 ? jn[u] : i));
-                if constexpr (MODE != cgd::kModeIon) mn[u] = ldg256(p.mu + (jn[u] >= 0 ? jn[u] : i));
+                const int j = pop(hh[s][u]);
+                pp[s][u] = ldg256(p.pos + j);
+                if constexpr (MODE != cgd::kModeIon) mm[s][u] = ldg256(p.mu + j);
             }
+        };
+        auto compute = [&](auto S) {
+            constexpr int s = decltype(S)::value;
 #pragma unroll
             for (int u = 0; u < kIlp; u++) {
-                const cgd::D3 d = {pi.x - pc[u].x, pi.y - pc[u].y, pi.z - pc[u].z};
+                const cgd::D3 d = {pi.x - pp[s][u].x, pi.y - pp[s][u].y, pi.z - pp[s][u].z};
                 const double r2 = d.x * d.x + d.y * d.y + d.z * d.z;
-                const bool pass = jc[u] >= 0 && r2 < p.rc2; // the exact, strict reference gate
+                const bool pass = hh[s][u] && r2 < p.rc2; // the exact, strict reference gate
                 npairs += pass ? 1u : 0u;
-                const double r2s = pass ? r2 : p.rc2_safe; // harmless in-range argument for rejected / absent pairs
                 cgd::D3 muj = {0.0, 0.0, 0.0};
-                if constexpr (MODE != cgd::kModeIon) muj = {mc[u].x, mc[u].y, mc[u].z};
-                cgd::pair_accumulate<F, YUK, MODE, WHAT>(f, p.core, tab, d, r2s, pi.w, pc[u].w, mui, muj, acc, pass);
+                if constexpr (MODE != cgd::kModeIon) muj = {mm[s][u].x, mm[s][u].y, mm[s][u].z};
+                cgd::pair_accumulate<F, YUK, MODE, WHAT>(f, p.core, tab, d, r2, pi.w, pp[s][u].w, mui, muj, acc, pass);
             }
-#pragma unroll
-            for (int u = 0; u < kIlp; u++) {
-                jc[u] = jn[u];
-                pc[u] = pn[u];
-                if constexpr (MODE != cgd::kModeIon) mc[u] = mn[u];
-            }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        fetch(I0{});
+        for (;;) {
+            if (!__any_sync(full, hh[0][0])) break;
+            fetch(I1{});
+            compute(I0{});
+            if (!__any_sync(full, hh[1][0])) break;
+            fetch(I0{});
+            compute(I1{});
         }
         __syncwarp();
     }

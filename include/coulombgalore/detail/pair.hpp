@@ -34,11 +34,20 @@ struct Radial {
     double rinv, r1, q, s0, ek, angcor, unicor, totcor, r3corr;
 };
 
-template <class F, bool YUK, int ND> CG_HD Radial radial_terms(const F &f, const CoreParams &cp, double r2, const double *tab) {
+// ANGCOR_ONLY: the caller needs nothing but angcor (ion field / force without screening) and the functor has a closed form
+template <class F, bool YUK, int ND, bool ANGCOR_ONLY = false>
+CG_HD Radial radial_terms(const F &f, const CoreParams &cp, double r2, const double *tab) {
     Radial R;
     R.rinv = rsqrt_pos(r2);
     R.r1 = r2 * R.rinv;
     R.q = R.r1 * cp.inverse_cutoff;
+    if constexpr (ANGCOR_ONLY) {
+        R.s0 = 0.0;
+        R.ek = 1.0;
+        R.angcor = f.angcor(R.q, tab);
+        R.unicor = R.totcor = R.r3corr = 0.0;
+        return R;
+    }
     double s[4] = {0.0, 0.0, 0.0, 0.0};
     f.template eval<ND>(R.q, s, tab);
     R.s0 = s[0];
@@ -75,7 +84,8 @@ template <class F, bool YUK, int MODE, int WHAT>
 CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const D3 &d, double r2, double zi,
                            double zj, const D3 &mui, const D3 &muj, Accum &acc, bool pass = true) {
     constexpr int ND = derivatives_needed(MODE, WHAT);
-    Radial R = radial_terms<F, YUK, ND>(f, cp, r2, tab);
+    constexpr bool kAngcorOnly = F::kHasAngcor && !YUK && MODE == kModeIon && (WHAT & (kWhatEnergy | kWhatPotential)) == 0;
+    Radial R = radial_terms<F, YUK, ND, kAngcorOnly>(f, cp, r2, tab);
     const double rinv2 = R.rinv * R.rinv;
     const double rinv3 = rinv2 * R.rinv;
     const double ek3 = pass ? R.ek * rinv3 : 0.0; // exp(-kr) / r^3

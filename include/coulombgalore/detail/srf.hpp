@@ -22,11 +22,17 @@ namespace detail {
 // specfun.hpp (device only; the host evaluates libm directly)
 enum { kTableNone = 0, kTableSpline = 1, kTableErfc = 2 };
 
+// defaults every functor inherits
+struct SrfDefaults {
+    // true: the functor offers angcor(q, tab) = S - q S' in closed form (cheaper than S and S' separately)
+    static constexpr bool kHasAngcor = false;
+};
+
 // 2/sqrt(pi); the reference forms it as 2/(2*sqrt(atan(1))) (e.g. wolf.hpp:36), equal to within one ulp
 constexpr double kTwoOverSqrtPi = 1.1283791670955125739;
 
 // ---------------------------------------------------------------------------------------------------------------
-struct PlainSrf { // plain.hpp:47-50
+struct PlainSrf : SrfDefaults { // plain.hpp:47-50
     static constexpr int kTable = kTableNone;
     CG_HD PlainSrf() {}
     CG_HD explicit PlainSrf(const cg_scheme_desc &) {}
@@ -38,7 +44,7 @@ struct PlainSrf { // plain.hpp:47-50
     }
 };
 
-struct ReactionFieldSrf { // reactionfield.hpp:60-73: S = 1 + a q^3 - b q
+struct ReactionFieldSrf : SrfDefaults { // reactionfield.hpp:60-73: S = 1 + a q^3 - b q
     static constexpr int kTable = kTableNone;
     double a, b;
     CG_HD ReactionFieldSrf() : a(0), b(0) {}
@@ -52,7 +58,7 @@ struct ReactionFieldSrf { // reactionfield.hpp:60-73: S = 1 + a q^3 - b q
     }
 };
 
-struct FanourgakisSrf { // fanourgakis.hpp:49-61
+struct FanourgakisSrf : SrfDefaults { // fanourgakis.hpp:49-61
     static constexpr int kTable = kTableNone;
     CG_HD FanourgakisSrf() {}
     CG_HD explicit FanourgakisSrf(const cg_scheme_desc &) {}
@@ -77,7 +83,7 @@ template <int ND> CG_HD void jet_mul(double *c, const double *g) { // c <- c * g
     c[0] = c[0] * g[0];
 }
 
-template <int ORDER> struct QPotentialSrf {
+template <int ORDER> struct QPotentialSrf : SrfDefaults {
     static constexpr int kTable = kTableNone;
     int order;
     CG_HD QPotentialSrf() : order(ORDER) {}
@@ -119,8 +125,9 @@ template <int ORDER> struct QPotentialSrf {
 // erfc family.  x = eta q, E = exp(-x^2), k1 = 2 eta / sqrt(pi); c = erfc(eta), e = exp(-eta^2), c2 = c + k1 e.
 enum ErfcKind { kWolf, kFennell, kZeroDipole, kZahn, kEwaldT, kEwaldPlain };
 
-template <int KIND> struct ErfcFamilySrf {
+template <int KIND> struct ErfcFamilySrf : SrfDefaults {
     static constexpr int kTable = kTableErfc;
+    static constexpr bool kHasAngcor = true;
     double eta, eta2, k1, c, e, c2, invF0;
     CG_HD ErfcFamilySrf() : eta(0), eta2(0), k1(0), c(0), e(0), c2(0), invF0(1) {}
     CG_HD explicit ErfcFamilySrf(const cg_scheme_desc &d)
@@ -166,11 +173,24 @@ template <int KIND> struct ErfcFamilySrf {
             if (ND >= 3) s[3] = g3;
         }
     }
+    // S - q S' with the q-linear and q-polynomial terms of S and q S' cancelled analytically: what ion fields and
+    // forces need (core.hpp:352-365 with kappa = 0).  erfc(x) + (2/sqrt(pi)) x exp(-x^2) is common to all kinds.
+    CG_HD double angcor(double q, const double *tab) const {
+        const double x = eta * q;
+        double E, ec;
+        erfc_and_gauss(x, ec, E, tab);
+        const double g = ec + (q * k1) * E;
+        if (KIND == kWolf || KIND == kEwaldPlain) return g;
+        if (KIND == kFennell) return g - (q * q) * c2;
+        if (KIND == kZeroDipole) return g - (q * q) * (q * c2);
+        if (KIND == kZahn) return g + (q * q) * c2;
+        return (g - (c + k1 * e)) * invF0; // kEwaldT
+    }
 };
 
 // Ewald with Debye screening (zeta = R_c / lambda_D > 0), ewald.hpp:175-195.
 //   S = 1/2 [ erfc(x+) e^{2 zeta q} + erfc(x-) ],  x+- = eta q +- zeta/(2 eta)
-struct EwaldScreenedSrf {
+struct EwaldScreenedSrf : SrfDefaults {
     static constexpr int kTable = kTableErfc;
     double eta, eta2, k1, zeta, zeta2, zeta3, half_z_over_eta, z_over_eta, z2_over_eta2;
     CG_HD EwaldScreenedSrf() : eta(0), eta2(0), k1(0), zeta(0), zeta2(0), zeta3(0), half_z_over_eta(0), z_over_eta(0), z2_over_eta2(0) {}
@@ -195,7 +215,7 @@ struct EwaldScreenedSrf {
 
 // ---------------------------------------------------------------------------------------------------------------
 // Poisson (poisson.hpp:119-220), run-time C and D.  q~ = q, or (1 - e^{2 kappa* q}) * yukawa_denom when screened.
-struct PoissonSrf {
+struct PoissonSrf : SrfDefaults {
     static constexpr int kTable = kTableNone;
     int C, D, yukawa;
     double rk, denom, binomCDC;
@@ -258,7 +278,7 @@ struct PoissonSrf {
 // Horner in dz = q - knot (splined.hpp:167-176).  Packed layout in `tab` (global memory on the device, staged to
 // shared memory by the kernels; a host pointer for the scheme classes):
 //   for k in 0..3:  knots[k][0..n_k)  at tab + koff[k],   coefficients[k][6*(n_k-1)]  at tab + coff[k]
-struct SplineSrf {
+struct SplineSrf : SrfDefaults {
     static constexpr int kTable = kTableSpline;
     int n[4], koff[4], coff[4], total;
     const double *tab;
