@@ -1,0 +1,58 @@
+// coulombgalore/batched.hpp -- the batched host entry point the reference lacks: positions, charges and dipoles in
+// SoA buffers, evaluated for ALL pairs within the cut-off by the sm_100a kernels behind the C ABI (include/cg_b200.h).
+//
+//     CoulombGalore::Wolf pot(12.0, 0.25);                          // exactly as with the reference
+//     CoulombGalore::BatchedEvaluator gpu(pot);                     // cg_create(pot.descriptor())
+//     gpu.set_system(n, x, y, z, q, nullptr, nullptr, nullptr, box, true);
+//     gpu.eval(CG_MODE_ION, CG_FORCE, force, nullptr, nullptr, nullptr, &pairs);   // sum_j ion_ion_force(z_j, z_i, r_i - r_j)
+//
+// Link with -lcg_b200 (coulombgalore_b200/libcg_b200.so).  Errors throw std::runtime_error carrying cg_last_error().
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+#include "../cg_b200.h"
+#include "core.hpp"
+
+namespace CoulombGalore {
+
+class BatchedEvaluator {
+    cg_handle *h_ = nullptr;
+    void check(int rc, const char *where) const {
+        if (rc != CG_OK) throw std::runtime_error(std::string(where) + ": " + cg_last_error(h_));
+    }
+
+  public:
+    explicit BatchedEvaluator(const SchemeBase &scheme, int device = -1) {
+        const int rc = cg_create(&scheme.descriptor(), device, &h_);
+        if (rc != CG_OK) throw std::runtime_error(std::string("cg_create: ") + cg_last_error(nullptr));
+    }
+    ~BatchedEvaluator() { cg_destroy(h_); }
+    BatchedEvaluator(const BatchedEvaluator &) = delete;
+    BatchedEvaluator &operator=(const BatchedEvaluator &) = delete;
+
+    cg_handle *handle() const { return h_; }
+    void set_stream(void *cuda_stream) { check(cg_set_stream(h_, cuda_stream), "cg_set_stream"); }
+    void set_shard(int rank, int nranks) { check(cg_set_shard(h_, rank, nranks), "cg_set_shard"); }
+    /** host SoA buffers; q / mu* may be null (all zero); box is read when pbc */
+    void set_system(int64_t n, const double *x, const double *y, const double *z, const double *q, const double *mux, const double *muy,
+                    const double *muz, const double box[3], bool pbc) {
+        check(cg_set_system(h_, n, x, y, z, q, mux, muy, muz, box, pbc ? 1 : 0), "cg_set_system");
+    }
+    /** device SoA buffers (zero copy) */
+    void set_system_device(int64_t n, const double *x, const double *y, const double *z, const double *q, const double *mux,
+                           const double *muy, const double *muz, const double box[3], bool pbc) {
+        check(cg_set_system_device(h_, n, x, y, z, q, mux, muy, muz, box, pbc ? 1 : 0), "cg_set_system_device");
+    }
+    /** host outputs: force[3n], field[3n], potential[n] (any may be null), total energy, ordered in-cutoff pair count */
+    void eval(int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
+        check(cg_eval(h_, mode, what, force, field, potential, energy, pairs), "cg_eval");
+    }
+    /** device outputs; scalars[0] = U, scalars[1] = pair count; asynchronous on the handle's stream */
+    void eval_device(int mode, int what, double *force, double *field, double *potential, double *scalars) {
+        check(cg_eval_device(h_, mode, what, force, field, potential, scalars), "cg_eval_device");
+    }
+};
+
+} // namespace CoulombGalore

@@ -126,14 +126,16 @@ inline int make_poisson(double cutoff, int C, int D, double debye_length, cg_sch
     return CG_OK;
 }
 
-inline int make_qpotential(double cutoff, int order, bool fixed5, cg_scheme_desc &d) { // qpotential.hpp:205-213, 253-261
+// fixed_order_chi: qPotentialFixedOrder<order> sets the order-5 value of chi whatever its order (qpotential.hpp:212),
+// qPotential(cutoff, order) leaves chi = 0 (qpotential.hpp:260)
+inline int make_qpotential(double cutoff, int order, bool fixed_order_chi, cg_scheme_desc &d) { // qpotential.hpp:205-213, 253-261
     if (order < 0) return CG_ERR_INVALID;
     d = desc_base(CG_QPOTENTIAL, cutoff, kInfinity);
-    d.order = fixed5 ? 5 : order;
+    d.order = order;
     d.self_energy_prefactor[0] = -0.5;
     d.self_energy_prefactor[1] = -0.5;
     finish_T0(d);
-    d.chi = fixed5 ? -86459.0 * std::acos(-1.0) * cutoff * cutoff / 235620.0 : 0.0;
+    d.chi = fixed_order_chi ? -86459.0 * std::acos(-1.0) * cutoff * cutoff / 235620.0 : 0.0;
     return CG_OK;
 }
 

@@ -14,27 +14,8 @@ INF = float("inf")
 
 def zoo():
     """name -> (product scheme factory, oracle params): every scheme of the reference, incl. the core-Yukawa variants."""
-    return {
-        "plain": (lambda: cg.Plain(), O.params(O.PLAIN)),
-        "plain_yukawa": (lambda: cg.Plain(23.0), O.params(O.PLAIN, debye_length=23.0)),
-        "reactionfield": (lambda: cg.ReactionField(12, 80, 1, False), O.params(O.REACTIONFIELD, cutoff=12, eps_rf=80, eps_r=1, shifted=False)),
-        "reactionfield_shifted": (lambda: cg.ReactionField(12, 80, 1, True), O.params(O.REACTIONFIELD, cutoff=12, eps_rf=80, eps_r=1, shifted=True)),
-        "poisson43": (lambda: cg.Poisson(12, 4, 3), O.params(O.POISSON, cutoff=12, C_=4, D=3)),
-        "poisson33_yukawa": (lambda: cg.Poisson(12, 3, 3, 30.0), O.params(O.POISSON, cutoff=12, C_=3, D=3, debye_length=30.0)),
-        "poisson10": (lambda: cg.Poisson(12, 1, 0), O.params(O.POISSON, cutoff=12, C_=1, D=0)),
-        "poisson1m1": (lambda: cg.Poisson(12, 1, -1), O.params(O.POISSON, cutoff=12, C_=1, D=-1)),
-        "qpotential3": (lambda: cg.qPotential(14, 3), O.params(O.QPOTENTIAL, cutoff=14, order=3)),
-        "qpotential4": (lambda: cg.qPotential(12, 4), O.params(O.QPOTENTIAL, cutoff=12, order=4)),
-        "qpotential5_fixed": (lambda: cg.qPotentialFixedOrder5(12), O.params(O.QPOTENTIAL5, cutoff=12)),
-        "fanourgakis": (lambda: cg.Fanourgakis(12), O.params(O.FANOURGAKIS, cutoff=12)),
-        "wolf": (lambda: cg.Wolf(12, 0.25), O.params(O.WOLF, cutoff=12, alpha=0.25)),
-        "fennell": (lambda: cg.Fennell(12, 0.25), O.params(O.FENNELL, cutoff=12, alpha=0.25)),
-        "zerodipole": (lambda: cg.ZeroDipole(12, 0.25), O.params(O.ZERODIPOLE, cutoff=12, alpha=0.25)),
-        "zahn": (lambda: cg.Zahn(12, 0.25), O.params(O.ZAHN, cutoff=12, alpha=0.25)),
-        "ewald": (lambda: cg.Ewald(10, 0.3), O.params(O.EWALD, cutoff=10, alpha=0.3)),
-        "ewald_screened": (lambda: cg.Ewald(10, 0.3, INF, 30.0), O.params(O.EWALD, cutoff=10, alpha=0.3, debye_length=30.0)),
-        "ewaldt": (lambda: cg.EwaldTruncated(12, 0.25), O.params(O.EWALDT, cutoff=12, alpha=0.25)),
-    }
+    from zoo import ZOO, oracle_params
+    return {k: ((lambda cls=v[1], args=v[2]: getattr(cg, cls)(*args)), oracle_params(k)) for k, v in ZOO.items()}
 
 
 def splined_pair(name, kind):

@@ -1,0 +1,85 @@
+"""The C-ABI library loads on a machine without a GPU, exports every symbol include/cg_b200.h declares, lays out
+cg_scheme_desc as ctypes does, refuses to run without a device, and validates its arguments (no compute here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import coulombgalore_b200 as cg
+from coulombgalore_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "cg_b200.h")
+
+
+def declared_functions():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_every_declared_symbol_is_exported():
+    names = declared_functions()
+    assert len(names) >= 30
+    lib = C.CDLL(_capi.LIB_PATH)
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_capi.EXPORTED) == names  # the ctypes binding covers the whole header
+
+
+def test_descriptor_layout_matches_the_header():
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "cg_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(cg_scheme_desc),' \
+          ' offsetof(cg_scheme_desc, cutoff), offsetof(cg_scheme_desc, poisson_w), offsetof(cg_scheme_desc, spline_knots), offsetof(cg_scheme_desc, spline_c));return 0;}'
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        out = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
+    S = _capi.SchemeDesc
+    assert out == [C.sizeof(S), S.cutoff.offset, S.poisson_w.offset, S.spline_knots.offset, S.spline_c.offset]
+
+
+def test_header_is_plain_c():
+    """No C++ or torch types cross the boundary: the header compiles as C99 with -pedantic."""
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write('#include "cg_b200.h"\nint main(void){return 0;}\n')
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                               os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+
+
+def test_constructors_validate_like_the_reference():
+    for bad in ((0, 3), (3, -2), (3, 0), (2, -1), (8, 6)):  # poisson.hpp:81-86 (+ the overflow / recursion cases of SURVEY.md A7)
+        with pytest.raises(ValueError):
+            cg.Poisson(12.0, *bad)
+    assert cg.Poisson(12.0, 1, -1).short_range_function(0.3) == 1.0
+    d = cg.Ewald(10.0, 0.3, cg.infinity, 30.0).desc
+    assert d.inverse_debye_length == 0.0 and d.zeta == pytest.approx(1.0 / 3.0)  # base kappa stays 0 (ewald.hpp:131)
+    assert cg.EwaldTruncated(12.0, 0.25, cg.infinity, 5.0).desc.inverse_debye_length == 0.0  # ewald_truncated.hpp:48
+    assert cg.Plain().cutoff == pytest.approx(np.sqrt(np.finfo(float).max))  # plain.hpp:38
+
+
+def test_splined_descriptor_from_host_tables():
+    s = cg.Splined().spline(cg.Poisson, 12.0, 4, 3)
+    assert s.numKnots() == [3, 4, 2, 2] and s.scheme == _capi.POISSON and s.desc.functor == _capi.SPLINE  # SURVEY.md a33; :1037-1038
+    q = np.array([0.25, 0.5, 0.75])
+    assert np.allclose(s.srf(q)[0], cg.Poisson(12.0, 4, 3).srf(q)[0], atol=1e-3)
+    with pytest.raises(ValueError):  # knots must ascend
+        t = s.tables()
+        t[0] = (t[0][0][::-1].copy(), t[0][1])
+        cg.Splined().spline_from_tables(cg.Poisson(12.0, 4, 3), t)
+
+
+@pytest.mark.skipif(cg.device_count() > 0, reason="needs a machine WITHOUT a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(cg.CgError) as e:
+        cg.BatchedEvaluator(cg.Wolf(12.0, 0.25))
+    assert e.value.rc == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_missing_library_fails_loudly():
+    code = "import os; os.environ['CG_B200_LIB']='/nonexistent/libcg_b200.so'; import coulombgalore_b200"
+    r = subprocess.run(["python", "-c", code], cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode != 0 and "is missing" in r.stderr
