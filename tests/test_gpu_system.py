@@ -1,0 +1,166 @@
+"""GPU tests beyond per-scheme parity: golden fixtures (no oracle library needed), edge cases, sharding, determinism and
+size-independent properties at the full BASELINE size (N = 10^6)."""
+import os
+
+import numpy as np
+import pytest
+
+import coulombgalore_b200 as cg
+from oracle import oracle as O
+
+from parity import TOL, compare, run_case, zoo
+from zoo import oracle_params
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"))
+ALL = cg.ENERGY | cg.FORCE | cg.FIELD | cg.POTENTIAL
+
+
+def ok(errs):
+    bad = {k: v for k, v in errs.items() if not (v <= 1.0)}
+    assert not bad, errs
+
+
+@pytest.mark.parametrize("case", sorted({k.split("/")[1] for k in GOLD.files if k.startswith("batch/")}))
+def test_against_golden_batches_of_the_reference(case):
+    """The committed outputs of the UNMODIFIED reference loop (tests/golden/make_golden.py); 6^3 lattice, L = 18 < 2 R_c,
+    so periodic cases exercise several images of the same particle inside the cut-off."""
+    name, mode, pbc = case.rsplit("_mode", 1)[0], int(case.split("_mode")[1][0]), case.endswith("pbc1")
+    lat = GOLD["lattice/n6_a3_seed31337"]
+    x, y, z, q, mu = lat[0].copy(), lat[1].copy(), lat[2].copy(), lat[3].copy(), (lat[4].copy(), lat[5].copy(), lat[6].copy())
+    ev = cg.BatchedEvaluator(zoo()[name][0]())
+    ev.set_system(x, y, z, q, mu, [18.0] * 3, pbc)
+    g = ev.eval(mode, ALL)
+    sc = GOLD["batch/%s/scalars" % case]
+    ref = dict(energy=sc[0], energy_abs=sc[1], pairs=int(sc[2]))
+    for f in ("force", "field", "potential", "force_scale", "field_scale", "potential_scale"):
+        ref[f] = GOLD["batch/%s/%s" % (case, f)]
+    ok(compare(g, ref, ALL))
+
+
+def test_edge_cases_empty_single_ragged(oracle_kind):
+    pot = cg.Wolf(12.0, 0.25)
+    osch = O.Scheme(oracle_params("wolf"), oracle_kind)
+    ev = cg.BatchedEvaluator(pot)
+    e = np.zeros(0)
+    ev.set_system(e, e, e, e, None, [40.0] * 3, True)
+    r = ev.eval(cg.MODE_ION, cg.ENERGY | cg.FORCE)
+    assert r["force"].shape == (0, 3) and r["energy"] == 0.0 and r["pairs"] == 0
+    one = np.array([1.0])
+    ev.set_system(one, one, one, one, None, [40.0] * 3, True)
+    r = ev.eval(cg.MODE_ION, cg.ENERGY | cg.FORCE)
+    assert np.all(r["force"] == 0.0) and r["pairs"] == 0
+    # ragged: 37 particles (neither a multiple of 32 nor of the cell grid), non-cubic periodic box, all in a corner
+    rng = np.random.default_rng(3)
+    box = [30.0, 41.0, 55.0]
+    x, y, z = (rng.uniform(0, 9.0, 37) for _ in range(3))
+    q = rng.choice([-1.0, 1.0], 37)
+    mu = tuple(rng.normal(size=37) for _ in range(3))
+    for mode in (cg.MODE_ION, cg.MODE_DIPOLE, cg.MODE_MULTIPOLE):
+        g, r = run_case(pot, osch, x, y, z, q, mu, box, True, mode, ALL)
+        ok(compare(g, r, ALL))
+    # two particles exactly at the cut-off distance: strict gate, no interaction (core.hpp:354)
+    g, r = run_case(pot, osch, np.array([1.0, 13.0]), np.array([1.0, 1.0]), np.array([1.0, 1.0]), np.array([1.0, -1.0]), None, box, False,
+                    cg.MODE_ION, cg.ENERGY | cg.FORCE)
+    assert g["pairs"] == r["pairs"] == 0 and np.all(g["force"] == 0.0)
+
+
+def test_open_box_non_uniform_density(oracle_kind):
+    """Clustered particles far apart in an open box: empty cells, one dense cell, groups with few neighbours."""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.normal(0, 2.0, 300), rng.normal(200, 1.0, 200), rng.uniform(-50, 250, 100)])
+    y = np.concatenate([rng.normal(0, 2.0, 300), rng.normal(-80, 1.0, 200), rng.uniform(-100, 20, 100)])
+    z = np.concatenate([rng.normal(0, 2.0, 300), rng.normal(35, 1.0, 200), rng.uniform(-10, 50, 100)])
+    q = rng.choice([-1.0, 1.0], 600)
+    mu = tuple(rng.normal(size=600) for _ in range(3))
+    for name, mode in (("wolf", cg.MODE_ION), ("reactionfield", cg.MODE_DIPOLE), ("fanourgakis", cg.MODE_MULTIPOLE), ("plain", cg.MODE_ION)):
+        mk, p = zoo()[name]
+        g, r = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, None, False, mode, ALL)
+        ok(compare(g, r, ALL))
+
+
+def test_errors_are_status_codes():
+    ev = cg.BatchedEvaluator(cg.Wolf(12.0, 0.25))
+    with pytest.raises(cg.CgError) as e:
+        ev.eval(cg.MODE_ION, cg.FORCE)
+    assert e.value.rc == -6  # CG_ERR_STATE: no system yet
+    one = np.array([1.0, 2.0])
+    with pytest.raises(cg.CgError) as e:
+        ev.set_system(one, one, one, one, None, [11.0] * 3, True)  # periodic box shorter than the cut-off
+    assert e.value.rc == -5
+    ev.set_system(one, one, one, one, None, [30.0] * 3, True)
+    with pytest.raises(cg.CgError) as e:
+        ev.eval(7, cg.FORCE)
+    assert e.value.rc == -1
+
+
+def test_device_pointer_path_equals_host_path_and_is_deterministic():
+    import torch
+    x, y, z, q, mu = O.generate(20, 3.0, 2024, "port" if not O.available("ref") else "ref")
+    pot = cg.Fennell(12.0, 0.25)
+    ev = cg.BatchedEvaluator(pot)
+    ev.set_system(x, y, z, q, None, [60.0] * 3, True)
+    h = ev.eval(cg.MODE_ION, cg.ENERGY | cg.FORCE)
+    dev = [torch.tensor(a, device="cuda") for a in (x, y, z, q)]
+    f = torch.empty((x.size, 3), dtype=torch.float64, device="cuda")
+    sc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    ev2 = cg.BatchedEvaluator(pot)
+    st = torch.cuda.Stream()
+    ev2.set_stream(st.cuda_stream)
+    outs = []
+    for _ in range(3):
+        ev2.set_system_device(dev[0], dev[1], dev[2], dev[3], None, [60.0] * 3, True)
+        ev2.eval_device(cg.MODE_ION, cg.ENERGY | cg.FORCE, force=f, scalars=sc)
+        st.synchronize()
+        outs.append((f.cpu().numpy().copy(), sc.cpu().numpy().copy()))
+    assert all(np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) for o in outs)  # bit-reproducible
+    assert np.array_equal(outs[0][0], h["force"]) and outs[0][1][0] == h["energy"] and int(outs[0][1][1]) == h["pairs"]
+
+
+def test_shards_partition_the_work(oracle_kind):
+    x, y, z, q, mu = O.generate(16, 3.0, 7, oracle_kind)
+    mk, p = zoo()["reactionfield"]
+    w = cg.ENERGY | cg.FORCE | cg.FIELD
+    full, ref = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, [48.0] * 3, True, cg.MODE_DIPOLE, w)
+    parts = [run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, [48.0] * 3, True, cg.MODE_DIPOLE, w, shard=(r, 3))[0] for r in range(3)]
+    assert sum(pt["pairs"] for pt in parts) == full["pairs"] == ref["pairs"]
+    assert abs(sum(pt["energy"] for pt in parts) - full["energy"]) <= 1e-13 * ref["energy_abs"]
+    # each particle is written by exactly one shard (the others leave zeros), and the union is the unsharded result
+    # (to rounding, not bitwise: a small system is also split along j, and the j-split factor depends on the shard size)
+    fsum = sum(pt["force"] for pt in parts)
+    assert np.max(np.linalg.norm(fsum - full["force"], axis=1) / ref["force_scale"]) <= 1e-14
+    owners = sum((np.abs(pt["force"]).sum(axis=1) > 0).astype(int) for pt in parts)
+    assert owners.max() == 1
+
+
+def test_full_size_properties_one_million(oracle_kind):
+    """BASELINE config 2 at full size: N = 100^3, L = 300, Wolf and Fennell forces.  Checks that do not need the oracle on all
+    pairs: pair count (an exact integer, symmetric => even), Newton's third law, and parity on a 4096-particle i-slice."""
+    import torch
+    n, L = 100, 300.0
+    N = n ** 3
+    dev = [torch.empty(N, dtype=torch.float64, device="cuda") for _ in range(4)]
+    f = torch.empty((N, 3), dtype=torch.float64, device="cuda")
+    sc = torch.zeros(2, dtype=torch.float64, device="cuda")
+    x = y = z = q = None
+    for name in ("wolf", "fennell"):
+        mk, p = zoo()[name]
+        ev = cg.BatchedEvaluator(mk())
+        ev.generate_lattice_device(n, 3.0, 1002, dev[0], dev[1], dev[2], dev[3])
+        ev.set_system_device(dev[0], dev[1], dev[2], dev[3], None, [L] * 3, True)
+        ev.eval_device(cg.MODE_ION, cg.FORCE, force=f, scalars=sc)
+        torch.cuda.synchronize()
+        pairs = int(sc[1].item())
+        assert pairs == 264441374 and pairs % 2 == 0
+        F = f.cpu().numpy()
+        assert np.linalg.norm(F.sum(axis=0)) <= 1e-12 * np.abs(F).sum()
+        if x is None:
+            x, y, z, q = (t.cpu().numpy() for t in dev)
+            xo, yo, zo, qo, _ = O.generate(n, 3.0, 1002, oracle_kind)
+            assert np.array_equal(x, xo) and np.array_equal(y, yo) and np.array_equal(z, zo) and np.array_equal(q, qo)  # device generator == oracle generator
+        lo, hi = 500000, 504096
+        r = O.Scheme(p, oracle_kind).batched(x, y, z, q, None, [L] * 3, True, O.MODE_ION, O.FORCE, lo, hi)
+        dn = np.linalg.norm(F[lo:hi] - r["force"], axis=1)
+        assert np.max(dn / np.maximum(np.linalg.norm(r["force"], axis=1), r["force_scale"])) <= TOL
+        ev.close()
