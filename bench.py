@@ -35,7 +35,7 @@ NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 37.2: 148 SMs x 64 DFMA/c
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n-side", type=int, default=CFG["n_side"], help="lattice sites per edge (default: the BASELINE config)")
@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -192,12 +192,11 @@ def main():
     full = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
     evs["wolf"].generate_lattice_device(n_side, CFG["a"], CFG["seed"], full[0], full[1], full[2], full[3])
     torch.cuda.synchronize()
-    lo, hi = N * rank // world, N * (rank + 1) // world
+    from coulombgalore_b200.distributed import ShardedStep, owned_range
+    lo, hi = owned_range(N, rank, world)
     owned = [t[lo:hi].clone() for t in full]  # this rank's particles
-    if world > 1:
-        counts = [N * (r + 1) // world - N * r // world for r in range(world)]
-        even = len(set(counts)) == 1
-    gathered = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)] if world > 1 else full
+    exchange = ShardedStep(N, 4, dev) if world > 1 else None
+    gathered = exchange.full if world > 1 else full
     force = torch.empty((N, 3), dtype=torch.float64, device=dev)
     scal = {k: torch.zeros(2, dtype=torch.float64, device=dev) for k in evs}
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -205,12 +204,7 @@ def main():
     def step_device():
         launches = 0
         if world > 1:
-            for k in range(4):  # the exchange step: positions + charges of every rank
-                if even:
-                    dist.all_gather_into_tensor(gathered[k], owned[k])
-                else:
-                    parts = list(gathered[k].split(counts))
-                    dist.all_gather(parts, owned[k])
+            exchange.gather(owned)  # the exchange step: NCCL all-gather of positions + charges of every rank
         for name, ev in evs.items():
             ev.set_system_device(gathered[0], gathered[1], gathered[2], gathered[3], None, box, True)
             ev.eval_device(cg.MODE_ION, cg.FORCE, force=force, scalars=scal[name])
