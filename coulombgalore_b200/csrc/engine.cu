@@ -102,6 +102,9 @@ struct SortParams {
     double inv_cs[3];
     int nprim[3], ghost[3], ntot[3];
     int pbc;
+    // shard: this rank evaluates the primary cell rows [row0, row1) (row = rz * nprim[1] + ry) and therefore only needs
+    // the cell layers [z0, z0 + nzl) of the full grid; everything outside is neither binned nor stored
+    int row0, row1, z0, nzl;
 };
 
 // per dimension: up to three images (shift 0 always; +1 / -1 when the image falls into the ghost layer)
@@ -140,7 +143,9 @@ __global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_coun
     for (int c = 0; c < mz; c++)
         for (int b = 0; b < my; b++)
             for (int a = 0; a < mx; a++) {
-                const int cell = (cz[c] * sp.ntot[1] + cy[b]) * sp.ntot[0] + cx[a];
+                const int czl = cz[c] - sp.z0;
+                if (czl < 0 || czl >= sp.nzl) continue; // outside this shard's layers
+                const int cell = (czl * sp.ntot[1] + cy[b]) * sp.ntot[0] + cx[a];
                 const int slot = atomicAdd(&cell_count[cell], 1);
                 if (SCATTER) {
                     const unsigned int code = (unsigned int)((sx[a] + 1) + 3 * (sy[b] + 1) + 9 * (sz[c] + 1));
@@ -190,23 +195,23 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int n_sorte
 
 // i-groups: per primary cell row, ceil(count/32) groups
 __global__ void row_group_count_kernel(const __grid_constant__ SortParams sp, const int *cell_start, int *row_ngroups) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nrows = sp.nprim[1] * sp.nprim[2];
-    if (r >= nrows) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= sp.row1 - sp.row0) return;
+    const int r = sp.row0 + k;
     const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
-    const int rowbase = ((rz + sp.ghost[2]) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
+    const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
     const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
-    row_ngroups[r] = (b - a + 31) / 32;
+    row_ngroups[k] = (b - a + 31) / 32;
 }
 
 __global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, const int *cell_start, const int *row_gstart, int2 *groups) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    const int nrows = sp.nprim[1] * sp.nprim[2];
-    if (r >= nrows) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= sp.row1 - sp.row0) return;
+    const int r = sp.row0 + k;
     const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
-    const int rowbase = ((rz + sp.ghost[2]) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
+    const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
     const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
-    int g = row_gstart[r];
+    int g = row_gstart[k];
     for (int s = a; s < b; s += 32) groups[g++] = make_int2(s, min(32, b - s));
 }
 
@@ -755,8 +760,23 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         if (ncell <= 48e6) break;
         cs0 *= 1.26;
     }
-    const int ncell = sp.ntot[0] * sp.ntot[1] * sp.ntot[2];
-    const int nrows_prim = sp.nprim[1] * sp.nprim[2];
+    // ---- shard: a contiguous block of primary cell rows (z-major), plus the cell layers within one cut-off of it ----
+    {
+        const int nrows_all = sp.nprim[1] * sp.nprim[2];
+        sp.row0 = (int)((int64_t)nrows_all * h->shard_rank / h->shard_n);
+        sp.row1 = (int)((int64_t)nrows_all * (h->shard_rank + 1) / h->shard_n);
+        sp.z0 = 0;
+        sp.nzl = sp.ntot[2];
+        if (h->shard_n > 1 && sp.row1 > sp.row0) {
+            const int halo = (int)std::ceil(rc * sp.inv_cs[2] - 1e-9) + 1; // +1: fp32 slack of the kernel's cell ranges
+            const int lz0 = sp.row0 / sp.nprim[1] + sp.ghost[2], lz1 = (sp.row1 - 1) / sp.nprim[1] + sp.ghost[2];
+            const int za = std::max(0, lz0 - halo), zb = std::min(sp.ntot[2] - 1, lz1 + halo);
+            sp.z0 = za;
+            sp.nzl = zb - za + 1;
+        }
+    }
+    const int ncell = sp.ntot[0] * sp.ntot[1] * sp.nzl;
+    const int nrows_prim = sp.row1 - sp.row0;
 
     // ---- 1-3. histogram, scan, groups ----
     CG_CUDA(h, h->cell_count.ensure((size_t)ncell + 1));
@@ -771,7 +791,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, &launches));
     scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell);
     launches++;
-    row_group_count_kernel<<<(nrows_prim + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
+    row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
     launches++;
     CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, &launches));
     scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim);
@@ -803,13 +823,13 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     }
     gather_kernel<<<(n_sorted + 256) / 256, 256, 0, st>>>(sp, n_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p, h->orig.p,
                                                        far_coord);
-    row_group_emit_kernel<<<(nrows_prim + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
+    row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
     launches += 4;
     CG_CUDA(h, cudaGetLastError());
     CG_CUDA(h, cudaEventRecord(h->ev[1], st));
 
     // ---- 6. pair kernel ----
-    const int g0 = (int)((int64_t)n_groups * h->shard_rank / h->shard_n), g1 = (int)((int64_t)n_groups * (h->shard_rank + 1) / h->shard_n);
+    const int g0 = 0, g1 = n_groups; // the group table already holds only this shard's rows
     const int ng = g1 - g0;
     int device_sms = 148;
     cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -817,9 +837,10 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         const char *e = std::getenv("CG_SPLIT");
         return e ? std::atoi(e) : 0;
     }();
+    // j-split: only when the groups cannot fill the machine once (2 CTAs of 8 warps per SM); then aim at two waves
     int split = 1;
-    const int want_items = device_sms * 2 * kWarpsPerCta * 2; // two waves of two CTAs per SM
-    if (ng > 0 && ng < want_items) split = std::min(64, (want_items + ng - 1) / ng);
+    const int wave = device_sms * 2 * kWarpsPerCta;
+    if (ng > 0 && ng < wave) split = std::min(64, (2 * wave + ng - 1) / ng);
     if (split_env > 0) split = std::min(64, split_env);
     const int items = ng * split;
 
@@ -846,7 +867,8 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     kp.split = split;
     kp.nx = sp.ntot[0];
     kp.ny = sp.ntot[1];
-    kp.nz = sp.ntot[2];
+    kp.nz = sp.nzl;
+    kp.cz_off = sp.z0;
     kp.inv_cs_x = (float)sp.inv_cs[0];
     kp.inv_cs_y = (float)sp.inv_cs[1];
     kp.inv_cs_z = (float)sp.inv_cs[2];

@@ -39,7 +39,8 @@ struct KParams {
     const int2 *groups;   // i-groups: (first sorted entry, count <= 32); a group never crosses a cell row
     int group_begin, group_end; // shard of groups this launch evaluates
     int split;            // j-split factor: work item = (group, s), s in [0, split)
-    int nx, ny, nz;       // cells per dimension (ghost layers included)
+    int nx, ny, nz;       // cells per dimension (ghost layers included; nz = the shard's layer window)
+    int cz_off;           // first cell layer of the window in the full grid
     float inv_cs_x, inv_cs_y, inv_cs_z, cs_x, cs_y, cs_z;
     float rc_m;           // cut-off plus fp32 rounding margin, for the candidate cell ranges
     double rc2_m;         // squared cut-off plus the rounding margin of the three-FFMA prefilter test

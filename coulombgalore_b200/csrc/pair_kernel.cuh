@@ -98,8 +98,8 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     const float rcm = p.rc_m;
     const int cy0 = clampi((int)floorf((ymin - rcm) * p.inv_cs_y - p.slack), 0, p.ny - 1);
     const int cy1 = clampi((int)floorf((ymax + rcm) * p.inv_cs_y + p.slack), 0, p.ny - 1);
-    const int cz0 = clampi((int)floorf((zmin - rcm) * p.inv_cs_z - p.slack), 0, p.nz - 1);
-    const int cz1 = clampi((int)floorf((zmax + rcm) * p.inv_cs_z + p.slack), 0, p.nz - 1);
+    const int cz0 = clampi((int)floorf((zmin - rcm) * p.inv_cs_z - p.slack) - p.cz_off, 0, p.nz - 1);
+    const int cz1 = clampi((int)floorf((zmax + rcm) * p.inv_cs_z + p.slack) - p.cz_off, 0, p.nz - 1);
     const int nyr = cy1 - cy0 + 1;
     const int nrows = nyr * (cz1 - cz0 + 1);
 
@@ -121,7 +121,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                 if (rr < nrows) {
                     const int rzi = rr / nyr;
                     const int ry = cy0 + (rr - rzi * nyr), rz = cz0 + rzi;
-                    const float ylo = (float)ry * p.cs_y, zlo = (float)rz * p.cs_z;
+                    const float ylo = (float)ry * p.cs_y, zlo = (float)(rz + p.cz_off) * p.cs_z;
                     const float dy = fmaxf(0.0f, fmaxf(ylo - ymax, ymin - (ylo + p.cs_y)));
                     const float dz = fmaxf(0.0f, fmaxf(zlo - zmax, zmin - (zlo + p.cs_z)));
                     const float w2 = rcm * rcm - (dy * dy + dz * dz);
