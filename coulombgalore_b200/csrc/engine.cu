@@ -522,6 +522,11 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
         h->table_doubles = f.total;
         // the handle owns its own copy of the tables: re-point the descriptor at it
         for (int k = 0; k < 4; k++) {
+            if (scheme->spline_knots[k] > 250) { // one byte per table in the lookup grid
+                g_create_error = "spline table too large";
+                delete h;
+                return CG_ERR_INVALID;
+            }
             h->desc.spline_r2[k] = h->host_table.data() + f.koff[k];
             h->desc.spline_c[k] = h->host_table.data() + f.coff[k];
         }
@@ -734,20 +739,28 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
             ext[d] *= (1.0 + 1e-12);
         }
     }
-    // target cell edge: half the cut-off, but not so small that cells are nearly empty or the grid explodes
+    // target cell edge: half the cut-off along x (the storage direction), but not so small that cells are nearly empty
+    // or the grid explodes (an unbounded cut-off, i.e. Plain, still gets cells of ~32 particles: they only provide the
+    // sorted order).  CG_CELL_DIV / CG_CELL_DIV_YZ: cells per cut-off along x / along y and z (tuning).
     static const double cell_div = [] {
         const char *e = std::getenv("CG_CELL_DIV");
         const double v = e ? std::atof(e) : 2.0;
         return (v >= 0.5 && v <= 8.0) ? v : 2.0;
     }();
+    static const double cell_div_yz = [] {
+        const char *e = std::getenv("CG_CELL_DIV_YZ");
+        const double v = e ? std::atof(e) : 0.0;
+        return (v >= 0.5 && v <= 8.0) ? v : 0.0;
+    }();
     const double vol = ext[0] * ext[1] * ext[2];
-    // (an unbounded cut-off, i.e. Plain, still gets cells of ~32 particles: they only provide the sorted order)
     double cs0 = std::min(rc / cell_div, std::cbrt(32.0 * vol / (double)n));
     cs0 = std::max(cs0, std::cbrt(2.0 * vol / (double)n)); // >= ~2 particles per cell on average
     for (;;) {
         double ncell = 1.0;
         for (int d = 0; d < 3; d++) {
-            int np = (int)std::min(4096.0, std::max(1.0, std::floor(ext[d] / cs0)));
+            double target = cs0;
+            if (d > 0 && cell_div_yz > 0.0 && rc < 1e100) target = std::max(cs0 * cell_div / cell_div_yz, cs0 * 0.25);
+            int np = (int)std::min(4096.0, std::max(1.0, std::floor(ext[d] / target)));
             sp.nprim[d] = np;
             const double cs = ext[d] / np;
             sp.box[d] = ext[d];

@@ -276,67 +276,114 @@ struct PoissonSrf : SrfDefaults {
 // ---------------------------------------------------------------------------------------------------------------
 // Splined (splined.hpp:321-386): four independent Andrea tables; eval = lower_bound over the knots, then a quintic
 // Horner in dz = q - knot (splined.hpp:167-176).  Packed layout in `tab` (global memory on the device, staged to
-// shared memory by the kernels; a host pointer for the scheme classes):
-//   for k in 0..3:  knots[k][0..n_k)  at tab + koff[k],   coefficients[k][6*(n_k-1)]  at tab + coff[k]
+// shared memory by the kernels; a host pointer for the scheme classes), all offsets in doubles:
+//   for k in 0..3:  knots[k][0..n_k)  at koff[k],   coefficients[k][6*(n_k-1)]  at coff[k] (16-byte aligned)
+//   lookup grid at lut_off: kSplineGrid 32-bit words, byte k of word c = the interval of table k that contains the
+//   left edge of grid cell c, i.e. a lower bound for every q in [c, c+1)/kSplineGrid; the device then advances at
+//   most `kmax` intervals with exact FP64 comparisons, which reproduces std::lower_bound bit for bit.
+constexpr int kSplineGrid = 64;
+
 struct SplineSrf : SrfDefaults {
     static constexpr int kTable = kTableSpline;
-    int n[4], koff[4], coff[4], total;
+    int n[4], koff[4], coff[4], lut_off, kmax, total;
     const double *tab;
-    CG_HD SplineSrf() : total(0), tab(nullptr) {
+    CG_HD SplineSrf() : lut_off(0), kmax(0), total(0), tab(nullptr) {
         for (int k = 0; k < 4; k++) n[k] = koff[k] = coff[k] = 0;
     }
     // layout only (tab is attached afterwards: the device copy for kernels, pack_from() on the host)
-    inline explicit SplineSrf(const cg_scheme_desc &d) : total(0), tab(nullptr) {
+    inline explicit SplineSrf(const cg_scheme_desc &d) : lut_off(0), kmax(0), total(0), tab(nullptr) {
         int t = 0;
         for (int k = 0; k < 4; k++) {
             n[k] = d.spline_knots[k];
             koff[k] = t;
-            t += n[k];
+            t += n[k] + (n[k] & 1); // keep the coefficients 16-byte aligned
             coff[k] = t;
             t += 6 * (n[k] - 1);
         }
+        lut_off = t;
+        t += kSplineGrid / 2; // kSplineGrid 32-bit words
         total = t;
+        kmax = max_advance(d);
     }
     // number of doubles of the packed table
-    static inline int packed_size(const cg_scheme_desc &d) {
-        int t = 0;
-        for (int k = 0; k < 4; k++) t += d.spline_knots[k] + 6 * (d.spline_knots[k] - 1);
-        return t;
+    static inline int packed_size(const cg_scheme_desc &d) { return SplineSrf(d).total; }
+    static inline int interval_of(const double *knots, int nk, double q) { // (#knots strictly below q) - 1, clamped
+        int pos = -1;
+        for (int i = 0; i < nk; i++) pos += (knots[i] < q) ? 1 : 0;
+        return pos < 0 ? 0 : (pos > nk - 2 ? nk - 2 : pos);
+    }
+    static inline int max_advance(const cg_scheme_desc &d) {
+        int m = 0;
+        for (int k = 0; k < 4; k++)
+            for (int c = 0; c < kSplineGrid; c++) {
+                const int lo = interval_of(d.spline_r2[k], d.spline_knots[k], (double)c / kSplineGrid);
+                const int hi = interval_of(d.spline_r2[k], d.spline_knots[k], (double)(c + 1) / kSplineGrid);
+                m = (hi - lo > m) ? hi - lo : m;
+            }
+        return m;
     }
     // host-side packing; `dst` must hold packed_size(d) doubles
     inline void pack_from(const cg_scheme_desc &d, double *dst) {
-        int t = 0;
+        *this = SplineSrf(d);
+        for (int i = 0; i < total; i++) dst[i] = 0.0;
         for (int k = 0; k < 4; k++) {
-            n[k] = d.spline_knots[k];
-            koff[k] = t;
-            for (int i = 0; i < n[k]; i++) dst[t++] = d.spline_r2[k][i];
-            coff[k] = t;
-            for (int i = 0; i < 6 * (n[k] - 1); i++) dst[t++] = d.spline_c[k][i];
+            for (int i = 0; i < n[k]; i++) dst[koff[k] + i] = d.spline_r2[k][i];
+            for (int i = 0; i < 6 * (n[k] - 1); i++) dst[coff[k] + i] = d.spline_c[k][i];
         }
-        total = t;
+        unsigned int *lut = reinterpret_cast<unsigned int *>(dst + lut_off);
+        for (int c = 0; c < kSplineGrid; c++) {
+            unsigned int w = 0;
+            for (int k = 0; k < 4; k++) w |= (unsigned int)interval_of(d.spline_r2[k], n[k], (double)c / kSplineGrid) << (8 * k);
+            lut[c] = w;
+        }
         tab = dst;
     }
-    CG_HD double table(int k, double q, const double *t) const {
-        const double *kn = t + koff[k];
-        // std::lower_bound(...) - begin - 1  ==  (#knots strictly below q) - 1; q on an interior knot -> lower interval
-        int pos = -1;
-        for (int i = 0; i < n[k]; i++) pos += (table_load(kn + i) < q) ? 1 : 0;
-        pos = pos < 0 ? 0 : (pos > n[k] - 2 ? n[k] - 2 : pos); // q == 0 asserts in the reference; clamp instead
-        const double dz = q - table_load(kn + pos);
-        const double *c = t + coff[k] + 6 * pos;
-        return table_load(c) + dz * (table_load(c + 1) + dz * (table_load(c + 2) + dz * (table_load(c + 3) + dz * (table_load(c + 4) + dz * (table_load(c + 5))))));
-    }
-    template <int ND> CG_HD void eval(double q, double *s, const double *t = nullptr) const {
 #ifdef __CUDA_ARCH__
-        const double *p = t; // staged in shared memory by the kernels
+    // device: grid lookup + at most kmax exact comparisons, coefficients fetched as three 16-byte shared-memory loads
+    __device__ __forceinline__ double table(int k, double q, unsigned int cellword, const double *t) const {
+        const unsigned base = (unsigned)__cvta_generic_to_shared(t);
+        int pos = (int)((cellword >> (8 * k)) & 255u);
+        for (int s = 0; s < kmax; s++) {
+            const int nx = pos + 1;
+            double kn;
+            asm("ld.shared.f64 %0, [%1];" : "=d"(kn) : "r"(base + 8u * (unsigned)(koff[k] + nx)));
+            pos = (nx <= n[k] - 2 && kn < q) ? nx : pos;
+        }
+        double k0, c0, c1, c2, c3, c4, c5;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(k0) : "r"(base + 8u * (unsigned)(koff[k] + pos)));
+        const unsigned ca = base + 8u * (unsigned)(coff[k] + 6 * pos);
+        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(ca));
+        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c2), "=d"(c3) : "r"(ca + 16u));
+        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c4), "=d"(c5) : "r"(ca + 32u));
+        const double dz = q - k0;
+        return c0 + dz * (c1 + dz * (c2 + dz * (c3 + dz * (c4 + dz * (c5)))));
+    }
+    template <int ND> __device__ __forceinline__ void eval(double q, double *s, const double *t = nullptr) const {
+        int c = __double2int_rd(q * (double)kSplineGrid);
+        c = min(max(c, 0), kSplineGrid - 1);
+        unsigned int w;
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((unsigned)__cvta_generic_to_shared(t) + 8u * (unsigned)lut_off + 4u * (unsigned)c));
+        s[0] = table(0, q, w, t);
+        if (ND >= 1) s[1] = table(1, q, w, t);
+        if (ND >= 2) s[2] = table(2, q, w, t);
+        if (ND >= 3) s[3] = table(3, q, w, t);
+    }
 #else
+    inline double table(int k, double q, const double *t) const {
+        const double *kn = t + koff[k];
+        const int pos = interval_of(kn, n[k], q); // q == 0 asserts in the reference; clamped here
+        const double dz = q - kn[pos];
+        const double *c = t + coff[k] + 6 * pos;
+        return c[0] + dz * (c[1] + dz * (c[2] + dz * (c[3] + dz * (c[4] + dz * (c[5])))));
+    }
+    template <int ND> inline void eval(double q, double *s, const double *t = nullptr) const {
         const double *p = t ? t : tab;
-#endif
         s[0] = table(0, q, p);
         if (ND >= 1) s[1] = table(1, q, p);
         if (ND >= 2) s[2] = table(2, q, p);
         if (ND >= 3) s[3] = table(3, q, p);
     }
+#endif
 };
 
 } // namespace detail
