@@ -51,6 +51,11 @@ class BatchedEvaluator:
     def set_stream(self, cuda_stream_ptr):
         check(lib.cg_set_stream(self.h, cuda_stream_ptr), "cg_set_stream", self.h)
 
+    def set_precision(self, precision):
+        """"fp64" (default; parity 1e-12) or "fp32": fp32 pair arithmetic with fp64 positions, gate and accumulators."""
+        code = {"fp64": 0, "fp32": 1}[precision]
+        check(lib.cg_set_precision(self.h, code), "cg_set_precision", self.h)
+
     def set_shard(self, rank, nranks):
         check(lib.cg_set_shard(self.h, rank, nranks), "cg_set_shard", self.h)
 

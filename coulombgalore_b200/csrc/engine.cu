@@ -610,10 +610,6 @@ int cg_set_stream(cg_handle *h, void *cuda_stream) {
 
 int cg_set_precision(cg_handle *h, int precision) {
     if (!h || (precision != CG_FP64 && precision != CG_FP32)) return CG_ERR_INVALID;
-    if (precision == CG_FP32) {
-        h->err = "fp32 pair arithmetic is not built into this library version";
-        return CG_ERR_UNSUPPORTED;
-    }
     h->precision = precision;
     return CG_OK;
 }
@@ -910,6 +906,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.slack = (float)(1e-4 + 1e-6 * nmax);
     }
     kp.rc2 = D.cutoff_squared;
+    kp.rc2_safe = D.cutoff_squared < 1e30 ? 0.25 * D.cutoff_squared : 1.0;
     kp.core.inverse_cutoff = D.inverse_cutoff;
     kp.core.cutoff_squared = D.cutoff_squared;
     kp.core.kappa = D.inverse_debye_length;
@@ -958,7 +955,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         table_doubles = 2 * cgd::kErfcTableEntries;
     }
     if (items > 0) {
-        CG_CUDA(h, fe->pair[ci](kp, D, dev_table, table_doubles, items, st));
+        CG_CUDA(h, (h->precision == CG_FP32 ? fe->pair32[ci] : fe->pair[ci])(kp, D, dev_table, table_doubles, items, st));
         pair_launches++;
         launches++;
     }

@@ -46,6 +46,7 @@ struct KParams {
     double rc2_m;         // squared cut-off plus the rounding margin of the three-FFMA prefilter test
     float slack;          // slack in cell units for fp32 cell-range rounding
     double rc2;           // exact gate: r2 < cutoff_squared (strict, reference core.hpp:354 etc.)
+    double rc2_safe;      // cutoff_squared / 4 (1 for Plain): the r2 a lane without work feeds to the branch-free arithmetic
     cgd::CoreParams core;
     int n;                // number of (original) particles
     int dummy;            // index of the far-away dummy entry appended to pos/mu (gathered by lanes that ran dry)
@@ -77,7 +78,8 @@ __host__ __device__ constexpr Combo combo(int i) {
 }
 
 struct FunctorEntry {
-    pair_launch_fn pair[kNumCombos];
+    pair_launch_fn pair[kNumCombos];   // fp64 pair arithmetic
+    pair_launch_fn pair32[kNumCombos]; // fp32 pair arithmetic (CG_FP32)
     srf_launch_fn srf;
     int table_kind; // cgd::kTableNone / kTableSpline / kTableErfc: which table the engine must pass
 };

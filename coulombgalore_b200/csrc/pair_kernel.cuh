@@ -57,7 +57,9 @@ template <int MODE> constexpr int min_blocks_per_sm() { return CG_MINB; }
 #endif
 template <int MODE> constexpr int pairs_in_flight() { return MODE == cgd::kModeIon ? CG_ILP : CG_ILP_DIP; }
 
-template <class F, bool YUK, int MODE, int WHAT>
+// T = double: the fp64 path (parity 1e-12).  T = float (CG_FP32): positions, the distance vector and the exact gate stay
+// fp64, the pair arithmetic incl. S(q) runs in fp32, per-chunk fp32 partial sums are folded into fp64 accumulators.
+template <class F, bool YUK, int MODE, int WHAT, class T>
 __global__ void __launch_bounds__(kThreads, min_blocks_per_sm<MODE>())
 pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, const double *__restrict__ dev_table,
             int table_doubles, int items) {
@@ -86,11 +88,14 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
 
     // the lane's own particle
     const double4 pi = ldg256(p.pos + i);
-    cgd::D3 mui = {0.0, 0.0, 0.0};
+    typedef cgd::Vec3T<T> V3;
+    constexpr bool kF32 = !std::is_same<T, double>::value;
+    V3 mui = {T(0), T(0), T(0)};
     if constexpr (MODE != cgd::kModeIon) {
         const double4 m = ldg256(p.mu + i);
-        mui = {m.x, m.y, m.z};
+        mui = {(T)m.x, (T)m.y, (T)m.z};
     }
+    const T zi = (T)pi.w;
     const float4 pf = p.pos32[i];
     // bounding box of the group (coordinates relative to the grid origin are >= 0: float order == int order)
     const float xmin = __int_as_float(__reduce_min_sync(full, __float_as_int(pf.x)));
@@ -111,7 +116,8 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     const int nyr = cy1 - cy0 + 1;
     const int nrows = nyr * (cz1 - cz0 + 1);
 
-    cgd::Accum acc;
+    cgd::AccumT<T> acc;  // what the pair arithmetic accumulates into
+    cgd::Accum acc64;    // fp32 path only: running fp64 totals
     unsigned int npairs = 0;
 
     // ---- iterator over the candidate batches (warp-uniform; jb/je hold one cell row's run per lane) ----
@@ -244,13 +250,17 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             constexpr int s = decltype(S)::value;
 #pragma unroll
             for (int u = 0; u < kIlp; u++) {
-                const cgd::D3 d = {pi.x - pp[s][u].x, pi.y - pp[s][u].y, pi.z - pp[s][u].z};
-                const double r2 = d.x * d.x + d.y * d.y + d.z * d.z;
-                const bool pass = hh[s][u] && r2 < p.rc2; // the exact, strict reference gate
+                const double dx = pi.x - pp[s][u].x, dy = pi.y - pp[s][u].y, dz = pi.z - pp[s][u].z;
+                const double r2 = dx * dx + dy * dy + dz * dz;
+                const bool pass = hh[s][u] && r2 < p.rc2; // the exact, strict reference gate (fp64 in both precisions)
                 npairs += pass ? 1u : 0u;
-                cgd::D3 muj = {0.0, 0.0, 0.0};
-                if constexpr (MODE != cgd::kModeIon) muj = {mm[s][u].x, mm[s][u].y, mm[s][u].z};
-                cgd::pair_accumulate<F, YUK, MODE, WHAT>(f, p.core, tab, d, r2, pi.w, pp[s][u].w, mui, muj, acc, pass);
+                const V3 d = {(T)dx, (T)dy, (T)dz};
+                V3 muj = {T(0), T(0), T(0)};
+                if constexpr (MODE != cgd::kModeIon) muj = {(T)mm[s][u].x, (T)mm[s][u].y, (T)mm[s][u].z};
+                // a lane that ran dry evaluates a harmless in-range distance (its contribution is zeroed by `pass`);
+                // rejected real pairs lie within the prefilter margin of the cut-off and are harmless as they are
+                const T r2e = hh[s][u] ? (T)r2 : (T)p.rc2_safe;
+                cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, r2e, zi, (T)pp[s][u].w, mui, muj, acc, pass);
             }
         };
         using I0 = std::integral_constant<int, 0>;
@@ -264,7 +274,28 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             fetch(I0{});
             compute(I1{});
         }
+        if constexpr (kF32) { // fold this chunk's fp32 partial sums into the fp64 totals
+            acc64.U += (double)acc.U;
+            acc64.Fx += (double)acc.Fx;
+            acc64.Fy += (double)acc.Fy;
+            acc64.Fz += (double)acc.Fz;
+            acc64.Ex += (double)acc.Ex;
+            acc64.Ey += (double)acc.Ey;
+            acc64.Ez += (double)acc.Ez;
+            acc64.phi += (double)acc.phi;
+            acc = cgd::AccumT<T>();
+        }
         __syncwarp();
+    }
+    if constexpr (!kF32) {
+        acc64.U = (double)acc.U;
+        acc64.Fx = (double)acc.Fx;
+        acc64.Fy = (double)acc.Fy;
+        acc64.Fz = (double)acc.Fz;
+        acc64.Ex = (double)acc.Ex;
+        acc64.Ey = (double)acc.Ey;
+        acc64.Ez = (double)acc.Ez;
+        acc64.phi = (double)acc.phi;
     }
 
     // ---- epilogue: per-particle outputs straight from registers, one reduction per item for the scalars ----
@@ -273,23 +304,23 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         const size_t o = part + (size_t)p.orig[i];
         if constexpr ((WHAT & cgd::kWhatForce) != 0) {
             if (p.force) {
-                p.force[3 * o + 0] = acc.Fx;
-                p.force[3 * o + 1] = acc.Fy;
-                p.force[3 * o + 2] = acc.Fz;
+                p.force[3 * o + 0] = acc64.Fx;
+                p.force[3 * o + 1] = acc64.Fy;
+                p.force[3 * o + 2] = acc64.Fz;
             }
         }
         if constexpr ((WHAT & cgd::kWhatField) != 0) {
             if (p.field) {
-                p.field[3 * o + 0] = acc.Ex;
-                p.field[3 * o + 1] = acc.Ey;
-                p.field[3 * o + 2] = acc.Ez;
+                p.field[3 * o + 0] = acc64.Ex;
+                p.field[3 * o + 1] = acc64.Ey;
+                p.field[3 * o + 2] = acc64.Ez;
             }
         }
         if constexpr ((WHAT & cgd::kWhatPotential) != 0) {
-            if (p.potential) p.potential[o] = acc.phi;
+            if (p.potential) p.potential[o] = acc64.phi;
         }
     }
-    double u = ((WHAT & cgd::kWhatEnergy) != 0 && active) ? acc.U : 0.0;
+    double u = ((WHAT & cgd::kWhatEnergy) != 0 && active) ? acc64.U : 0.0;
     unsigned int np = active ? npairs : 0u;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
@@ -307,13 +338,13 @@ inline size_t pair_smem_bytes(int table_doubles) {
     return (size_t)table_bytes + kWarpsPerCta * (32 * sizeof(float4) + kSlots * 32 * sizeof(uint2));
 }
 
-template <class F, bool YUK, int MODE, int WHAT>
+template <class F, bool YUK, int MODE, int WHAT, class T>
 cudaError_t launch_pair(const KParams &p, const cg_scheme_desc &desc, const double *dev_table, int table_doubles,
                         int items, cudaStream_t stream) {
     const F f(desc);
     if (F::kTable == cgd::kTableNone) table_doubles = 0;
     const size_t smem = pair_smem_bytes(table_doubles);
-    auto kern = pair_kernel<F, YUK, MODE, WHAT>;
+    auto kern = pair_kernel<F, YUK, MODE, WHAT, T>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int grid = (items + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -354,16 +385,17 @@ cudaError_t launch_srf(const cg_scheme_desc &desc, const double *dev_table, int 
     return cudaGetLastError();
 }
 
-// table of launchers for one functor: the eight instantiated (mode, what) combinations
+// table of launchers for one functor: the eight instantiated (mode, what) combinations, in fp64 and fp32
+#define CGB_PAIR_ROW(FUNCTOR, YUK, T)                                                                                          \
+    {launch_pair<FUNCTOR, YUK, combo(0).mode, combo(0).what, T>, launch_pair<FUNCTOR, YUK, combo(1).mode, combo(1).what, T>,   \
+     launch_pair<FUNCTOR, YUK, combo(2).mode, combo(2).what, T>, launch_pair<FUNCTOR, YUK, combo(3).mode, combo(3).what, T>,   \
+     launch_pair<FUNCTOR, YUK, combo(4).mode, combo(4).what, T>, launch_pair<FUNCTOR, YUK, combo(5).mode, combo(5).what, T>,   \
+     launch_pair<FUNCTOR, YUK, combo(6).mode, combo(6).what, T>, launch_pair<FUNCTOR, YUK, combo(7).mode, combo(7).what, T>}
 #define CGB_DEFINE_FUNCTOR_ENTRY(NAME, FUNCTOR, YUK)                                                                  \
     namespace cgb {                                                                                                   \
     const FunctorEntry *NAME() {                                                                                      \
-        static const FunctorEntry e = {                                                                               \
-            {launch_pair<FUNCTOR, YUK, combo(0).mode, combo(0).what>, launch_pair<FUNCTOR, YUK, combo(1).mode, combo(1).what>, \
-             launch_pair<FUNCTOR, YUK, combo(2).mode, combo(2).what>, launch_pair<FUNCTOR, YUK, combo(3).mode, combo(3).what>, \
-             launch_pair<FUNCTOR, YUK, combo(4).mode, combo(4).what>, launch_pair<FUNCTOR, YUK, combo(5).mode, combo(5).what>, \
-             launch_pair<FUNCTOR, YUK, combo(6).mode, combo(6).what>, launch_pair<FUNCTOR, YUK, combo(7).mode, combo(7).what>}, \
-            launch_srf<FUNCTOR>, FUNCTOR::kTable};                                                                    \
+        static const FunctorEntry e = {CGB_PAIR_ROW(FUNCTOR, YUK, double), CGB_PAIR_ROW(FUNCTOR, YUK, float), launch_srf<FUNCTOR>, \
+                                       FUNCTOR::kTable};                                                             \
         return &e;                                                                                                    \
     }                                                                                                                 \
     }

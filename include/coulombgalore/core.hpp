@@ -175,7 +175,7 @@ template <class T, bool debyehuckel = true> class EnergyImplementation : public 
     // adapts the derived class' four S-functions to the functor interface of detail/pair.hpp
     struct Functor {
         const T *self;
-        template <int ND> void eval(double q, double *s, const double *) const {
+        template <int ND, class R = double> void eval(double q, double *s, const double *) const {
             s[0] = self->short_range_function(q);
             if (ND >= 1) s[1] = self->short_range_function_derivative(q);
             if (ND >= 2) s[2] = self->short_range_function_second_derivative(q);

@@ -23,14 +23,14 @@ constexpr double kInfinity = std::numeric_limits<double>::infinity();
 
 // integer power by repeated squaring; negative exponents give the reciprocal.  Same multiplication order as
 // libgcc's __powidf2, which is what the reference's powi() resolves to on GCC (reference core.hpp:77-83).
-CG_HD double powi(double x, int m) {
+template <class T> CG_HD T powi(T x, int m) {
     unsigned int n = m < 0 ? 0u - (unsigned int)m : (unsigned int)m;
-    double y = (n & 1u) ? x : 1.0;
+    T y = (n & 1u) ? x : T(1);
     while (n >>= 1) {
         x = x * x;
         if (n & 1u) y *= x;
     }
-    return m < 0 ? 1.0 / y : y;
+    return m < 0 ? T(1) / y : y;
 }
 
 // 32-bit unsigned factorial/binomial: overflow for n >= 13 is part of the reference's behaviour
@@ -40,10 +40,11 @@ inline constexpr unsigned int binomial(signed int n, signed int k) {
     return factorial((unsigned int)n) / (factorial((unsigned int)k) * factorial((unsigned int)(n - k)));
 }
 
-struct D3 {
-    double x, y, z;
+template <class T> struct Vec3T {
+    T x, y, z;
 };
-CG_HD double dot(const D3 &a, const D3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+typedef Vec3T<double> D3;
+template <class T> CG_HD T dot(const Vec3T<T> &a, const Vec3T<T> &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 
 } // namespace detail
 } // namespace CoulombGalore

@@ -30,82 +30,87 @@ constexpr int derivatives_needed(int mode, int what) {
                             : ((what & kWhatForce) ? 3 : ((what & (kWhatField | kWhatEnergy)) ? 2 : 1));
 }
 
-struct Radial {
-    double rinv, r1, q, s0, ek, angcor, unicor, totcor, r3corr;
+template <class T> struct RadialT {
+    T rinv, r1, q, s0, ek, angcor, unicor, totcor, r3corr;
 };
+typedef RadialT<double> Radial;
 
-// ANGCOR_ONLY: the caller needs nothing but angcor (ion field / force without screening) and the functor has a closed form
-template <class F, bool YUK, int ND, bool ANGCOR_ONLY = false>
-CG_HD Radial radial_terms(const F &f, const CoreParams &cp, double r2, const double *tab) {
-    Radial R;
+// ANGCOR_ONLY: the caller needs nothing but angcor (ion field / force without screening) and the functor has a closed form.
+// T: arithmetic type of the pair math (double; float for the CG_FP32 kernels)
+template <class F, bool YUK, int ND, bool ANGCOR_ONLY = false, class T = double>
+CG_HD RadialT<T> radial_terms(const F &f, const CoreParams &cp, T r2, const double *tab) {
+    RadialT<T> R;
     R.rinv = rsqrt_pos(r2);
     R.r1 = r2 * R.rinv;
-    R.q = R.r1 * cp.inverse_cutoff;
+    R.q = R.r1 * (T)cp.inverse_cutoff;
     if constexpr (ANGCOR_ONLY) {
-        R.s0 = 0.0;
-        R.ek = 1.0;
-        R.angcor = f.angcor(R.q, tab);
-        R.unicor = R.totcor = R.r3corr = 0.0;
+        R.s0 = T(0);
+        R.ek = T(1);
+        R.angcor = f.template angcor<T>(R.q, tab);
+        R.unicor = R.totcor = R.r3corr = T(0);
+        return R;
+    } else {
+        T s[4] = {T(0), T(0), T(0), T(0)};
+        f.template eval<ND, T>(R.q, s, tab);
+        R.s0 = s[0];
+        const T third = T(1.0 / 3.0);
+        const T qs1 = R.q * s[1];
+        const T q2s2 = (ND >= 2) ? (R.q * R.q) * s[2] : T(0);
+        const T q3s3 = (ND >= 3) ? (R.q * R.q) * (R.q * s[3]) : T(0);
+        if (YUK) {
+            const T kr = (T)cp.kappa * R.r1;
+            R.ek = exp_any(-kr);
+            R.angcor = s[0] * (T(1) + kr) - qs1;
+            R.unicor = (s[0] * kr - T(2) * qs1) * kr * third + q2s2 * third;
+            R.totcor = R.angcor + R.unicor;
+            R.r3corr = R.angcor * kr * kr - qs1 * T(2) * (T(1) + kr) * kr + q2s2 * (T(1) + T(3) * kr) - q3s3;
+        } else {
+            R.ek = T(1);
+            R.angcor = s[0] - qs1;
+            R.unicor = q2s2 * third;
+            R.totcor = R.angcor + R.unicor;
+            R.r3corr = q2s2 - q3s3;
+        }
         return R;
     }
-    double s[4] = {0.0, 0.0, 0.0, 0.0};
-    f.template eval<ND>(R.q, s, tab);
-    R.s0 = s[0];
-    const double qs1 = R.q * s[1];
-    const double q2s2 = (ND >= 2) ? (R.q * R.q) * s[2] : 0.0;
-    const double q3s3 = (ND >= 3) ? (R.q * R.q) * (R.q * s[3]) : 0.0;
-    if (YUK) {
-        const double kr = cp.kappa * R.r1;
-        R.ek = exp_any(-kr);
-        R.angcor = s[0] * (1.0 + kr) - qs1;
-        R.unicor = (s[0] * kr - 2.0 * qs1) * kr * (1.0 / 3.0) + q2s2 * (1.0 / 3.0);
-        R.totcor = R.angcor + R.unicor;
-        R.r3corr = R.angcor * kr * kr - qs1 * 2.0 * (1.0 + kr) * kr + q2s2 * (1.0 + 3.0 * kr) - q3s3;
-    } else {
-        R.ek = 1.0;
-        R.angcor = s[0] - qs1;
-        R.unicor = q2s2 * (1.0 / 3.0);
-        R.totcor = R.angcor + R.unicor;
-        R.r3corr = q2s2 - q3s3;
-    }
-    return R;
 }
 
 // per-particle accumulators; members that a (mode, what) instantiation never touches stay dead and cost nothing
-struct Accum {
-    double U = 0.0, Fx = 0.0, Fy = 0.0, Fz = 0.0, Ex = 0.0, Ey = 0.0, Ez = 0.0, phi = 0.0;
+template <class T> struct AccumT {
+    T U = T(0), Fx = T(0), Fy = T(0), Fz = T(0), Ex = T(0), Ey = T(0), Ez = T(0), phi = T(0);
 };
+typedef AccumT<double> Accum;
 
 // One in-cutoff ordered pair (i <- j), d = r_i - r_j, r2 = |d|^2 < cutoff^2 already established by the caller.
 // Conventions: SURVEY.md 8b / oracle/harness.hpp.
-// `pass` = the pair is inside the cut-off.  The kernels evaluate branch-free (r2 must then be a harmless in-range
-// value when !pass): every contribution carries a scalar factor that is zeroed by a select.
-template <class F, bool YUK, int MODE, int WHAT>
-CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const D3 &d, double r2, double zi,
-                           double zj, const D3 &mui, const D3 &muj, Accum &acc, bool pass = true) {
+// `pass` = the pair is inside the cut-off.  The kernels evaluate branch-free (the radial arithmetic must then stay
+// finite for rejected / absent pairs): every contribution carries a scalar factor that is zeroed by a select.
+template <class F, bool YUK, int MODE, int WHAT, class T = double>
+CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const Vec3T<T> &d, T r2, T zi, T zj,
+                           const Vec3T<T> &mui, const Vec3T<T> &muj, AccumT<T> &acc, bool pass = true) {
     constexpr int ND = derivatives_needed(MODE, WHAT);
     constexpr bool kAngcorOnly = F::kHasAngcor && !YUK && MODE == kModeIon && (WHAT & (kWhatEnergy | kWhatPotential)) == 0;
-    Radial R = radial_terms<F, YUK, ND, kAngcorOnly>(f, cp, r2, tab);
-    const double rinv2 = R.rinv * R.rinv;
-    const double rinv3 = rinv2 * R.rinv;
-    const double ek3 = pass ? R.ek * rinv3 : 0.0; // exp(-kr) / r^3
+    const RadialT<T> R = radial_terms<F, YUK, ND, kAngcorOnly, T>(f, cp, r2, tab);
+    const T rinv2 = R.rinv * R.rinv;
+    const T rinv3 = rinv2 * R.rinv;
+    const T ek3 = pass ? R.ek * rinv3 : T(0); // exp(-kr) / r^3
 
     if (MODE == kModeIon) {
         // ion_potential core.hpp:268-280, ion_field :352-365, ion_ion_energy :501, ion_ion_force :630
         if (WHAT & (kWhatPotential | kWhatEnergy)) {
-            const double p = pass ? zj * R.rinv * R.s0 * R.ek : 0.0;
+            const T p = pass ? zj * R.rinv * R.s0 * R.ek : T(0);
             if (WHAT & kWhatPotential) acc.phi += p;
             if (WHAT & kWhatEnergy) acc.U += zi * p;
         }
         if (WHAT & (kWhatField | kWhatForce)) {
-            const double c = zj * ek3 * R.angcor;
+            const T c = zj * ek3 * R.angcor;
             if (WHAT & kWhatField) {
                 acc.Ex += c * d.x;
                 acc.Ey += c * d.y;
                 acc.Ez += c * d.z;
             }
             if (WHAT & kWhatForce) {
-                const double cf = zi * c;
+                const T cf = zi * c;
                 acc.Fx += cf * d.x;
                 acc.Fy += cf * d.y;
                 acc.Fz += cf * d.z;
@@ -114,14 +119,14 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, 
         return;
     }
 
-    const double mjd = dot(muj, d);
+    const T mjd = dot(muj, d);
     if (MODE == kModeDipole) {
         // dipole_potential :294-307, dipole_field :380-399, dipole_dipole_energy :543-546, dipole_dipole_force :677-702
         if (WHAT & kWhatPotential) acc.phi += mjd * ek3 * R.angcor;
         if (WHAT & (kWhatField | kWhatEnergy)) {
-            const double cd = 3.0 * mjd * rinv2 * R.totcor * ek3; // coefficient of d
-            const double cm = -R.angcor * ek3;                    // coefficient of mu_j  (B - A = -angcor)
-            const double ex = cd * d.x + cm * muj.x, ey = cd * d.y + cm * muj.y, ez = cd * d.z + cm * muj.z;
+            const T cd = T(3) * mjd * rinv2 * R.totcor * ek3; // coefficient of d
+            const T cm = -R.angcor * ek3;                     // coefficient of mu_j  (B - A = -angcor)
+            const T ex = cd * d.x + cm * muj.x, ey = cd * d.y + cm * muj.y, ez = cd * d.z + cm * muj.z;
             if (WHAT & kWhatField) {
                 acc.Ex += ex;
                 acc.Ey += ey;
@@ -130,12 +135,12 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, 
             if (WHAT & kWhatEnergy) acc.U -= mui.x * ex + mui.y * ey + mui.z * ez;
         }
         if (WHAT & kWhatForce) {
-            const double mid = dot(mui, d), mm = dot(mui, muj);
-            const double ab = mid * mjd * rinv2;
-            const double t3 = 3.0 * R.totcor;
-            const double e5 = ek3 * rinv2; // exp(-kr)/r^5
-            const double cd = -(t3 * (5.0 * ab - mm) + ab * R.r3corr) * e5;
-            const double ci = t3 * mjd * e5, cj = t3 * mid * e5;
+            const T mid = dot(mui, d), mm = dot(mui, muj);
+            const T ab = mid * mjd * rinv2;
+            const T t3 = T(3) * R.totcor;
+            const T e5 = ek3 * rinv2; // exp(-kr)/r^5
+            const T cd = -(t3 * (T(5) * ab - mm) + ab * R.r3corr) * e5;
+            const T ci = t3 * mjd * e5, cj = t3 * mid * e5;
             acc.Fx += cd * d.x + ci * mui.x + cj * muj.x;
             acc.Fy += cd * d.y + ci * mui.y + cj * muj.y;
             acc.Fz += cd * d.z + ci * mui.z + cj * muj.z;
@@ -146,30 +151,30 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, 
     // MODE == kModeMultipole: potential = ion_potential + dipole_potential, field = multipole_field :457-486 (quad = 0),
     // energy = multipole_multipole_energy :581-615, force = multipole_multipole_force :737-779, both with A = i,
     // B = j, r = r_j - r_i = -d and zero quadrupoles.
-    if (WHAT & kWhatPotential) acc.phi += (pass ? zj * R.rinv * R.s0 * R.ek : 0.0) + mjd * ek3 * R.angcor;
+    if (WHAT & kWhatPotential) acc.phi += (pass ? zj * R.rinv * R.s0 * R.ek : T(0)) + mjd * ek3 * R.angcor;
     if (WHAT & kWhatField) {
-        const double cd = (zj * R.angcor + 3.0 * mjd * rinv2 * R.totcor) * ek3;
-        const double cm = -R.angcor * ek3;
+        const T cd = (zj * R.angcor + T(3) * mjd * rinv2 * R.totcor) * ek3;
+        const T cm = -R.angcor * ek3;
         acc.Ex += cd * d.x + cm * muj.x;
         acc.Ey += cd * d.y + cm * muj.y;
         acc.Ez += cd * d.z + cm * muj.z;
     }
     if (WHAT & (kWhatEnergy | kWhatForce)) {
-        const double mid = dot(mui, d), mm = dot(mui, muj);
-        const double ab = mid * mjd * rinv2;
+        const T mid = dot(mui, d), mm = dot(mui, muj);
+        const T ab = mid * mjd * rinv2;
         if (WHAT & kWhatEnergy) {
-            const double ion_ion = zi * zj * R.s0 * r2;
-            const double ion_dipole = (zi * mjd - zj * mid) * R.angcor;
-            const double dipole_dipole = -(3.0 * ab - mm) * R.totcor - mm * R.unicor;
+            const T ion_ion = zi * zj * R.s0 * r2;
+            const T ion_dipole = (zi * mjd - zj * mid) * R.angcor;
+            const T dipole_dipole = -(T(3) * ab - mm) * R.totcor - mm * R.unicor;
             acc.U += (ion_ion + ion_dipole + dipole_dipole) * ek3;
         }
         if (WHAT & kWhatForce) {
-            const double t3 = 3.0 * R.totcor;
-            const double e4 = ek3 * R.rinv; // exp(-kr)/r^4
-            const double ar = R.angcor * R.r1;
-            const double cd = (-zi * zj * ar + R.rinv * (t3 * (zi * mjd + zj * mid) - t3 * (5.0 * ab - mm) - ab * R.r3corr)) * e4;
-            const double ci = (-zj * ar + t3 * mjd * R.rinv) * e4;
-            const double cj = (-zi * ar + t3 * mid * R.rinv) * e4;
+            const T t3 = T(3) * R.totcor;
+            const T e4 = ek3 * R.rinv; // exp(-kr)/r^4
+            const T ar = R.angcor * R.r1;
+            const T cd = (-zi * zj * ar + R.rinv * (t3 * (zi * mjd + zj * mid) - t3 * (T(5) * ab - mm) - ab * R.r3corr)) * e4;
+            const T ci = (-zj * ar + t3 * mjd * R.rinv) * e4;
+            const T cj = (-zi * ar + t3 * mid * R.rinv) * e4;
             acc.Fx += cd * d.x + ci * mui.x + cj * muj.x;
             acc.Fy += cd * d.y + ci * mui.y + cj * muj.y;
             acc.Fz += cd * d.z + ci * mui.z + cj * muj.z;

@@ -119,5 +119,30 @@ template <bool SIGNED = false> CG_HD void erfc_and_gauss(double x, double &ec, d
 #endif
 }
 
+// ---- fp32 variants (CG_FP32 kernels): CUDA / libm single-precision functions, no tables ----
+CG_HD float rsqrt_pos(float x) {
+#ifdef __CUDA_ARCH__
+    return rsqrtf(x);
+#else
+    return 1.0f / std::sqrt(x);
+#endif
+}
+CG_HD float exp_any(float y) {
+#ifdef __CUDA_ARCH__
+    return expf(y);
+#else
+    return std::exp(y);
+#endif
+}
+template <bool SIGNED = false> CG_HD void erfc_and_gauss(float x, float &ec, float &E, const double *) {
+#ifdef __CUDA_ARCH__
+    E = expf(-x * x);
+    ec = erfcf(x);
+#else
+    E = std::exp(-x * x);
+    ec = std::erfc(x);
+#endif
+}
+
 } // namespace detail
 } // namespace CoulombGalore

@@ -36,11 +36,11 @@ struct PlainSrf : SrfDefaults { // plain.hpp:47-50
     static constexpr int kTable = kTableNone;
     CG_HD PlainSrf() {}
     CG_HD explicit PlainSrf(const cg_scheme_desc &) {}
-    template <int ND> CG_HD void eval(double, double *s, const double * = nullptr) const {
-        s[0] = 1.0;
-        if (ND >= 1) s[1] = 0.0;
-        if (ND >= 2) s[2] = 0.0;
-        if (ND >= 3) s[3] = 0.0;
+    template <int ND, class T = double> CG_HD void eval(T, T *s, const double * = nullptr) const {
+        s[0] = T(1);
+        if (ND >= 1) s[1] = T(0);
+        if (ND >= 2) s[2] = T(0);
+        if (ND >= 3) s[3] = T(0);
     }
 };
 
@@ -49,12 +49,13 @@ struct ReactionFieldSrf : SrfDefaults { // reactionfield.hpp:60-73: S = 1 + a q^
     double a, b;
     CG_HD ReactionFieldSrf() : a(0), b(0) {}
     CG_HD explicit ReactionFieldSrf(const cg_scheme_desc &d) : a(d.rf_a), b(d.rf_b) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
-        const double aq = a * q, aq2 = aq * q;
-        s[0] = 1.0 + (aq2 - b) * q;
-        if (ND >= 1) s[1] = 3.0 * aq2 - b;
-        if (ND >= 2) s[2] = 6.0 * aq;
-        if (ND >= 3) s[3] = 6.0 * a;
+    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double * = nullptr) const {
+        const T A = (T)a, B = (T)b;
+        const T aq = A * q, aq2 = aq * q;
+        s[0] = T(1) + (aq2 - B) * q;
+        if (ND >= 1) s[1] = T(3) * aq2 - B;
+        if (ND >= 2) s[2] = T(6) * aq;
+        if (ND >= 3) s[3] = T(6) * A;
     }
 };
 
@@ -62,12 +63,12 @@ struct FanourgakisSrf : SrfDefaults { // fanourgakis.hpp:49-61
     static constexpr int kTable = kTableNone;
     CG_HD FanourgakisSrf() {}
     CG_HD explicit FanourgakisSrf(const cg_scheme_desc &) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
-        const double q2 = q * q, a = 1.0 - q, a2 = a * a;
-        s[0] = (a2 * a2) * (1.0 + q * (2.25 + q * (3.0 + 2.5 * q)));
-        if (ND >= 1) s[1] = -1.75 + (q2 * q2) * (26.25 + q * (-42.0 + 17.5 * q));
-        if (ND >= 2) s[2] = 105.0 * (q2 * q) * a2;
-        if (ND >= 3) s[3] = 525.0 * q2 * (q - 0.6) * (q - 1.0);
+    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double * = nullptr) const {
+        const T q2 = q * q, a = T(1) - q, a2 = a * a;
+        s[0] = (a2 * a2) * (T(1) + q * (T(2.25) + q * (T(3) + T(2.5) * q)));
+        if (ND >= 1) s[1] = T(-1.75) + (q2 * q2) * (T(26.25) + q * (T(-42) + T(17.5) * q));
+        if (ND >= 2) s[2] = T(105) * (q2 * q) * a2;
+        if (ND >= 3) s[3] = T(525) * q2 * (q - T(0.6)) * (q - T(1));
     }
 };
 
@@ -76,9 +77,9 @@ struct FanourgakisSrf : SrfDefaults { // fanourgakis.hpp:49-61
 // The factored form is kept (all g_n are positive, no cancellation as q -> 1); derivatives by Leibniz' rule over
 // the factors with the recurrence g_n = 1 + q g_{n-1}, O(P) work instead of the reference's O(P^2) powi loops.
 // ORDER > 0: compile-time order (fully unrolled); ORDER == 0: run-time order.
-template <int ND> CG_HD void jet_mul(double *c, const double *g) { // c <- c * g as Taylor jets up to order ND
-    if (ND >= 3) c[3] = c[3] * g[0] + 3.0 * (c[2] * g[1] + c[1] * g[2]) + c[0] * g[3];
-    if (ND >= 2) c[2] = c[2] * g[0] + 2.0 * c[1] * g[1] + c[0] * g[2];
+template <int ND, class T> CG_HD void jet_mul(T *c, const T *g) { // c <- c * g as Taylor jets up to order ND
+    if (ND >= 3) c[3] = c[3] * g[0] + T(3) * (c[2] * g[1] + c[1] * g[2]) + c[0] * g[3];
+    if (ND >= 2) c[2] = c[2] * g[0] + T(2) * c[1] * g[1] + c[0] * g[2];
     if (ND >= 1) c[1] = c[1] * g[0] + c[0] * g[1];
     c[0] = c[0] * g[0];
 }
@@ -88,32 +89,32 @@ template <int ORDER> struct QPotentialSrf : SrfDefaults {
     int order;
     CG_HD QPotentialSrf() : order(ORDER) {}
     CG_HD explicit QPotentialSrf(const cg_scheme_desc &d) : order(d.order) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double * = nullptr) const {
         const int P = ORDER > 0 ? ORDER : order;
-        double g[4] = {1.0, 0.0, 0.0, 0.0}; // jet of g_1
-        double c[4] = {1.0, 0.0, 0.0, 0.0}; // jet of prod g_n
+        T g[4] = {T(1), T(0), T(0), T(0)}; // jet of g_1
+        T c[4] = {T(1), T(0), T(0), T(0)}; // jet of prod g_n
 #ifdef __CUDACC__
 #pragma unroll
 #endif
         for (int n = 2; n <= P; n++) {
-            if (ND >= 3) g[3] = 3.0 * g[2] + q * g[3];
-            if (ND >= 2) g[2] = 2.0 * g[1] + q * g[2];
+            if (ND >= 3) g[3] = T(3) * g[2] + q * g[3];
+            if (ND >= 2) g[2] = T(2) * g[1] + q * g[2];
             if (ND >= 1) g[1] = g[0] + q * g[1];
-            g[0] = 1.0 + q * g[0];
-            jet_mul<ND>(c, g);
+            g[0] = T(1) + q * g[0];
+            jet_mul<ND, T>(c, g);
         }
         // jet of (1-q)^P
-        const double a = 1.0 - q;
-        double d[4];
-        double ap = (P > 3) ? powi(a, P - 3) : 1.0; // a^(max(P-3,0))
-        d[3] = (P >= 3) ? -(double)(P * (P - 1) * (P - 2)) * ap : 0.0;
+        const T a = T(1) - q;
+        T d[4];
+        T ap = (P > 3) ? powi(a, P - 3) : T(1); // a^(max(P-3,0))
+        d[3] = (P >= 3) ? -(T)(P * (P - 1) * (P - 2)) * ap : T(0);
         if (P >= 3) ap *= a;
-        d[2] = (P >= 2) ? (double)(P * (P - 1)) * ap : 0.0;
+        d[2] = (P >= 2) ? (T)(P * (P - 1)) * ap : T(0);
         if (P >= 2) ap *= a;
-        d[1] = (P >= 1) ? -(double)P * ap : 0.0;
+        d[1] = (P >= 1) ? -(T)P * ap : T(0);
         if (P >= 1) ap *= a;
         d[0] = ap;
-        jet_mul<ND>(c, d);
+        jet_mul<ND, T>(c, d);
         s[0] = c[0];
         if (ND >= 1) s[1] = c[1];
         if (ND >= 2) s[2] = c[2];
@@ -133,39 +134,41 @@ template <int KIND> struct ErfcFamilySrf : SrfDefaults {
     CG_HD explicit ErfcFamilySrf(const cg_scheme_desc &d)
         : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), c(d.erfc_eta), e(d.exp_eta2),
           c2(d.erfc_eta + d.eta * kTwoOverSqrtPi * d.exp_eta2), invF0(KIND == kEwaldT ? 1.0 / d.F0 : 1.0) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double *tab = nullptr) const {
-        const double x = eta * q;
-        double E, ec;
+    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double *tab = nullptr) const {
+        const T x = (T)eta * q;
+        T E, ec;
         erfc_and_gauss(x, ec, E, tab); // ec = erfc(x), E = exp(-x^2)
-        const double k1E = k1 * E;
-        const double g2 = 2.0 * eta2 * q * k1E;                    // 4 eta^3 q E / sqrt(pi)
-        const double g3 = 2.0 * eta2 * k1E * (1.0 - 2.0 * x * x);  // 4 eta^3 (1 - 2 x^2) E / sqrt(pi)
+        const T K1 = (T)k1, C = (T)c, C2 = (T)c2, ETA2 = (T)eta2;
+        const T k1E = K1 * E;
+        const T g2 = T(2) * ETA2 * q * k1E;                  // 4 eta^3 q E / sqrt(pi)
+        const T g3 = T(2) * ETA2 * k1E * (T(1) - T(2) * x * x); // 4 eta^3 (1 - 2 x^2) E / sqrt(pi)
         if (KIND == kWolf) { // wolf.hpp:60-71
-            s[0] = ec - q * c;
-            if (ND >= 1) s[1] = -k1E - c;
+            s[0] = ec - q * C;
+            if (ND >= 1) s[1] = -k1E - C;
             if (ND >= 2) s[2] = g2;
             if (ND >= 3) s[3] = g3;
         } else if (KIND == kFennell) { // fennell.hpp:59-73
-            s[0] = ec - q * c + (q - 1.0) * q * c2;
-            if (ND >= 1) s[1] = -k1E + 2.0 * q * c2 - (c2 + c);
-            if (ND >= 2) s[2] = g2 + 2.0 * c2;
+            s[0] = ec - q * C + (q - T(1)) * q * C2;
+            if (ND >= 1) s[1] = -k1E + T(2) * q * C2 - (C2 + C);
+            if (ND >= 2) s[2] = g2 + T(2) * C2;
             if (ND >= 3) s[3] = g3;
         } else if (KIND == kZeroDipole) { // zerodipole.hpp:61-80
-            const double q2 = q * q;
-            s[0] = ec - q * c + 0.5 * (q2 - 1.0) * q * c2;
-            if (ND >= 1) s[1] = -k1E + 1.5 * q2 * c2 - (0.5 * c2 + c);
-            if (ND >= 2) s[2] = g2 + 3.0 * q * c2;
-            if (ND >= 3) s[3] = g3 + 3.0 * c2;
+            const T q2 = q * q;
+            s[0] = ec - q * C + T(0.5) * (q2 - T(1)) * q * C2;
+            if (ND >= 1) s[1] = -k1E + T(1.5) * q2 * C2 - (T(0.5) * C2 + C);
+            if (ND >= 2) s[2] = g2 + T(3) * q * C2;
+            if (ND >= 3) s[3] = g3 + T(3) * C2;
         } else if (KIND == kZahn) { // zahn.hpp:60-76
-            s[0] = ec - (q - 1.0) * q * c2;
-            if (ND >= 1) s[1] = -k1E - (2.0 * q - 1.0) * c2;
-            if (ND >= 2) s[2] = g2 - 2.0 * c2;
+            s[0] = ec - (q - T(1)) * q * C2;
+            if (ND >= 1) s[1] = -k1E - (T(2) * q - T(1)) * C2;
+            if (ND >= 2) s[2] = g2 - T(2) * C2;
             if (ND >= 3) s[3] = g3;
         } else if (KIND == kEwaldT) { // ewald_truncated.hpp:71-82
-            s[0] = (ec - c - (1.0 - q) * k1 * e) * invF0;
-            if (ND >= 1) s[1] = -(k1E - k1 * e) * invF0;
-            if (ND >= 2) s[2] = g2 * invF0;
-            if (ND >= 3) s[3] = g3 * invF0;
+            const T IF0 = (T)invF0, k1e = K1 * (T)e;
+            s[0] = (ec - C - (T(1) - q) * k1e) * IF0;
+            if (ND >= 1) s[1] = -(k1E - k1e) * IF0;
+            if (ND >= 2) s[2] = g2 * IF0;
+            if (ND >= 3) s[3] = g3 * IF0;
         } else { // Ewald without screening, ewald.hpp:175-195 with zeta = 0
             s[0] = ec;
             if (ND >= 1) s[1] = -k1E;
@@ -175,16 +178,16 @@ template <int KIND> struct ErfcFamilySrf : SrfDefaults {
     }
     // S - q S' with the q-linear and q-polynomial terms of S and q S' cancelled analytically: what ion fields and
     // forces need (core.hpp:352-365 with kappa = 0).  erfc(x) + (2/sqrt(pi)) x exp(-x^2) is common to all kinds.
-    CG_HD double angcor(double q, const double *tab) const {
-        const double x = eta * q;
-        double E, ec;
+    template <class T = double> CG_HD T angcor(T q, const double *tab) const {
+        const T x = (T)eta * q;
+        T E, ec;
         erfc_and_gauss(x, ec, E, tab);
-        const double g = ec + (q * k1) * E;
+        const T g = ec + (q * (T)k1) * E;
         if (KIND == kWolf || KIND == kEwaldPlain) return g;
-        if (KIND == kFennell) return g - (q * q) * c2;
-        if (KIND == kZeroDipole) return g - (q * q) * (q * c2);
-        if (KIND == kZahn) return g + (q * q) * c2;
-        return (g - (c + k1 * e)) * invF0; // kEwaldT
+        if (KIND == kFennell) return g - (q * q) * (T)c2;
+        if (KIND == kZeroDipole) return g - (q * q) * (q * (T)c2);
+        if (KIND == kZahn) return g + (q * q) * (T)c2;
+        return (g - (T)(c + k1 * e)) * (T)invF0; // kEwaldT
     }
 };
 
@@ -198,18 +201,18 @@ struct EwaldScreenedSrf : SrfDefaults {
         : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), zeta(d.zeta), zeta2(d.zeta * d.zeta),
           zeta3(d.zeta * d.zeta * d.zeta), half_z_over_eta(d.zeta / (2.0 * d.eta)), z_over_eta(d.zeta / d.eta),
           z2_over_eta2((d.zeta * d.zeta) / (d.eta * d.eta)) {}
-    template <int ND> CG_HD void eval(double q, double *s, const double *tab = nullptr) const {
-        const double xq = eta * q;
-        const double xm = xq - half_z_over_eta, xp = xq + half_z_over_eta;
-        double ecm, Em, ecp, Ep; // erfc(x-), exp(-x-^2), erfc(x+)
+    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double *tab = nullptr) const {
+        const T xq = (T)eta * q, H = (T)half_z_over_eta, ZE = (T)z_over_eta, Z = (T)zeta, K1 = (T)k1;
+        const T xm = xq - H, xp = xq + H;
+        T ecm, Em, ecp, Ep; // erfc(x-), exp(-x-^2), erfc(x+)
         erfc_and_gauss<true>(xm, ecm, Em, tab);
         erfc_and_gauss<false>(xp, ecp, Ep, tab);
         (void)Ep;
-        const double P = ecp * exp_any(2.0 * zeta * q); // erfc(x+) exp(2 zeta q), as the reference forms it
-        s[0] = 0.5 * (P + ecm);
-        if (ND >= 1) s[1] = -k1 * Em + zeta * P;
-        if (ND >= 2) s[2] = 2.0 * k1 * eta * (xq - z_over_eta) * Em + 2.0 * zeta2 * P;
-        if (ND >= 3) s[3] = 2.0 * k1 * eta2 * (1.0 - 2.0 * (xq - z_over_eta) * xm - z2_over_eta2) * Em + 4.0 * zeta3 * P;
+        const T P = ecp * exp_any(T(2) * Z * q); // erfc(x+) exp(2 zeta q), as the reference forms it
+        s[0] = T(0.5) * (P + ecm);
+        if (ND >= 1) s[1] = -K1 * Em + Z * P;
+        if (ND >= 2) s[2] = T(2) * K1 * (T)eta * (xq - ZE) * Em + T(2) * (T)zeta2 * P;
+        if (ND >= 3) s[3] = T(2) * K1 * (T)eta2 * (T(1) - T(2) * (xq - ZE) * xm - (T)z2_over_eta2) * Em + T(4) * (T)zeta3 * P;
     }
 };
 
@@ -225,48 +228,49 @@ struct PoissonSrf : SrfDefaults {
         : C(d.C), D(d.D), yukawa(d.yukawa_map), rk(d.reduced_kappa), denom(d.yukawa_denom), binomCDC(d.binomCDC) {
         for (int i = 0; i < CG_MAX_POISSON_C; i++) w[i] = d.poisson_w[i];
     }
-    template <int ND> CG_HD void eval(double q, double *s, const double * = nullptr) const {
+    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double * = nullptr) const {
         if (D == -C) { // poisson.hpp:120-122 etc.
-            s[0] = 1.0;
-            if (ND >= 1) s[1] = 0.0;
-            if (ND >= 2) s[2] = 0.0;
-            if (ND >= 3) s[3] = 0.0;
+            s[0] = T(1);
+            if (ND >= 1) s[1] = T(0);
+            if (ND >= 2) s[2] = T(0);
+            if (ND >= 3) s[3] = T(0);
             return;
         }
-        double qp = q, d1 = 1.0, d2 = 0.0, d3 = 0.0;
+        T qp = q, d1 = T(1), d2 = T(0), d3 = T(0);
         if (yukawa) { // :126, :147-149, :174-176, :204-207
-            const double ex = exp_any(2.0 * rk * q);
-            qp = (1.0 - ex) * denom;
-            d1 = -2.0 * rk * ex * denom;
-            d2 = 2.0 * rk * d1;
-            d3 = 2.0 * rk * d2;
+            const T RK = (T)rk, DEN = (T)denom;
+            const T ex = exp_any(T(2) * RK * q);
+            qp = (T(1) - ex) * DEN;
+            d1 = T(-2) * RK * ex * DEN;
+            d2 = T(2) * RK * d1;
+            d3 = T(2) * RK * d2;
         }
         if (D == 0 && C == 1) { // :128-130, :141-143: the derivatives are returned as zero
-            s[0] = 1.0 - qp;
-            if (ND >= 1) s[1] = 0.0;
-            if (ND >= 2) s[2] = 0.0;
-            if (ND >= 3) s[3] = 0.0;
+            s[0] = T(1) - qp;
+            if (ND >= 1) s[1] = T(0);
+            if (ND >= 2) s[2] = T(0);
+            if (ND >= 3) s[3] = T(0);
             return;
         }
         // tmp1 = sum_c w_c qp^c, tmp2 = d tmp1 / d qp  (Horner)
-        double t1 = 0.0, t2 = 0.0;
+        T t1 = T(0), t2 = T(0);
         for (int c = C - 1; c >= 0; c--) {
             t2 = t2 * qp + t1;
-            t1 = t1 * qp + w[c];
+            t1 = t1 * qp + (T)w[c];
         }
-        const double a = 1.0 - qp;
-        const double aD = powi(a, D);
+        const T a = T(1) - qp;
+        const T aD = powi(a, D);
         s[0] = aD * a * t1;
         if (ND >= 1) {
-            const double dS = -(double)(D + 1) * aD * t1 + aD * a * t2;
+            const T dS = -(T)(D + 1) * aD * t1 + aD * a * t2;
             s[1] = dS * d1;
             if (ND >= 2) {
-                const double d2S = binomCDC * powi(a, D - 1) * powi(qp, C - 1);
+                const T d2S = (T)binomCDC * powi(a, D - 1) * powi(qp, C - 1);
                 // the reference adds the chain-rule terms only inside `if (use_yukawa_screening)`; d2 = d3 = 0 otherwise
                 s[2] = d2S * d1 * d1 + dS * d2;
                 if (ND >= 3) {
-                    const double d3S = binomCDC * powi(a, D - 2) * powi(qp, C - 2) * ((2.0 - (double)(C + D)) * qp + (double)C - 1.0);
-                    s[3] = d3S * d1 * d1 * d1 + 3.0 * d2S * d1 * d2 + dS * d3;
+                    const T d3S = (T)binomCDC * powi(a, D - 2) * powi(qp, C - 2) * ((T(2) - (T)(C + D)) * qp + (T)C - T(1));
+                    s[3] = d3S * d1 * d1 * d1 + T(3) * d2S * d1 * d2 + dS * d3;
                 }
             }
         }
@@ -358,15 +362,17 @@ struct SplineSrf : SrfDefaults {
         const double dz = q - k0;
         return c0 + dz * (c1 + dz * (c2 + dz * (c3 + dz * (c4 + dz * (c5)))));
     }
-    template <int ND> __device__ __forceinline__ void eval(double q, double *s, const double *t = nullptr) const {
+    // (fp32 kernels evaluate the tables in fp64 and round the results: the tables are the scheme)
+    template <int ND, class T = double> __device__ __forceinline__ void eval(T qin, T *s, const double *t = nullptr) const {
+        const double q = (double)qin;
         int c = __double2int_rd(q * (double)kSplineGrid);
         c = min(max(c, 0), kSplineGrid - 1);
         unsigned int w;
         asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((unsigned)__cvta_generic_to_shared(t) + 8u * (unsigned)lut_off + 4u * (unsigned)c));
-        s[0] = table(0, q, w, t);
-        if (ND >= 1) s[1] = table(1, q, w, t);
-        if (ND >= 2) s[2] = table(2, q, w, t);
-        if (ND >= 3) s[3] = table(3, q, w, t);
+        s[0] = (T)table(0, q, w, t);
+        if (ND >= 1) s[1] = (T)table(1, q, w, t);
+        if (ND >= 2) s[2] = (T)table(2, q, w, t);
+        if (ND >= 3) s[3] = (T)table(3, q, w, t);
     }
 #else
     inline double table(int k, double q, const double *t) const {
@@ -376,12 +382,13 @@ struct SplineSrf : SrfDefaults {
         const double *c = t + coff[k] + 6 * pos;
         return c[0] + dz * (c[1] + dz * (c[2] + dz * (c[3] + dz * (c[4] + dz * (c[5])))));
     }
-    template <int ND> inline void eval(double q, double *s, const double *t = nullptr) const {
+    template <int ND, class T = double> inline void eval(T qin, T *s, const double *t = nullptr) const {
         const double *p = t ? t : tab;
-        s[0] = table(0, q, p);
-        if (ND >= 1) s[1] = table(1, q, p);
-        if (ND >= 2) s[2] = table(2, q, p);
-        if (ND >= 3) s[3] = table(3, q, p);
+        const double q = (double)qin;
+        s[0] = (T)table(0, q, p);
+        if (ND >= 1) s[1] = (T)table(1, q, p);
+        if (ND >= 2) s[2] = (T)table(2, q, p);
+        if (ND >= 3) s[3] = (T)table(3, q, p);
     }
 #endif
 };

@@ -9,6 +9,7 @@ import coulombgalore_b200 as cg
 from oracle import oracle as O
 
 TOL = 1e-12
+TOL_FP32 = 1e-5  # same norms, fp32 pair arithmetic (SURVEY.md 8d "Parity tolerance")
 INF = float("inf")
 
 
@@ -51,10 +52,12 @@ def compare(gpu, ref, what, tol=TOL):
     return out
 
 
-def run_case(pot, osch, x, y, z, q, mu, box, pbc, mode, what, shard=None):
+def run_case(pot, osch, x, y, z, q, mu, box, pbc, mode, what, shard=None, precision=None):
     ev = cg.BatchedEvaluator(pot)
     if shard:
         ev.set_shard(*shard)
+    if precision:
+        ev.set_precision(precision)
     ev.set_system(x, y, z, q, mu, box, pbc)
     g = ev.eval(mode, what)
     g["counters"] = ev.counters()

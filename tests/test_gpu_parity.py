@@ -5,7 +5,7 @@ import pytest
 import coulombgalore_b200 as cg
 from oracle import oracle as O
 
-from parity import TOL, compare, run_case, splined_pair, zoo
+from parity import TOL, TOL_FP32, compare, run_case, splined_pair, zoo
 
 pytestmark = pytest.mark.gpu
 
@@ -83,3 +83,19 @@ def test_splined_schemes(name, oracle_kind):
     x, y, z, q, mu = lattice(16 if pbc else 10, 3.0, 99, oracle_kind)
     g, r = run_case(pot, osch, x, y, z, q, mu, [48.0] * 3, pbc, cg.MODE_MULTIPOLE, ALL)
     assert_parity(compare(g, r, ALL))
+
+
+@pytest.mark.parametrize("name", sorted(zoo().keys()))
+def test_fp32_variant(name, oracle_kind):
+    """CG_FP32: fp32 pair arithmetic (fp64 positions / distance vector / gate / accumulators) against the fp64 oracle,
+    same norms at 1e-5; the in-cutoff pair count stays exact because the gate is evaluated in fp64."""
+    mk, p = zoo()[name]
+    pot = mk()
+    pbc = pot.cutoff < 1e10
+    x, y, z, q, mu = lattice(16 if pbc else 10, 3.0, 4711, oracle_kind)
+    for mode in (cg.MODE_ION, cg.MODE_MULTIPOLE):
+        g, r = run_case(pot, O.Scheme(p, oracle_kind), x, y, z, q, mu, [48.0] * 3, pbc, mode, ALL, precision="fp32")
+        errs = compare(g, r, ALL, tol=TOL_FP32)
+        bad = {k: v for k, v in errs.items() if not (v <= 1.0)}
+        assert not bad, errs
+        assert max(errs.values()) > 1e-6  # and it really is single precision

@@ -26,6 +26,8 @@ def main():
         N = c["n"] ** 3
         ev = cg.BatchedEvaluator(c["pot"]())
         ev.set_stream(st.cuda_stream)
+        if os.environ.get("CG_PRECISION"):
+            ev.set_precision(os.environ["CG_PRECISION"])
         if os.environ.get("CG_SHARD"):  # emulate one rank of an R-rank run: CG_SHARD=rank,nranks
             ev.set_shard(*[int(v) for v in os.environ["CG_SHARD"].split(",")])
         arr = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(7)]
