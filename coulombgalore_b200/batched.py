@@ -69,15 +69,38 @@ class BatchedEvaluator:
         check(lib.cg_set_system(self.h, self.n, _hp(x), _hp(y), _hp(z), _hp(q), _hp(mx), _hp(my), _hp(mz),
                                 None if b is None else b.ctypes.data_as(_capi._dp), int(bool(pbc))), "cg_set_system", self.h)
 
-    def eval(self, mode, what):
-        """-> dict(force (n,3), field (n,3), potential (n,), energy, pairs); entries not requested are None."""
-        n = self.n
-        f = np.empty((n, 3)) if what & FORCE else None
-        e = np.empty((n, 3)) if what & FIELD else None
-        p = np.empty(n) if what & POTENTIAL else None
+    def _outputs(self, what, out):
+        n, out = self.n, out or {}
+
+        def buf(key, flag, shape):
+            if not what & flag:
+                return None
+            a = out.get(key)
+            if a is None:
+                return np.empty(shape)
+            if a.dtype != np.float64 or a.shape != shape or not a.flags.c_contiguous:
+                raise ValueError("out[%r] must be a C-contiguous float64 array of shape %r" % (key, shape))
+            return a
+        return buf("force", FORCE, (n, 3)), buf("field", FIELD, (n, 3)), buf("potential", POTENTIAL, (n,))
+
+    def eval(self, mode, what, out=None):
+        """-> dict(force (n,3), field (n,3), potential (n,), energy, pairs); entries not requested are None.
+        out: optional dict of caller-owned result arrays (e.g. pinned host memory) to fill instead of new ones."""
+        self.eval_begin(mode, what, out)
+        return self.eval_end()
+
+    def eval_begin(self, mode, what, out=None):
+        """Enqueue the evaluation and the copies into the host arrays; returns at once (see cg_eval_begin)."""
+        f, e, p = self._outputs(what, out)
+        self._pending = (what, f, e, p)
+        check(lib.cg_eval_begin(self.h, mode, what, _hp(f), _hp(e), _hp(p)), "cg_eval_begin", self.h)
+
+    def eval_end(self):
+        what, f, e, p = getattr(self, "_pending", None) or (0, None, None, None)  # nothing in flight: the library says so
+        self._pending = None
         u = C.c_double(0.0)
         cnt = C.c_int64(0)
-        check(lib.cg_eval(self.h, mode, what, _hp(f), _hp(e), _hp(p), C.byref(u), C.byref(cnt)), "cg_eval", self.h)
+        check(lib.cg_eval_end(self.h, C.byref(u), C.byref(cnt)), "cg_eval_end", self.h)
         return dict(force=f, field=e, potential=p, energy=u.value if what & ENERGY else None, pairs=cnt.value)
 
     # ---- device path (zero copy) ----
@@ -111,7 +134,7 @@ class BatchedEvaluator:
     def counters(self):
         c = (C.c_int64 * 8)()
         check(lib.cg_last_counters(self.h, c), "cg_last_counters", self.h)
-        return dict(sorted_entries=c[0], cells=c[1], groups=c[2], pair_launches=c[3], launches=c[4], split=c[5], items=c[7])
+        return dict(sorted_entries=c[0], cells=c[1], groups=c[2], pair_launches=c[3], launches=c[4], split=c[5], sync_free=c[6], items=c[7])
 
     def fp64_peak_probe(self):
         t, ms = C.c_double(0), C.c_double(0)

@@ -132,8 +132,10 @@ __device__ __forceinline__ int images_1d(const SortParams &sp, int d, double v, 
     return m;
 }
 
+// counts[0] = sorted entries, counts[1] = i-groups, counts[2] = overflow flag (an array was smaller than needed)
 template <bool SCATTER>
-__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys) {
+__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int cap,
+                           int *counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= sp.n) return;
     int sx[3], cx[3], sy[3], cy[3], sz[3], cz[3];
@@ -149,16 +151,18 @@ __global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_coun
                 const int slot = atomicAdd(&cell_count[cell], 1);
                 if (SCATTER) {
                     const unsigned int code = (unsigned int)((sx[a] + 1) + 3 * (sy[b] + 1) + 9 * (sz[c] + 1));
-                    keys[cell_start[cell] + slot] = (unsigned int)p * 27u + code;
+                    const int at = cell_start[cell] + slot;
+                    if (at < cap) keys[at] = (unsigned int)p * 27u + code;
+                    else counts[2] = 1;
                 }
             }
 }
 
 // make the order inside every cell deterministic: ascending key (cells hold a handful of entries)
-__global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int *keys) {
+__global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int *keys, int cap) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= ncell) return;
-    const int a = cell_start[c], b = cell_start[c + 1];
+    const int a = min(cell_start[c], cap), b = min(cell_start[c + 1], cap);
     for (int i = a + 1; i < b; i++) {
         const unsigned int k = keys[i];
         int j = i - 1;
@@ -170,9 +174,14 @@ __global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int 
     }
 }
 
-__global__ void gather_kernel(const __grid_constant__ SortParams sp, int n_sorted, const unsigned int *keys, double4 *pos,
+__global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, double4 *pos,
                               double4 *mu, float4 *pos32, int *orig, double far) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_sorted = counts[0];
+    if (n_sorted > cap - 1) { // no room (the dummy entry needs one slot too): flag it, stay inside the arrays
+        if (k == 0) counts[2] = 1;
+        n_sorted = cap - 1;
+    }
     if (k > n_sorted) return;
     if (k == n_sorted) { // dummy entry far outside the system: chargeless, momentless, beyond every cut-off
         pos[k] = make_double4(far, far, far, 0.0);
@@ -277,8 +286,12 @@ static cudaError_t exclusive_scan(const int *in, int *out, int n, int *tmp, cuda
     return cudaGetLastError();
 }
 
-__global__ void scan_total_kernel(const int *in, int *out, int n) { // out[n] = out[n-1] + in[n-1]
-    if (threadIdx.x == 0 && blockIdx.x == 0) out[n] = n > 0 ? out[n - 1] + in[n - 1] : 0;
+__global__ void scan_total_kernel(const int *in, int *out, int n, int *total) { // out[n] = out[n-1] + in[n-1]
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const int t = n > 0 ? out[n - 1] + in[n - 1] : 0;
+        out[n] = t;
+        if (total) *total = t;
+    }
 }
 
 // ---- bounding box for open boundaries ----
@@ -319,9 +332,11 @@ __global__ void combine_kernel(int64_t len, int split, const double *part, doubl
 }
 
 // deterministic: fixed strided partial sums, then a fixed tree
-__global__ void reduce_items_kernel(int items, const double *item_energy, const unsigned long long *item_pairs, double *scalars) {
+__global__ void reduce_items_kernel(const int *counts, int split, const double *item_energy, const unsigned long long *item_pairs,
+                                    double *scalars) {
     __shared__ double se[1024];
     __shared__ unsigned long long sp[1024];
+    const int items = counts[1] * split;
     double e = 0.0;
     unsigned long long c = 0;
     for (int k = threadIdx.x; k < items; k += 1024) {
@@ -341,6 +356,10 @@ __global__ void reduce_items_kernel(int items, const double *item_energy, const 
     if (threadIdx.x == 0) {
         scalars[0] = 0.5 * se[0]; // U = 1/2 sum_i sum_j u_ij
         scalars[1] = (double)sp[0];
+        if (counts[2]) { // an array overflowed in the sync-free path: the results are invalid, make that unmistakable
+            scalars[0] = nan("");
+            scalars[1] = -1.0;
+        }
     }
 }
 
@@ -452,7 +471,26 @@ struct cg_handle {
     // outputs
     DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
     DevBuf<unsigned long long> item_pairs;
-    int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups
+    int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
+    int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
+    DevBuf<int> d_counts;
+    cudaEvent_t counts_ev = nullptr;
+    bool counts_pending = false;
+    // sync-free path: valid while (n, box, pbc, shard) are unchanged and the arrays sized by the last exact run still fit
+    struct {
+        bool valid = false;
+        int64_t n = -1;
+        bool pbc = false;
+        double box[3] = {0, 0, 0};
+        int shard_rank = 0, shard_n = 1;
+        int cap_sorted = 0, last_groups = 0;
+    } fast;
+    bool last_overflow = false;
+    struct {
+        bool active = false;
+        int mode = 0, what = 0;
+        double *force = nullptr, *field = nullptr, *potential = nullptr;
+    } pending; // cg_eval_begin .. cg_eval_end
     double *h_minmax = nullptr;  // pinned
     double *h_scalars = nullptr; // pinned
     double ms[4] = {0, 0, 0, 0};
@@ -552,6 +590,9 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
     bool ok = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_counts, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&h->h_counts_async, 4 * sizeof(int)) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->counts_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && h->d_counts.ensure(8) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_minmax, 6 * 64 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_scalars, 2 * sizeof(double)) == cudaSuccess;
     if (!ok) {
@@ -593,6 +634,9 @@ int cg_destroy(cg_handle *h) {
     h->scalars.release();
     h->item_pairs.release();
     if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_counts_async) cudaFreeHost(h->h_counts_async);
+    if (h->counts_ev) cudaEventDestroy(h->counts_ev);
+    h->d_counts.release();
     if (h->h_minmax) cudaFreeHost(h->h_minmax);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
     for (auto &e : h->ev)
@@ -787,40 +831,76 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     const int ncell = sp.ntot[0] * sp.ntot[1] * sp.nzl;
     const int nrows_prim = sp.row1 - sp.row0;
 
+    // ---- sync-free fast path?  The previous evaluation left its device counts in pinned memory. ----
+    if (h->counts_pending && cudaEventQuery(h->counts_ev) == cudaSuccess) { // never wait: a stale view only delays the fallback
+        h->counts_pending = false;
+        h->counters[0] = h->h_counts_async[0];
+        h->counters[2] = h->h_counts_async[1];
+        h->last_overflow = h->h_counts_async[2] != 0;
+        h->fast.last_groups = h->h_counts_async[1];
+        if (h->last_overflow || h->h_counts_async[0] + 1024 > h->fast.cap_sorted) h->fast.valid = false;
+    }
+    static const bool fast_enabled = [] {
+        const char *e = std::getenv("CG_SYNC_FREE");
+        return !(e && e[0] == '0');
+    }();
+    const bool fast = fast_enabled && h->fast.valid && h->pbc && h->fast.pbc && h->fast.n == h->n && h->fast.shard_rank == h->shard_rank &&
+                      h->fast.shard_n == h->shard_n && h->fast.box[0] == h->box[0] && h->fast.box[1] == h->box[1] && h->fast.box[2] == h->box[2];
+
     // ---- 1-3. histogram, scan, groups ----
+    int *counts = h->d_counts.p;
     CG_CUDA(h, h->cell_count.ensure((size_t)ncell + 1));
     CG_CUDA(h, h->cell_start.ensure((size_t)ncell + 2));
     CG_CUDA(h, h->scan_tmp.ensure(4 * ((size_t)std::max(ncell, nrows_prim) / kScanTile + 8) + 64));
     CG_CUDA(h, h->row_ngroups.ensure((size_t)nrows_prim + 1));
     CG_CUDA(h, h->row_gstart.ensure((size_t)nrows_prim + 2));
     CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
+    CG_CUDA(h, cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
     const int nb_p = (n + 255) / 256;
-    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, nullptr, nullptr);
+    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, nullptr, nullptr, 0, counts);
     launches++;
     CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, &launches));
-    scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell);
+    scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell, counts + 0);
     launches++;
     row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
     launches++;
     CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, &launches));
-    scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim);
+    scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim, counts + 1);
     launches++;
-    CG_CUDA(h, cudaMemcpyAsync(&h->h_counts[0], h->cell_start.p + ncell, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CG_CUDA(h, cudaMemcpyAsync(&h->h_counts[1], h->row_gstart.p + nrows_prim, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CG_CUDA(h, cudaStreamSynchronize(st));
-    const int n_sorted = h->h_counts[0], n_groups = h->h_counts[1];
+    int cap_sorted, ng_bound, ng_guess;
+    if (fast) { // array sizes and the launch shape come from the previous evaluation; no host round trip
+        cap_sorted = h->fast.cap_sorted;
+        ng_bound = n / 32 + nrows_prim + 2; // every primary row adds at most one partial group
+        ng_guess = h->fast.last_groups;
+    } else {
+        CG_CUDA(h, cudaMemcpyAsync(h->h_counts, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CG_CUDA(h, cudaStreamSynchronize(st));
+        const int n_sorted = h->h_counts[0];
+        cap_sorted = n_sorted + n_sorted / 12 + 4096;
+        ng_bound = ng_guess = h->h_counts[1];
+        h->counters[0] = n_sorted;
+        h->counters[2] = h->h_counts[1];
+        h->fast.valid = h->pbc;
+        h->fast.n = h->n;
+        h->fast.pbc = h->pbc;
+        for (int d = 0; d < 3; d++) h->fast.box[d] = h->box[d];
+        h->fast.shard_rank = h->shard_rank;
+        h->fast.shard_n = h->shard_n;
+        h->fast.cap_sorted = cap_sorted;
+        h->fast.last_groups = ng_guess;
+    }
 
     // ---- 4-5. scatter, deterministic order, gather ----
-    CG_CUDA(h, h->keys.ensure((size_t)n_sorted));
-    CG_CUDA(h, h->pos.ensure((size_t)n_sorted + 1));
+    CG_CUDA(h, h->keys.ensure((size_t)cap_sorted));
+    CG_CUDA(h, h->pos.ensure((size_t)cap_sorted));
     const bool need_mu = mode != CG_MODE_ION;
-    if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)n_sorted + 1));
-    CG_CUDA(h, h->pos32.ensure((size_t)n_sorted));
-    CG_CUDA(h, h->orig.ensure((size_t)n_sorted));
-    CG_CUDA(h, h->groups.ensure((size_t)n_groups + 1));
+    if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)cap_sorted));
+    CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
+    CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
+    CG_CUDA(h, h->groups.ensure((size_t)ng_bound + 1));
     CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
-    bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, h->cell_start.p, h->keys.p);
-    cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ncell, h->cell_start.p, h->keys.p);
+    bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, h->cell_start.p, h->keys.p, cap_sorted, counts);
+    cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ncell, h->cell_start.p, h->keys.p, cap_sorted);
     double far_coord;
     {
         double span = 0.0, lo = 0.0;
@@ -830,16 +910,19 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         }
         far_coord = lo - 4.0 * span - 4.0 * std::min(rc, 1e9) - 1.0;
     }
-    gather_kernel<<<(n_sorted + 256) / 256, 256, 0, st>>>(sp, n_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p, h->orig.p,
-                                                       far_coord);
+    gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p,
+                                                         h->orig.p, far_coord);
     row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
     launches += 4;
     CG_CUDA(h, cudaGetLastError());
+    // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
+    CG_CUDA(h, cudaMemcpyAsync(h->h_counts_async, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CG_CUDA(h, cudaEventRecord(h->counts_ev, st));
+    h->counts_pending = true;
     CG_CUDA(h, cudaEventRecord(h->ev[1], st));
 
     // ---- 6. pair kernel ----
-    const int g0 = 0, g1 = n_groups; // the group table already holds only this shard's rows
-    const int ng = g1 - g0;
+    const int ng = ng_guess; // groups of this shard (the previous evaluation's count in the sync-free path)
     int device_sms = 148;
     cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, h->device);
     static const int split_env = [] {
@@ -851,7 +934,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     const int wave = device_sms * 2 * kWarpsPerCta;
     if (ng > 0 && ng < wave) split = std::min(64, (2 * wave + ng - 1) / ng);
     if (split_env > 0) split = std::min(64, split_env);
-    const int items = ng * split;
+    const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split
 
     // smallest instantiated (mode, what) superset
     int ci = -1;
@@ -871,8 +954,10 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     kp.orig = h->orig.p;
     kp.cell_start = h->cell_start.p;
     kp.groups = h->groups.p;
-    kp.group_begin = g0;
-    kp.group_end = g1;
+    kp.group_begin = 0;
+    kp.group_end = ng_bound;
+    kp.counts = counts;
+    kp.cap_sorted = cap_sorted;
     kp.split = split;
     kp.nx = sp.ntot[0];
     kp.ny = sp.ntot[1];
@@ -911,7 +996,6 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     kp.core.cutoff_squared = D.cutoff_squared;
     kp.core.kappa = D.inverse_debye_length;
     kp.n = n;
-    kp.dummy = n_sorted;
     CG_CUDA(h, h->item_energy.ensure((size_t)std::max(items, 1)));
     CG_CUDA(h, h->item_pairs.ensure((size_t)std::max(items, 1)));
     kp.item_energy = h->item_energy.p;
@@ -976,18 +1060,16 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
             launches++;
         }
     }
-    reduce_items_kernel<<<1, 1024, 0, st>>>(items, h->item_energy.p, h->item_pairs.p, d_scalars);
+    reduce_items_kernel<<<1, 1024, 0, st>>>(counts, split, h->item_energy.p, h->item_pairs.p, d_scalars);
     launches++;
     CG_CUDA(h, cudaGetLastError());
     CG_CUDA(h, cudaEventRecord(h->ev[3], st));
-    h->counters[0] = n_sorted;
     h->counters[1] = ncell;
-    h->counters[2] = n_groups;
     h->counters[3] = pair_launches;
     h->counters[4] = launches;
     h->counters[5] = split;
-    h->counters[6] = 0;
-    h->counters[7] = items;
+    h->counters[6] = fast ? 1 : 0;
+    h->counters[7] = (int64_t)ng_guess * split;
     return CG_OK;
 }
 
@@ -996,7 +1078,7 @@ int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *fiel
     return eval_device_impl(h, mode, what, force, field, potential, scalars);
 }
 
-int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
+int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field, double *potential) {
     if (!h) return CG_ERR_INVALID;
     cudaSetDevice(h->device);
     const size_t n = (size_t)h->n;
@@ -1027,10 +1109,34 @@ int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, doub
     if (de) CG_CUDA(h, cudaMemcpyAsync(field, de, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (dp) CG_CUDA(h, cudaMemcpyAsync(potential, dp, n * sizeof(double), cudaMemcpyDeviceToHost, st));
     CG_CUDA(h, cudaMemcpyAsync(h->h_scalars, h->scalars.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CG_CUDA(h, cudaStreamSynchronize(st));
+    h->pending = {true, mode, what, force, field, potential};
+    return CG_OK;
+}
+
+int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
+    if (!h) return CG_ERR_INVALID;
+    if (!h->pending.active) {
+        h->err = "cg_eval_end without cg_eval_begin";
+        return CG_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    CG_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->pending.active = false;
+    if (h->counts_pending && h->h_counts_async[2] != 0) { // the sync-free sizing was too small: redo with exact sizes
+        h->counts_pending = false;
+        h->fast.valid = false;
+        const int rc = cg_eval_begin(h, h->pending.mode, h->pending.what, h->pending.force, h->pending.field, h->pending.potential);
+        if (rc != CG_OK) return rc;
+        return cg_eval_end(h, energy, pairs);
+    }
     if (energy) *energy = h->h_scalars[0];
     if (pairs) *pairs = (int64_t)(h->h_scalars[1] + 0.5);
     return CG_OK;
+}
+
+int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
+    const int rc = cg_eval_begin(h, mode, what, force, field, potential);
+    return rc != CG_OK ? rc : cg_eval_end(h, energy, pairs);
 }
 
 int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out) {
@@ -1062,6 +1168,10 @@ int cg_last_timings(cg_handle *h, double ms[4]) {
 
 int cg_last_counters(cg_handle *h, int64_t c[8]) {
     if (!h || !c) return CG_ERR_INVALID;
+    if (h->counts_pending && cudaEventQuery(h->counts_ev) == cudaSuccess) {
+        h->counters[0] = h->h_counts_async[0];
+        h->counters[2] = h->h_counts_async[1];
+    }
     for (int k = 0; k < 8; k++) c[k] = h->counters[k];
     return CG_OK;
 }

@@ -49,7 +49,8 @@ struct KParams {
     double rc2_safe;      // cutoff_squared / 4 (1 for Plain): the r2 a lane without work feeds to the branch-free arithmetic
     cgd::CoreParams core;
     int n;                // number of (original) particles
-    int dummy;            // index of the far-away dummy entry appended to pos/mu (gathered by lanes that ran dry)
+    const int *counts;    // device counts of this evaluation: [0] sorted entries, [1] i-groups, [2] overflow flag
+    int cap_sorted;       // capacity of the sorted arrays (the far-away dummy entry sits at min(counts[0], cap_sorted - 1))
     // outputs, indexed by original particle index; with split > 1 they are [split][n] partial buffers
     double *force, *field, *potential;
     double *item_energy;              // [items] sum_j u_ij over the item's pairs (not yet halved)

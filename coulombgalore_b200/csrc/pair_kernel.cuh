@@ -78,9 +78,11 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         tab = s_table;
     }
     const int item = blockIdx.x * kWarpsPerCta + warp;
-    if (item >= items) return;
-    const unsigned full = 0xffffffffu;
     const int split = p.split;
+    // `items` is only the launch bound; after an overflow the cell table points past the sorted arrays: touch nothing
+    if (item >= items || item >= p.counts[1] * split || p.counts[2] != 0) return;
+    const int dummy = min(p.counts[0], p.cap_sorted - 1);
+    const unsigned full = 0xffffffffu;
     const int g = p.group_begin + item / split, slice = item - (item / split) * split;
     const int2 grp = p.groups[g];
     const bool active = lane < grp.y;
@@ -225,7 +227,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         auto pop = [&](bool &has) -> int {
             has = cnt > 0;
             const int b = 31 - __clz((int)cur); // highest set bit (-1 when empty)
-            const int j = has ? base + (b ^ 7) : p.dummy;
+            const int j = has ? base + (b ^ 7) : dummy;
             cur &= ~(has ? (1u << b) : 0u);
             cnt -= has ? 1 : 0;
             if (cur == 0u && cnt > 0) {

@@ -159,6 +159,12 @@ int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double 
  * *energy (total U), *pairs (ordered in-cutoff pair count).  Blocks until the results are in the buffers. */
 int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy,
             int64_t *pairs);
+/* The same call in two halves, so that several handles (one per scheme, each on its own stream) overlap their
+ * uploads, kernels and downloads: cg_eval_begin enqueues the evaluation and the copies into the HOST buffers (pinned
+ * buffers make the copies truly asynchronous; pageable ones work, staged by the driver) and returns at once;
+ * cg_eval_end waits, and hands out U and the pair count.  The buffers must stay valid until cg_eval_end returns. */
+int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field, double *potential);
+int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs);
 /* Same with DEVICE output buffers; scalars[0] = U, scalars[1] = pair count (as double), on the device.
  * Asynchronous on the handle's stream. */
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,

@@ -50,6 +50,11 @@ class BatchedEvaluator {
         check(cg_eval(h_, mode, what, force, field, potential, energy, pairs), "cg_eval");
     }
     /** device outputs; scalars[0] = U, scalars[1] = pair count; asynchronous on the handle's stream */
+    // the same in two halves (several evaluators overlap their copies and kernels; buffers stay valid until eval_end)
+    void eval_begin(int mode, int what, double *force, double *field, double *potential) {
+        check(cg_eval_begin(h_, mode, what, force, field, potential), "cg_eval_begin");
+    }
+    void eval_end(double *energy, int64_t *pairs) { check(cg_eval_end(h_, energy, pairs), "cg_eval_end"); }
     void eval_device(int mode, int what, double *force, double *field, double *potential, double *scalars) {
         check(cg_eval_device(h_, mode, what, force, field, potential, scalars), "cg_eval_device");
     }

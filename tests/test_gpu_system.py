@@ -118,6 +118,55 @@ def test_device_pointer_path_equals_host_path_and_is_deterministic():
     assert np.array_equal(outs[0][0], h["force"]) and outs[0][1][0] == h["energy"] and int(outs[0][1][1]) == h["pairs"]
 
 
+def test_two_schemes_in_flight_with_caller_owned_buffers(oracle_kind):
+    """cg_eval_begin / cg_eval_end: two handles evaluate concurrently into caller-owned (here pinned) host arrays."""
+    import torch
+    x, y, z, q, mu = O.generate(14, 3.0, 99, oracle_kind)
+    box, w = [42.0] * 3, cg.ENERGY | cg.FORCE | cg.POTENTIAL
+    names = ("wolf", "fennell")
+    evs = {k: cg.BatchedEvaluator(zoo()[k][0]()) for k in names}
+    outs = {k: dict(force=torch.empty((x.size, 3), dtype=torch.float64).pin_memory().numpy(), potential=np.empty(x.size)) for k in names}
+    for rep in range(2):  # the second round runs the sync-free path
+        for k, ev in evs.items():
+            ev.set_system(x, y, z, q, None, box, True)
+            ev.eval_begin(cg.MODE_ION, w, out=outs[k])
+        for k, ev in evs.items():
+            g = ev.eval_end()
+            assert g["force"] is outs[k]["force"] and g["potential"] is outs[k]["potential"]
+            ok(compare(g, O.Scheme(zoo()[k][1], oracle_kind).batched(x, y, z, q, None, box, True, cg.MODE_ION, w), w))
+    with pytest.raises(cg.CgError):
+        evs["wolf"].eval_end()  # nothing in flight
+    with pytest.raises(ValueError):
+        evs["wolf"].eval(cg.MODE_ION, cg.FORCE, out=dict(force=np.empty((3, 3))))
+
+
+def test_sync_free_path_and_its_overflow_fallback(oracle_kind):
+    """The second evaluation of a same-shaped periodic system sizes its arrays and launches from the previous one (no host
+    round trip).  When the new positions need more room than that (all particles near the box corners: each gets seven
+    periodic images inside the halo), the device flags the overflow and the host call redoes the evaluation exactly."""
+    rng = np.random.default_rng(11)
+    n, L = 6000, 64.0
+    box = [L] * 3
+    q = rng.choice([-1.0, 1.0], n)
+    mk, p = zoo()["wolf"]
+    osch = O.Scheme(p, oracle_kind)
+    w = cg.ENERGY | cg.FORCE
+    centre = [rng.uniform(20.0, 44.0, n) for _ in range(3)]  # no particle within R_c of a face: no images at all
+    uniform = [rng.uniform(0.0, L, n) for _ in range(3)]
+    corners = [np.where(rng.random(n) < 0.5, rng.uniform(0.0, 5.0, n), rng.uniform(L - 5.0, L, n)) for _ in range(3)]
+    ev = cg.BatchedEvaluator(mk())
+    seen = []
+    for pos in (centre, centre, uniform, corners, corners, centre):
+        ev.set_system(pos[0], pos[1], pos[2], q, None, box, True)
+        g = ev.eval(cg.MODE_ION, w)
+        seen.append(ev.counters()["sync_free"])
+        ok(compare(g, osch.batched(pos[0], pos[1], pos[2], q, None, box, True, cg.MODE_ION, w), w))
+    # 1st: exact sizing; 2nd: sync-free; 3rd/4th: more images than the arrays hold -> detected, redone exactly
+    assert seen[0] == 0 and seen[1] == 1, seen
+    assert 0 in seen[2:4], seen
+    ev.close()
+
+
 def test_shards_partition_the_work(oracle_kind):
     x, y, z, q, mu = O.generate(16, 3.0, 7, oracle_kind)
     mk, p = zoo()["reactionfield"]
