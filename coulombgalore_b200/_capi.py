@@ -77,6 +77,7 @@ def _load():
         "cg_destroy": [H],
         "cg_set_stream": [H, C.c_void_p],
         "cg_set_precision": [H, C.c_int],
+        "cg_share_system": [H, H],
         "cg_set_shard": [H, C.c_int, C.c_int],
         "cg_set_system": [H, C.c_int64] + [C.c_void_p] * 7 + [_dp, C.c_int],
         "cg_set_system_device": [H, C.c_int64] + [C.c_void_p] * 7 + [_dp, C.c_int],
@@ -110,7 +111,7 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_scheme_qpotential5", "cg_scheme_fanourgakis", "cg_scheme_fennell", "cg_scheme_zerodipole",
             "cg_scheme_zahn", "cg_scheme_wolf", "cg_scheme_ewald", "cg_scheme_ewaldt", "cg_spline_storage_doubles",
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
-            "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_set_shard",
+            "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
             "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_srf_device", "cg_last_timings",
             "cg_last_counters", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
 

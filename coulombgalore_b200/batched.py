@@ -36,6 +36,7 @@ class BatchedEvaluator:
         check(lib.cg_create(C.byref(scheme.desc), device, C.byref(self.h)), "cg_create")
         self.n = 0
         self._keep = None
+        self._source = None
 
     def close(self):
         if self.h is not None and self.h.value:
@@ -56,6 +57,12 @@ class BatchedEvaluator:
         code = {"fp64": 0, "fp32": 1}[precision]
         check(lib.cg_set_precision(self.h, code), "cg_set_precision", self.h)
 
+    def share_system(self, source):
+        """Evaluate this scheme on `source`'s system (same cut-off): one upload, binning and sort per configuration for
+        any number of schemes.  Evaluate `source` first after each of its set_system calls.  None detaches."""
+        check(lib.cg_share_system(self.h, None if source is None else source.h), "cg_share_system", self.h)
+        self._source = source
+
     def set_shard(self, rank, nranks):
         check(lib.cg_set_shard(self.h, rank, nranks), "cg_set_shard", self.h)
 
@@ -70,7 +77,7 @@ class BatchedEvaluator:
                                 None if b is None else b.ctypes.data_as(_capi._dp), int(bool(pbc))), "cg_set_system", self.h)
 
     def _outputs(self, what, out):
-        n, out = self.n, out or {}
+        n, out = (self._source.n if self._source is not None else self.n), out or {}
 
         def buf(key, flag, shape):
             if not what & flag:

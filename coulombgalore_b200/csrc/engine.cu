@@ -441,6 +441,14 @@ template <class T> struct DevBuf {
     }
 };
 
+// what the spatial sort of a handle produced (the arrays themselves live in the handle's DevBufs)
+struct Sorted {
+    SortParams sp;
+    int ncell = 0, nrows_prim = 0, cap_sorted = 0, ng_bound = 0, ng_guess = 0;
+    bool has_mu = false, fast = false, valid = false;
+    double rc = 0.0; // the cut-off the cell grid was built for
+};
+
 struct cg_handle {
     int device = 0;
     cg_scheme_desc desc;
@@ -486,6 +494,11 @@ struct cg_handle {
         int cap_sorted = 0, last_groups = 0;
     } fast;
     bool last_overflow = false;
+    Sorted sorted;
+    cudaEvent_t sorted_ev = nullptr, pair_done_ev = nullptr;
+    cg_handle *share_from = nullptr;     // cg_share_system: evaluate on that handle's sorted system
+    std::vector<cg_handle *> borrowers;  // handles whose share_from is this one
+    std::vector<cg_handle *> readers;    // borrowers with a pair kernel in flight on the current sorted arrays
     struct {
         bool active = false;
         int mode = 0, what = 0;
@@ -507,6 +520,15 @@ static thread_local std::string g_create_error;
             return (e__ == cudaErrorMemoryAllocation) ? CG_ERR_ALLOC : CG_ERR_CUDA;                                 \
         }                                                                                                           \
     } while (0)
+
+static void detach_share(cg_handle *h) {
+    cg_handle *s = h->share_from;
+    if (!s) return;
+    auto drop = [h](std::vector<cg_handle *> &v) { v.erase(std::remove(v.begin(), v.end(), h), v.end()); };
+    drop(s->borrowers);
+    drop(s->readers);
+    h->share_from = nullptr;
+}
 
 extern "C" {
 
@@ -592,6 +614,8 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
     ok = ok && cudaMallocHost((void **)&h->h_counts, 4 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_counts_async, 4 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->counts_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->sorted_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->pair_done_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && h->d_counts.ensure(8) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_minmax, 6 * 64 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_scalars, 2 * sizeof(double)) == cudaSuccess;
@@ -609,6 +633,12 @@ int cg_destroy(cg_handle *h) {
     if (!h) return CG_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    detach_share(h);
+    for (cg_handle *b : h->borrowers) { // their kernels read this handle's arrays: let them finish, then cut the link
+        cudaStreamSynchronize(b->stream);
+        b->share_from = nullptr;
+    }
+    h->borrowers.clear();
     for (auto &b : h->own_in) b.release();
     h->d_table.release();
     h->d_erfc_table.release();
@@ -636,6 +666,8 @@ int cg_destroy(cg_handle *h) {
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_counts_async) cudaFreeHost(h->h_counts_async);
     if (h->counts_ev) cudaEventDestroy(h->counts_ev);
+    if (h->sorted_ev) cudaEventDestroy(h->sorted_ev);
+    if (h->pair_done_ev) cudaEventDestroy(h->pair_done_ev);
     h->d_counts.release();
     if (h->h_minmax) cudaFreeHost(h->h_minmax);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -658,6 +690,30 @@ int cg_set_precision(cg_handle *h, int precision) {
     return CG_OK;
 }
 
+int cg_share_system(cg_handle *h, cg_handle *source) {
+    if (!h || source == h) return CG_ERR_INVALID;
+    if (source && (source->share_from || source->device != h->device)) {
+        h->err = "cg_share_system: the source must own its system and live on the same device";
+        return CG_ERR_INVALID;
+    }
+    if (source && source->desc.cutoff != h->desc.cutoff) {
+        h->err = "cg_share_system: both schemes need the same cut-off (the cell grid is built for it)";
+        return CG_ERR_UNSUPPORTED;
+    }
+    if (!h->borrowers.empty()) {
+        h->err = "cg_share_system: this handle lends its own system";
+        return CG_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    detach_share(h);
+    if (source) {
+        h->share_from = source;
+        source->borrowers.push_back(h);
+    }
+    return CG_OK;
+}
+
 int cg_set_shard(cg_handle *h, int rank, int nranks) {
     if (!h || nranks < 1 || rank < 0 || rank >= nranks) return CG_ERR_INVALID;
     h->shard_rank = rank;
@@ -666,6 +722,10 @@ int cg_set_shard(cg_handle *h, int rank, int nranks) {
 }
 
 static int set_system_common(cg_handle *h, int64_t n, const double *box, int pbc) {
+    if (h->share_from) {
+        h->err = "this handle evaluates another handle's system (cg_share_system); detach it first";
+        return CG_ERR_STATE;
+    }
     if (n < 0 || n > 150000000LL) {
         h->err = "particle count out of range";
         return CG_ERR_INVALID;
@@ -684,6 +744,7 @@ static int set_system_common(cg_handle *h, int64_t n, const double *box, int pbc
     }
     h->n = n;
     h->have_system = true;
+    h->sorted.valid = false; // borrowers must wait for this handle's next evaluation
     return CG_OK;
 }
 
@@ -719,32 +780,18 @@ int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double 
     return CG_OK;
 }
 
-// the evaluation proper; outputs are device pointers (may be null)
-static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars) {
-    if (!h->have_system) {
-        h->err = "cg_eval before cg_set_system";
-        return CG_ERR_STATE;
-    }
-    if (mode < 0 || mode > 2 || (what & ~15) || what == 0) return CG_ERR_INVALID;
-    cudaSetDevice(h->device);
+// ---- binning, spatial sort and i-groups of the handle's own system (steps 0-5); the result is described by h->sorted ----
+static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
     cudaStream_t st = h->stream;
-    int launches = 0, pair_launches = 0;
-    CG_CUDA(h, cudaEventRecord(h->ev[0], st));
-    if (!d_scalars) {
-        CG_CUDA(h, h->scalars.ensure(2));
-        d_scalars = h->scalars.p;
-    }
     const int n = (int)h->n;
-    if (n == 0) {
-        CG_CUDA(h, cudaMemsetAsync(d_scalars, 0, 2 * sizeof(double), st));
-        for (int k = 1; k < 4; k++) CG_CUDA(h, cudaEventRecord(h->ev[k], st));
-        return CG_OK;
-    }
-    const cg_scheme_desc &D = h->desc;
-    const double rc = D.cutoff;
-
+    const double rc = h->desc.cutoff;
+    // evaluations of other handles that borrowed the previous sorted arrays must have finished reading them
+    for (cg_handle *r : h->readers) CG_CUDA(h, cudaStreamWaitEvent(st, r->pair_done_ev, 0));
+    h->readers.clear();
     // ---- 0. cell grid ----
-    SortParams sp;
+    Sorted &S = h->sorted;
+    S.valid = false;
+    SortParams &sp = S.sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.n = n;
     sp.x = h->in[0];
@@ -765,7 +812,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         const int nb = 64;
         CG_CUDA(h, h->minmax_partial.ensure(6 * nb));
         minmax_kernel<<<nb, 256, 0, st>>>(n, sp.x, sp.y, sp.z, h->minmax_partial.p);
-        launches++;
+        (*launches_out)++;
         CG_CUDA(h, cudaMemcpyAsync(h->h_minmax, h->minmax_partial.p, 6 * nb * sizeof(double), cudaMemcpyDeviceToHost, st));
         CG_CUDA(h, cudaStreamSynchronize(st));
         for (int d = 0; d < 3; d++) {
@@ -830,6 +877,8 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     }
     const int ncell = sp.ntot[0] * sp.ntot[1] * sp.nzl;
     const int nrows_prim = sp.row1 - sp.row0;
+    S.ncell = ncell;
+    S.nrows_prim = nrows_prim;
 
     // ---- sync-free fast path?  The previous evaluation left its device counts in pinned memory. ----
     if (h->counts_pending && cudaEventQuery(h->counts_ev) == cudaSuccess) { // never wait: a stale view only delays the fallback
@@ -858,15 +907,15 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     CG_CUDA(h, cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
     const int nb_p = (n + 255) / 256;
     bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, nullptr, nullptr, 0, counts);
-    launches++;
-    CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, &launches));
+    (*launches_out)++;
+    CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, launches_out));
     scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell, counts + 0);
-    launches++;
+    (*launches_out)++;
     row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
-    launches++;
-    CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, &launches));
+    (*launches_out)++;
+    CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, launches_out));
     scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim, counts + 1);
-    launches++;
+    (*launches_out)++;
     int cap_sorted, ng_bound, ng_guess;
     if (fast) { // array sizes and the launch shape come from the previous evaluation; no host round trip
         cap_sorted = h->fast.cap_sorted;
@@ -893,7 +942,6 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     // ---- 4-5. scatter, deterministic order, gather ----
     CG_CUDA(h, h->keys.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->pos.ensure((size_t)cap_sorted));
-    const bool need_mu = mode != CG_MODE_ION;
     if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
@@ -913,12 +961,74 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p,
                                                          h->orig.p, far_coord);
     row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
-    launches += 4;
+    *launches_out += 4;
     CG_CUDA(h, cudaGetLastError());
     // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
     CG_CUDA(h, cudaMemcpyAsync(h->h_counts_async, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CG_CUDA(h, cudaEventRecord(h->counts_ev, st));
     h->counts_pending = true;
+    S.rc = rc;
+    S.cap_sorted = cap_sorted;
+    S.ng_bound = ng_bound;
+    S.ng_guess = ng_guess;
+    S.has_mu = need_mu;
+    S.fast = fast;
+    S.valid = true;
+    CG_CUDA(h, cudaEventRecord(h->sorted_ev, st));
+    return CG_OK;
+}
+
+// the evaluation proper; outputs are device pointers (may be null)
+static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars) {
+    cg_handle *sys = h->share_from ? h->share_from : h;
+    if (!sys->have_system) {
+        h->err = "cg_eval before cg_set_system";
+        return CG_ERR_STATE;
+    }
+    if (mode < 0 || mode > 2 || (what & ~15) || what == 0) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->stream;
+    int launches = 0, pair_launches = 0;
+    CG_CUDA(h, cudaEventRecord(h->ev[0], st));
+    if (!d_scalars) {
+        CG_CUDA(h, h->scalars.ensure(2));
+        d_scalars = h->scalars.p;
+    }
+    const int n = (int)sys->n;
+    if (n == 0) {
+        CG_CUDA(h, cudaMemsetAsync(d_scalars, 0, 2 * sizeof(double), st));
+        for (int k = 1; k < 4; k++) CG_CUDA(h, cudaEventRecord(h->ev[k], st));
+        return CG_OK;
+    }
+    const cg_scheme_desc &D = h->desc;
+    const double rc = D.cutoff;
+
+    // ---- 0-5. the sorted system: the handle's own, or borrowed from the handle named by cg_share_system ----
+    cg_handle *s = h->share_from ? h->share_from : h;
+    if (s == h) {
+        const bool need_mu = h->in[4] != nullptr && (mode != CG_MODE_ION || !h->borrowers.empty());
+        if (mode != CG_MODE_ION && !need_mu) {
+            h->err = "dipole / multipole evaluation of a system without dipole moments";
+            return CG_ERR_STATE;
+        }
+        const int rcs = sort_system(h, need_mu, &launches);
+        if (rcs != CG_OK) return rcs;
+    } else {
+        if (!s->sorted.valid || s->sorted.rc != D.cutoff) {
+            h->err = "cg_share_system: the source handle has no sorted system for this cut-off (evaluate it first, after its cg_set_system)";
+            return CG_ERR_STATE;
+        }
+        if (mode != CG_MODE_ION && !s->sorted.has_mu) {
+            h->err = "cg_share_system: the source handle's system has no dipole moments";
+            return CG_ERR_STATE;
+        }
+        CG_CUDA(h, cudaStreamWaitEvent(st, s->sorted_ev, 0));
+    }
+    const Sorted &S = s->sorted;
+    const SortParams &sp = S.sp;
+    const int ncell = S.ncell, cap_sorted = S.cap_sorted, ng_bound = S.ng_bound, ng_guess = S.ng_guess;
+    const bool need_mu = mode != CG_MODE_ION, fast = S.fast;
+    int *counts = s->d_counts.p;
     CG_CUDA(h, cudaEventRecord(h->ev[1], st));
 
     // ---- 6. pair kernel ----
@@ -948,12 +1058,12 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
 
     KParams kp;
     std::memset(&kp, 0, sizeof(kp));
-    kp.pos = h->pos.p;
-    kp.mu = need_mu ? h->mu.p : nullptr;
-    kp.pos32 = h->pos32.p;
-    kp.orig = h->orig.p;
-    kp.cell_start = h->cell_start.p;
-    kp.groups = h->groups.p;
+    kp.pos = s->pos.p;
+    kp.mu = need_mu ? s->mu.p : nullptr;
+    kp.pos32 = s->pos32.p;
+    kp.orig = s->orig.p;
+    kp.cell_start = s->cell_start.p;
+    kp.groups = s->groups.p;
     kp.group_begin = 0;
     kp.group_end = ng_bound;
     kp.counts = counts;
@@ -1005,7 +1115,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
            *o_pot = (what & CG_POTENTIAL) ? d_pot : nullptr;
     if (split > 1) {
         // per-slice partial buffers; with a shard, particles of other ranks are never written: clear them first
-        const bool clear = h->shard_n > 1;
+        const bool clear = s->shard_n > 1;
         if (o_force) {
             CG_CUDA(h, h->part_force.ensure((size_t)split * n * 3));
             if (clear) CG_CUDA(h, cudaMemsetAsync(h->part_force.p, 0, (size_t)split * n * 3 * sizeof(double), st));
@@ -1044,6 +1154,12 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         launches++;
     }
     CG_CUDA(h, cudaEventRecord(h->ev[2], st));
+    if (s != h) { // the lender must not re-sort under this kernel
+        CG_CUDA(h, cudaEventRecord(h->pair_done_ev, st));
+        if (std::find(s->readers.begin(), s->readers.end(), h) == s->readers.end()) s->readers.push_back(h);
+        h->counters[0] = s->counters[0];
+        h->counters[2] = s->counters[2];
+    }
 
     // ---- 7-8. epilogue ----
     if (split > 1 && items > 0) {
@@ -1081,7 +1197,8 @@ int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *fiel
 int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field, double *potential) {
     if (!h) return CG_ERR_INVALID;
     cudaSetDevice(h->device);
-    const size_t n = (size_t)h->n;
+    const cg_handle *sys = h->share_from ? h->share_from : h;
+    const size_t n = (size_t)sys->n;
     double *df = nullptr, *de = nullptr, *dp = nullptr;
     if ((what & CG_FORCE) && force) {
         CG_CUDA(h, h->out_force.ensure(3 * n + 1));
@@ -1096,7 +1213,7 @@ int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field
         dp = h->out_pot.p;
     }
     CG_CUDA(h, h->scalars.ensure(2));
-    if (h->shard_n > 1) { // particles outside the shard are not written by the kernels
+    if (sys->shard_n > 1) { // particles outside the shard are not written by the kernels
         if (df) CG_CUDA(h, cudaMemsetAsync(df, 0, 3 * n * sizeof(double), h->stream));
         if (de) CG_CUDA(h, cudaMemsetAsync(de, 0, 3 * n * sizeof(double), h->stream));
         if (dp) CG_CUDA(h, cudaMemsetAsync(dp, 0, n * sizeof(double), h->stream));
@@ -1122,9 +1239,18 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
     cudaSetDevice(h->device);
     CG_CUDA(h, cudaStreamSynchronize(h->stream));
     h->pending.active = false;
-    if (h->counts_pending && h->h_counts_async[2] != 0) { // the sync-free sizing was too small: redo with exact sizes
-        h->counts_pending = false;
-        h->fast.valid = false;
+    if (h->h_scalars[1] < 0.0) { // the sync-free sizing was too small (reduce_items_kernel says so): redo with exact sizes
+        cg_handle *s = h->share_from ? h->share_from : h;
+        s->counts_pending = false;
+        s->fast.valid = false;
+        if (s != h) { // borrowed arrays: sort the lender's system again, exactly
+            int l = 0;
+            const int rcs = sort_system(s, s->sorted.has_mu, &l);
+            if (rcs != CG_OK) {
+                h->err = s->err;
+                return rcs;
+            }
+        }
         const int rc = cg_eval_begin(h, h->pending.mode, h->pending.what, h->pending.force, h->pending.field, h->pending.potential);
         if (rc != CG_OK) return rc;
         return cg_eval_end(h, energy, pairs);

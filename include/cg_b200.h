@@ -143,6 +143,11 @@ const char *cg_version(void);
 /* run on a caller-owned CUDA stream (cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream); NULL -> own stream */
 int cg_set_stream(cg_handle *h, void *cuda_stream);
 int cg_set_precision(cg_handle *h, int precision);
+/* Evaluate this handle's scheme on the system of `source` (same device, same cut-off): `source` uploads, bins and
+ * sorts the particles once per configuration (its cg_set_system* + cg_eval*), every borrower reuses the sorted arrays
+ * -- the way to compute several schemes (e.g. Wolf and Fennell) on one configuration.  Evaluate `source` first after
+ * each cg_set_system*; the streams are ordered by events, the host calls must come from one thread.  NULL detaches. */
+int cg_share_system(cg_handle *h, cg_handle *source);
 /* evaluate only the i-particles of shard `rank` out of `nranks` (contiguous blocks of the spatially sorted order);
  * every rank still needs all N particles as j.  Default 0 of 1. */
 int cg_set_shard(cg_handle *h, int rank, int nranks);

@@ -34,6 +34,8 @@ class BatchedEvaluator {
 
     cg_handle *handle() const { return h_; }
     void set_stream(void *cuda_stream) { check(cg_set_stream(h_, cuda_stream), "cg_set_stream"); }
+    // evaluate on `source`'s system (same cut-off): one upload + sort per configuration for several schemes
+    void share_system(BatchedEvaluator &source) { check(cg_share_system(h_, source.h_), "cg_share_system"); }
     void set_shard(int rank, int nranks) { check(cg_set_shard(h_, rank, nranks), "cg_set_shard"); }
     /** host SoA buffers; q / mu* may be null (all zero); box is read when pbc */
     void set_system(int64_t n, const double *x, const double *y, const double *z, const double *q, const double *mux, const double *muy,

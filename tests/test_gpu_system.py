@@ -140,6 +140,42 @@ def test_two_schemes_in_flight_with_caller_owned_buffers(oracle_kind):
         evs["wolf"].eval(cg.MODE_ION, cg.FORCE, out=dict(force=np.empty((3, 3))))
 
 
+def test_schemes_sharing_one_sorted_system(oracle_kind):
+    """cg_share_system: the lender uploads and sorts once, borrowers of the same cut-off evaluate on its arrays."""
+    x, y, z, q, mu = O.generate(14, 3.0, 5, oracle_kind)
+    box = [42.0] * 3
+    lender = cg.BatchedEvaluator(zoo()["wolf"][0]())
+    b_ion = cg.BatchedEvaluator(zoo()["fennell"][0]())
+    b_dip = cg.BatchedEvaluator(zoo()["zerodipole"][0]())
+    own = cg.BatchedEvaluator(zoo()["fennell"][0]())
+    for b in (b_ion, b_dip):
+        b.share_system(lender)
+    with pytest.raises(cg.CgError):
+        b_ion.eval(cg.MODE_ION, cg.FORCE)  # the lender has not sorted anything yet
+    with pytest.raises(cg.CgError):
+        b_ion.set_system(x, y, z, q, None, box, True)  # a borrower has no system of its own
+    with pytest.raises(cg.CgError):
+        cg.BatchedEvaluator(cg.Wolf(11.0, 0.25)).share_system(lender)  # other cut-off, other cell grid
+    w = cg.ENERGY | cg.FORCE
+    for rep, shift in enumerate((0.0, 1.7, 3.1)):  # new positions each round; rounds 2+ take the sync-free path
+        xs = np.mod(x + shift, 42.0)
+        lender.set_system(xs, y, z, q, mu, box, True)
+        lender.eval_begin(cg.MODE_ION, w)
+        b_ion.eval_begin(cg.MODE_ION, w)
+        b_dip.eval_begin(cg.MODE_DIPOLE, w | cg.FIELD)
+        g0, g1, g2 = lender.eval_end(), b_ion.eval_end(), b_dip.eval_end()
+        ok(compare(g0, O.Scheme(zoo()["wolf"][1], oracle_kind).batched(xs, y, z, q, mu, box, True, cg.MODE_ION, w), w))
+        ok(compare(g1, O.Scheme(zoo()["fennell"][1], oracle_kind).batched(xs, y, z, q, mu, box, True, cg.MODE_ION, w), w))
+        ok(compare(g2, O.Scheme(zoo()["zerodipole"][1], oracle_kind).batched(xs, y, z, q, mu, box, True, cg.MODE_DIPOLE, w | cg.FIELD),
+                   w | cg.FIELD))
+        own.set_system(xs, y, z, q, mu, box, True)
+        assert np.array_equal(own.eval(cg.MODE_ION, w)["force"], g1["force"])  # bitwise the same as with an own sort
+    b_ion.share_system(None)
+    b_ion.set_system(x, y, z, q, None, box, True)
+    assert b_ion.eval(cg.MODE_ION, w)["pairs"] > 0
+    b_dip.close(); lender.close(); b_ion.close(); own.close()
+
+
 def test_sync_free_path_and_its_overflow_fallback(oracle_kind):
     """The second evaluation of a same-shaped periodic system sizes its arrays and launches from the previous one (no host
     round trip).  When the new positions need more room than that (all particles near the box corners: each gets seven
@@ -155,15 +191,23 @@ def test_sync_free_path_and_its_overflow_fallback(oracle_kind):
     uniform = [rng.uniform(0.0, L, n) for _ in range(3)]
     corners = [np.where(rng.random(n) < 0.5, rng.uniform(0.0, 5.0, n), rng.uniform(L - 5.0, L, n)) for _ in range(3)]
     ev = cg.BatchedEvaluator(mk())
+    bor = cg.BatchedEvaluator(zoo()["fennell"][0]())
+    bor.share_system(ev)
+    osch_b = O.Scheme(zoo()["fennell"][1], oracle_kind)
     seen = []
     for pos in (centre, centre, uniform, corners, corners, centre):
         ev.set_system(pos[0], pos[1], pos[2], q, None, box, True)
-        g = ev.eval(cg.MODE_ION, w)
+        ev.eval_begin(cg.MODE_ION, w)
+        bor.eval_begin(cg.MODE_ION, w)
+        gb = bor.eval_end()  # the borrower finds the overflow first and has the lender sort again
+        g = ev.eval_end()
         seen.append(ev.counters()["sync_free"])
         ok(compare(g, osch.batched(pos[0], pos[1], pos[2], q, None, box, True, cg.MODE_ION, w), w))
+        ok(compare(gb, osch_b.batched(pos[0], pos[1], pos[2], q, None, box, True, cg.MODE_ION, w), w))
     # 1st: exact sizing; 2nd: sync-free; 3rd/4th: more images than the arrays hold -> detected, redone exactly
     assert seen[0] == 0 and seen[1] == 1, seen
     assert 0 in seen[2:4], seen
+    bor.close()
     ev.close()
 
 
