@@ -213,7 +213,8 @@ __global__ void row_group_count_kernel(const __grid_constant__ SortParams sp, co
     row_ngroups[k] = (b - a + 31) / 32;
 }
 
-__global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, const int *cell_start, const int *row_gstart, int2 *groups) {
+__global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, const int *cell_start, const int *row_gstart, int2 *groups,
+                                      int ng_cap) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= sp.row1 - sp.row0) return;
     const int r = sp.row0 + k;
@@ -221,7 +222,7 @@ __global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, con
     const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
     const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
     int g = row_gstart[k];
-    for (int s = a; s < b; s += 32) groups[g++] = make_int2(s, min(32, b - s));
+    for (int s = a; s < b && g < ng_cap; s += 32) groups[g++] = make_int2(s, min(32, b - s)); // beyond ng_cap: overflow is flagged
 }
 
 // ---- exclusive scan (ints): 4096 elements per block, recursive over block sums ----
@@ -286,11 +287,13 @@ static cudaError_t exclusive_scan(const int *in, int *out, int n, int *tmp, cuda
     return cudaGetLastError();
 }
 
-__global__ void scan_total_kernel(const int *in, int *out, int n, int *total) { // out[n] = out[n-1] + in[n-1]
+// out[n] = out[n-1] + in[n-1]; the total also goes to *total, and *overflow is raised when it exceeds `limit`
+__global__ void scan_total_kernel(const int *in, int *out, int n, int *total, int limit, int *overflow) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         const int t = n > 0 ? out[n - 1] + in[n - 1] : 0;
         out[n] = t;
         if (total) *total = t;
+        if (overflow && t > limit) *overflow = 1;
     }
 }
 
@@ -909,19 +912,23 @@ static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
     bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, nullptr, nullptr, 0, counts);
     (*launches_out)++;
     CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, launches_out));
-    scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell, counts + 0);
+    scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell, counts + 0, 0, nullptr);
     (*launches_out)++;
     row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
     (*launches_out)++;
     CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, launches_out));
-    scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim, counts + 1);
-    (*launches_out)++;
     int cap_sorted, ng_bound, ng_guess;
     if (fast) { // array sizes and the launch shape come from the previous evaluation; no host round trip
         cap_sorted = h->fast.cap_sorted;
-        ng_bound = n / 32 + nrows_prim + 2; // every primary row adds at most one partial group
         ng_guess = h->fast.last_groups;
+        // launch bound: the last count with some room, at most the strict bound (a partial group per primary row)
+        ng_bound = std::min(n / 32 + nrows_prim + 2, ng_guess + ng_guess / 8 + 64);
     } else {
+        ng_bound = 0x7fffffff;
+    }
+    scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim, counts + 1, ng_bound, counts + 2);
+    (*launches_out)++;
+    if (!fast) {
         CG_CUDA(h, cudaMemcpyAsync(h->h_counts, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CG_CUDA(h, cudaStreamSynchronize(st));
         const int n_sorted = h->h_counts[0];
@@ -960,7 +967,7 @@ static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
     }
     gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p,
                                                          h->orig.p, far_coord);
-    row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p);
+    row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p, ng_bound);
     *launches_out += 4;
     CG_CUDA(h, cudaGetLastError());
     // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
@@ -1039,10 +1046,11 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         const char *e = std::getenv("CG_SPLIT");
         return e ? std::atoi(e) : 0;
     }();
-    // j-split: only when the groups cannot fill the machine once (2 CTAs of 8 warps per SM); then aim at two waves
+    // j-split: only when the groups cannot fill the machine once (2 CTAs of 8 warps per SM); then as many slices as
+    // fit into that one wave (measured: 144 groups -> 16, 1024 -> 2, 2048 and more -> 1 are the fastest choices)
     int split = 1;
     const int wave = device_sms * 2 * kWarpsPerCta;
-    if (ng > 0 && ng < wave) split = std::min(64, (2 * wave + ng - 1) / ng);
+    if (ng > 0 && ng < wave) split = std::max(1, std::min(64, wave / ng));
     if (split_env > 0) split = std::min(64, split_env);
     const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split
 

@@ -71,6 +71,10 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     // per-lane lists of (hit mask, first candidate index) of the batches in which the lane had at least one hit
     uint2 *hits = reinterpret_cast<uint2 *>(smem_raw + table_bytes + kWarpsPerCta * 32 * sizeof(float4)) + warp * (kSlots * 32) + lane;
     constexpr int kIlp = pairs_in_flight<MODE>();
+    // `items` is only the launch bound (the sync-free path does not know the group count on the host); CTAs beyond the
+    // real work leave before they touch anything.  After an overflow the cell table points past the sorted arrays.
+    const int real_items = p.counts[2] != 0 ? 0 : min(items, p.counts[1] * p.split);
+    if ((int)blockIdx.x * kWarpsPerCta >= real_items) return;
     const double *tab = nullptr;
     if constexpr (F::kTable != cgd::kTableNone) { // Splined: the four Andrea tables; erfc family: the erfc/exp table
         for (int k = threadIdx.x; k < table_doubles; k += kThreads) s_table[k] = dev_table[k];
@@ -79,8 +83,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     }
     const int item = blockIdx.x * kWarpsPerCta + warp;
     const int split = p.split;
-    // `items` is only the launch bound; after an overflow the cell table points past the sorted arrays: touch nothing
-    if (item >= items || item >= p.counts[1] * split || p.counts[2] != 0) return;
+    if (item >= real_items) return;
     const int dummy = min(p.counts[0], p.cap_sorted - 1);
     const unsigned full = 0xffffffffu;
     const int g = p.group_begin + item / split, slice = item - (item / split) * split;
@@ -127,6 +130,10 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     unsigned have = 0;      // lanes whose run of the current chunk is still unvisited
     int jb = 0, je = 0;     // this lane's run in the current chunk
     int cur_j = 0, cur_end = 0;
+    // j-split: batch k of the run of the item's r-th row belongs to slice (r + k) mod split.  Every slice gets candidates from
+    // all rows and, over `split` consecutive runs, from every position along x, i.e. hits for every lane; cutting the
+    // runs themselves (or a plain round robin, which resonates with the batches per run) would hand the left part of
+    // each run to one slice and starve the lanes on the right.
     auto next_batch = [&](int &j0, int &n) -> bool {
         while (cur_j >= cur_end) { // next run
             if (have == 0) {       // next 32 rows
@@ -148,11 +155,10 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                         const int rowbase = (rz * p.ny + ry) * p.nx;
                         jb = p.cell_start[rowbase + cxa];
                         je = p.cell_start[rowbase + cxb + 1];
-                        if (split > 1) { // j-split: this slice's share of the run
-                            const long long len = je - jb;
-                            const int a = jb + (int)(len * slice / split), b = jb + (int)(len * (slice + 1) / split);
-                            jb = a;
-                            je = b;
+                        if (split > 1) { // this slice's first batch of the run (see above); rr = the row's index in the item
+                            int first = (slice - rr) % split;
+                            first += first < 0 ? split : 0;
+                            jb += 32 * first;
                         }
                     }
                 }
@@ -166,7 +172,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         }
         j0 = cur_j;
         n = min(32, cur_end - cur_j);
-        cur_j += 32;
+        cur_j += 32 * p.split;
         return true;
     };
     const float4 sentinel = make_float4(0.0f, 0.0f, 0.0f, INFINITY); // |c|^2 = inf never passes

@@ -22,12 +22,21 @@ class ShardedStep:
         self.counts = [owned_range(n_total, r, self.world)[1] - owned_range(n_total, r, self.world)[0] for r in range(self.world)]
         self.even = len(set(self.counts)) == 1
         self.full = [torch.empty(n_total, dtype=dtype, device=device) for _ in range(n_arrays)]
+        self._coalescing_manager = getattr(dist, "_coalescing_manager", None)
+        self.coalesce = (self._coalescing_manager is not None and self.world > 1 and torch.device(device).type == "cuda"
+                         and dist.get_backend(group) == "nccl")
 
     def gather(self, owned):
         """owned: this rank's slices, one tensor per SoA array -> the full arrays on every rank."""
         if self.world == 1:
             for f, o in zip(self.full, owned):
                 f.copy_(o)
+            return self.full
+        if self.even and self.coalesce:
+            # one NCCL group (a single fused launch) for all SoA arrays instead of one collective per array
+            with self._coalescing_manager(group=self.group, device=self.full[0].device, async_ops=False):
+                for f, o in zip(self.full, owned):
+                    dist.all_gather_into_tensor(f, o, group=self.group)
             return self.full
         for f, o in zip(self.full, owned):
             if self.even:

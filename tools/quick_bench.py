@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Kernel-level timing of the BASELINE configs on one GPU (tuning aid; the judged numbers come from bench.py).
-usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,3,4,5s}  (5s = config 5 at n=128)"""
+usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,3,4s,4,5s,5}  (4s / 5s = configs 4 / 5 at n = 100 / 128)"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -13,6 +13,8 @@ CONFIGS = {
     "2f": dict(pot=lambda: cg.Fennell(12, 0.25), n=100, a=3.0, seed=1002, pbc=True, mode=cg.MODE_ION, what=cg.FORCE, falg=39),
     "3": dict(pot=lambda: cg.ReactionField(12, 80, 1, False), n=64, a=3.0, seed=1003, pbc=True, mode=cg.MODE_DIPOLE, what=cg.ENERGY | cg.FIELD | cg.FORCE, falg=101),
     "4s": dict(pot=lambda: cg.Ewald(10, 0.3, INF, 30.0), n=100, a=3.0, seed=1004, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=133),
+    "4": dict(pot=lambda: cg.Ewald(10, 0.3, INF, 30.0), n=160, a=3.0, seed=1004, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=133),
+    "5": dict(pot=lambda: cg.Splined().spline(cg.Poisson, 12, 4, 3), n=256, a=3.0, seed=1005, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=153),
     "5s": dict(pot=lambda: cg.Splined().spline(cg.Poisson, 12, 4, 3), n=128, a=3.0, seed=1005, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=153),
 }
 
