@@ -85,6 +85,10 @@ def _load():
         "cg_eval_begin": [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
         "cg_eval_end": [H, _dp, C.POINTER(C.c_int64)],
         "cg_eval_device": [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "cg_self_terms": [H, _dp, C.c_void_p],
+        "cg_self_terms_device": [H, C.c_void_p, C.c_void_p],
+        "cg_dipole_torque": [H, C.c_void_p, C.c_void_p],
+        "cg_dipole_torque_device": [H, C.c_void_p, C.c_void_p],
         "cg_srf_device": [H, C.c_int64, C.c_void_p, C.c_void_p],
         "cg_last_timings": [H, _dp],
         "cg_last_counters": [H, C.POINTER(C.c_int64)],
@@ -112,7 +116,7 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_scheme_zahn", "cg_scheme_wolf", "cg_scheme_ewald", "cg_scheme_ewaldt", "cg_spline_storage_doubles",
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
-            "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_srf_device", "cg_last_timings",
+            "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",
             "cg_last_counters", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
 
 

@@ -125,6 +125,27 @@ class BatchedEvaluator:
         check(lib.cg_eval_device(self.h, mode, what, _devptr(force), _devptr(field), _devptr(potential), _devptr(scalars)),
               "cg_eval_device", self.h)
 
+    # ---- O(N) terms (reference core.hpp:794, 809-842) ----
+    def self_terms(self, self_field=False):
+        """-> dict(self_energy, neutralization_energy, charge_sum[, self_field (n,3)]) of the current system."""
+        n = self._source.n if self._source is not None else self.n
+        out = (C.c_double * 3)()
+        sf = np.empty((n, 3)) if self_field else None
+        check(lib.cg_self_terms(self.h, out, _hp(sf)), "cg_self_terms", self.h)
+        return dict(self_energy=out[0], neutralization_energy=out[1], charge_sum=out[2], self_field=sf)
+
+    def self_terms_device(self, out3, self_field=None):
+        check(lib.cg_self_terms_device(self.h, _devptr(out3), _devptr(self_field)), "cg_self_terms_device", self.h)
+
+    def dipole_torque(self, field):
+        field = np.ascontiguousarray(field, dtype=np.float64)
+        tq = np.empty_like(field)
+        check(lib.cg_dipole_torque(self.h, _hp(field), _hp(tq)), "cg_dipole_torque", self.h)
+        return tq
+
+    def dipole_torque_device(self, field, torque):
+        check(lib.cg_dipole_torque_device(self.h, _devptr(field), _devptr(torque)), "cg_dipole_torque_device", self.h)
+
     def srf_device(self, q, out):
         check(lib.cg_srf_device(self.h, q.numel(), _devptr(q), _devptr(out)), "cg_srf_device", self.h)
 

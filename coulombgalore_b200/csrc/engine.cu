@@ -424,6 +424,79 @@ __global__ void dfma_probe_kernel(int iters, double a, double b, double *sink) {
 // =================================================================================================================
 using namespace cgb;
 
+// ---- O(N) terms (reference core.hpp:124-145, 794, 809-842): self-energy, self-field, neutralisation, torque ----
+struct SelfParams {
+    int n;
+    const double *q, *mx, *my, *mz;
+    double f0, f1, s1;     // self-energy prefactors (ion, dipole), self-field prefactor (dipole)
+    double inv_rc, inv_rc3;
+};
+constexpr int kSelfThreads = 256;
+
+__global__ void self_partial_kernel(const __grid_constant__ SelfParams sp, double *partial, double *self_field) {
+    __shared__ double sh[2][kSelfThreads / 32];
+    double e = 0.0, zs = 0.0;
+    for (int i = blockIdx.x * kSelfThreads + threadIdx.x; i < sp.n; i += gridDim.x * kSelfThreads) {
+        const double z = sp.q ? sp.q[i] : 0.0;
+        double mx = 0.0, my = 0.0, mz = 0.0;
+        if (sp.mx) {
+            mx = sp.mx[i];
+            my = sp.my[i];
+            mz = sp.mz[i];
+        }
+        const double m2 = mx * mx + my * my + mz * mz;
+        e += (0.0 + sp.f0 * (z * z) * sp.inv_rc) + sp.f1 * m2 * sp.inv_rc3; // the reference's summation order
+        zs += z;
+        if (self_field) {
+            self_field[3 * (size_t)i + 0] = sp.s1 * mx * sp.inv_rc3;
+            self_field[3 * (size_t)i + 1] = sp.s1 * my * sp.inv_rc3;
+            self_field[3 * (size_t)i + 2] = sp.s1 * mz * sp.inv_rc3;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        e += __shfl_down_sync(0xffffffffu, e, off);
+        zs += __shfl_down_sync(0xffffffffu, zs, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sh[0][threadIdx.x >> 5] = e;
+        sh[1][threadIdx.x >> 5] = zs;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < kSelfThreads / 32; w++) {
+            a += sh[0][w];
+            b += sh[1][w];
+        }
+        partial[2 * blockIdx.x + 0] = a;
+        partial[2 * blockIdx.x + 1] = b;
+    }
+}
+
+// out[0] = self-energy, out[1] = chi / (2 V) (sum z)^2 (0 for an open system), out[2] = sum z; fixed summation order
+__global__ void self_final_kernel(int nb, const double *partial, double chi, double volume, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k < nb; k++) {
+        a += partial[2 * k + 0];
+        b += partial[2 * k + 1];
+    }
+    out[0] = a;
+    out[1] = volume > 0.0 ? chi / 2.0 / volume * b * b : 0.0;
+    out[2] = b;
+}
+
+__global__ void torque_kernel(int n, const double *mx, const double *my, const double *mz, const double *field, double *torque) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ax = mx[i], ay = my[i], az = mz[i];
+    const double bx = field[3 * (size_t)i], by = field[3 * (size_t)i + 1], bz = field[3 * (size_t)i + 2];
+    torque[3 * (size_t)i + 0] = ay * bz - az * by; // mu x E
+    torque[3 * (size_t)i + 1] = az * bx - ax * bz;
+    torque[3 * (size_t)i + 2] = ax * by - ay * bx;
+}
+
 template <class T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
@@ -478,7 +551,7 @@ struct cg_handle {
     DevBuf<double4> pos, mu;
     DevBuf<float4> pos32;
     DevBuf<int2> groups;
-    DevBuf<double> minmax_partial;
+    DevBuf<double> minmax_partial, self_partial;
     // outputs
     DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
     DevBuf<unsigned long long> item_pairs;
@@ -498,7 +571,7 @@ struct cg_handle {
     } fast;
     bool last_overflow = false;
     Sorted sorted;
-    cudaEvent_t sorted_ev = nullptr, pair_done_ev = nullptr;
+    cudaEvent_t sorted_ev = nullptr, pair_done_ev = nullptr, inputs_ev = nullptr; // inputs_ev: the host path's upload
     cg_handle *share_from = nullptr;     // cg_share_system: evaluate on that handle's sorted system
     std::vector<cg_handle *> borrowers;  // handles whose share_from is this one
     std::vector<cg_handle *> readers;    // borrowers with a pair kernel in flight on the current sorted arrays
@@ -619,9 +692,10 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
     ok = ok && cudaEventCreateWithFlags(&h->counts_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->sorted_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->pair_done_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&h->inputs_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && h->d_counts.ensure(8) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_minmax, 6 * 64 * sizeof(double)) == cudaSuccess;
-    ok = ok && cudaMallocHost((void **)&h->h_scalars, 2 * sizeof(double)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void **)&h->h_scalars, 8 * sizeof(double)) == cudaSuccess;
     if (!ok) {
         g_create_error = std::string("CUDA resource creation failed: ") + cudaGetErrorString(cudaGetLastError());
         delete h;
@@ -657,6 +731,7 @@ int cg_destroy(cg_handle *h) {
     h->pos32.release();
     h->groups.release();
     h->minmax_partial.release();
+    h->self_partial.release();
     h->out_force.release();
     h->out_field.release();
     h->out_pot.release();
@@ -671,6 +746,7 @@ int cg_destroy(cg_handle *h) {
     if (h->counts_ev) cudaEventDestroy(h->counts_ev);
     if (h->sorted_ev) cudaEventDestroy(h->sorted_ev);
     if (h->pair_done_ev) cudaEventDestroy(h->pair_done_ev);
+    if (h->inputs_ev) cudaEventDestroy(h->inputs_ev);
     h->d_counts.release();
     if (h->h_minmax) cudaFreeHost(h->h_minmax);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -768,6 +844,7 @@ int cg_set_system(cg_handle *h, int64_t n, const double *x, const double *y, con
         }
     }
     h->inputs_on_device = false;
+    CG_CUDA(h, cudaEventRecord(h->inputs_ev, h->stream));
     return CG_OK;
 }
 
@@ -780,6 +857,8 @@ int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double 
     const double *src[7] = {x, y, z, q, mux, muy, muz};
     for (int k = 0; k < 7; k++) h->in[k] = src[k];
     h->inputs_on_device = true;
+    cudaSetDevice(h->device);
+    CG_CUDA(h, cudaEventRecord(h->inputs_ev, h->stream));
     return CG_OK;
 }
 
@@ -998,7 +1077,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     int launches = 0, pair_launches = 0;
     CG_CUDA(h, cudaEventRecord(h->ev[0], st));
     if (!d_scalars) {
-        CG_CUDA(h, h->scalars.ensure(2));
+        CG_CUDA(h, h->scalars.ensure(8));
         d_scalars = h->scalars.p;
     }
     const int n = (int)sys->n;
@@ -1220,7 +1299,7 @@ int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field
         CG_CUDA(h, h->out_pot.ensure(n + 1));
         dp = h->out_pot.p;
     }
-    CG_CUDA(h, h->scalars.ensure(2));
+    CG_CUDA(h, h->scalars.ensure(8));
     if (sys->shard_n > 1) { // particles outside the shard are not written by the kernels
         if (df) CG_CUDA(h, cudaMemsetAsync(df, 0, 3 * n * sizeof(double), h->stream));
         if (de) CG_CUDA(h, cudaMemsetAsync(de, 0, 3 * n * sizeof(double), h->stream));
@@ -1271,6 +1350,89 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
 int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
     const int rc = cg_eval_begin(h, mode, what, force, field, potential);
     return rc != CG_OK ? rc : cg_eval_end(h, energy, pairs);
+}
+
+int cg_self_terms_device(cg_handle *h, double *out3, double *self_field) {
+    if (!h || !out3) return CG_ERR_INVALID;
+    cg_handle *sys = h->share_from ? h->share_from : h;
+    if (!sys->have_system) {
+        h->err = "cg_self_terms before cg_set_system";
+        return CG_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->stream;
+    const cg_scheme_desc &D = h->desc;
+    SelfParams sp;
+    sp.n = (int)sys->n;
+    sp.q = sys->in[3];
+    sp.mx = sys->in[4];
+    sp.my = sys->in[5];
+    sp.mz = sys->in[6];
+    sp.f0 = D.self_energy_prefactor[0];
+    sp.f1 = D.self_energy_prefactor[1];
+    sp.s1 = D.self_field_prefactor[1];
+    sp.inv_rc = D.inverse_cutoff;
+    sp.inv_rc3 = cgd::powi(D.inverse_cutoff, 3);
+    const int nb = std::max(1, std::min(1024, (sp.n + kSelfThreads - 1) / kSelfThreads));
+    CG_CUDA(h, h->self_partial.ensure(2 * (size_t)nb));
+    if (sys != h) CG_CUDA(h, cudaStreamWaitEvent(st, sys->inputs_ev, 0)); // the lender's upload
+    self_partial_kernel<<<nb, kSelfThreads, 0, st>>>(sp, h->self_partial.p, self_field);
+    const double volume = sys->pbc ? sys->box[0] * sys->box[1] * sys->box[2] : 0.0;
+    self_final_kernel<<<1, 32, 0, st>>>(nb, h->self_partial.p, D.chi, volume, out3);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+int cg_self_terms(cg_handle *h, double out[3], double *self_field) {
+    if (!h || !out) return CG_ERR_INVALID;
+    const cg_handle *sys = h->share_from ? h->share_from : h;
+    const size_t n = (size_t)sys->n;
+    cudaSetDevice(h->device);
+    CG_CUDA(h, h->scalars.ensure(8));
+    double *dsf = nullptr;
+    if (self_field) {
+        CG_CUDA(h, h->out_field.ensure(3 * n + 1));
+        dsf = h->out_field.p;
+    }
+    const int rc = cg_self_terms_device(h, h->scalars.p + 4, dsf);
+    if (rc != CG_OK) return rc;
+    if (dsf && n > 0) CG_CUDA(h, cudaMemcpyAsync(self_field, dsf, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CG_CUDA(h, cudaMemcpyAsync(h->h_scalars + 4, h->scalars.p + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 3; k++) out[k] = h->h_scalars[4 + k];
+    return CG_OK;
+}
+
+int cg_dipole_torque_device(cg_handle *h, const double *field, double *torque) {
+    if (!h || !field || !torque) return CG_ERR_INVALID;
+    cg_handle *sys = h->share_from ? h->share_from : h;
+    if (!sys->have_system || !sys->in[4]) {
+        h->err = "cg_dipole_torque needs a system with dipole moments";
+        return CG_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    const int n = (int)sys->n;
+    if (n == 0) return CG_OK;
+    if (sys != h) CG_CUDA(h, cudaStreamWaitEvent(h->stream, sys->inputs_ev, 0));
+    torque_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(n, sys->in[4], sys->in[5], sys->in[6], field, torque);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+int cg_dipole_torque(cg_handle *h, const double *field, double *torque) {
+    if (!h || !field || !torque) return CG_ERR_INVALID;
+    const cg_handle *sys = h->share_from ? h->share_from : h;
+    const size_t n = (size_t)sys->n;
+    if (n == 0) return CG_OK;
+    cudaSetDevice(h->device);
+    CG_CUDA(h, h->out_field.ensure(3 * n + 1));
+    CG_CUDA(h, h->out_force.ensure(3 * n + 1));
+    CG_CUDA(h, cudaMemcpyAsync(h->out_field.p, field, 3 * n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    const int rc = cg_dipole_torque_device(h, h->out_field.p, h->out_force.p);
+    if (rc != CG_OK) return rc;
+    CG_CUDA(h, cudaMemcpyAsync(torque, h->out_force.p, 3 * n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CG_CUDA(h, cudaStreamSynchronize(h->stream));
+    return CG_OK;
 }
 
 int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out) {
@@ -1325,7 +1487,7 @@ int cg_fp64_peak_probe(cg_handle *h, double *tflops, double *ms_out) {
     cudaSetDevice(h->device);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
-    CG_CUDA(h, h->scalars.ensure(2));
+    CG_CUDA(h, h->scalars.ensure(8));
     const int iters = 1 << 15, blocks = sms * 8, threads = 256;
     cudaStream_t st = h->stream;
     dfma_probe_kernel<<<blocks, threads, 0, st>>>(1024, 0.999999, 1e-9, h->scalars.p); // warm-up

@@ -175,6 +175,15 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs);
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,
                    double *scalars);
 
+/* O(N) terms of the current system, per particle as the reference's scheme functions give them
+ * (core.hpp:124-145, 809-842): out[0] = sum_i self_energy({z_i^2, |mu_i|^2}), out[1] = neutralization_energy(charges,
+ * box volume) (0 for an open system), out[2] = sum_i z_i; self_field[3n] (may be NULL) = self_field({0, mu_i}).
+ * The _device forms take device pointers and are asynchronous on the handle's stream. */
+int cg_self_terms(cg_handle *h, double out[3], double *self_field);
+int cg_self_terms_device(cg_handle *h, double *out3, double *self_field);
+/* torque[3n] = mu_i x field_i (reference core.hpp:794); field as written by cg_eval* with CG_FIELD */
+int cg_dipole_torque(cg_handle *h, const double *field, double *torque);
+int cg_dipole_torque_device(cg_handle *h, const double *field, double *torque);
 /* per-functor probe: S..S''' evaluated by the device functor, q and out are DEVICE pointers, out[k*n+i] */
 int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out);
 

@@ -57,6 +57,9 @@ class BatchedEvaluator {
         check(cg_eval_begin(h_, mode, what, force, field, potential), "cg_eval_begin");
     }
     void eval_end(double *energy, int64_t *pairs) { check(cg_eval_end(h_, energy, pairs), "cg_eval_end"); }
+    // O(N) terms: out[0] = sum self_energy, out[1] = neutralization_energy, out[2] = sum z; self_field[3n] may be null
+    void self_terms(double out[3], double *self_field) { check(cg_self_terms(h_, out, self_field), "cg_self_terms"); }
+    void dipole_torque(const double *field, double *torque) { check(cg_dipole_torque(h_, field, torque), "cg_dipole_torque"); }
     void eval_device(int mode, int what, double *force, double *field, double *potential, double *scalars) {
         check(cg_eval_device(h_, mode, what, force, field, potential, scalars), "cg_eval_device");
     }

@@ -99,6 +99,15 @@ int cgo_batched(void *handle, int64_t N, const double *x, const double *y, const
                 double *force, double *field, double *potential, double *energy_i, double *force_scale,
                 double *field_scale, double *potential_scale, double *totals);
 
+/*
+ * O(N) terms of a configuration, per particle through the scheme's own functions (reference core.hpp:794, 809-842):
+ * scalars[0] = sum_i self_energy({z_i^2, |mu_i|^2}), scalars[1] = sum of the absolute terms (tolerance scale),
+ * scalars[2] = neutralization_energy(charges, volume) (0 when volume <= 0), scalars[3] = sum_i z_i;
+ * self_field[3N] = self_field({0, mu_i}); torque[3N] = dipole_torque(mu_i, field_i).  Output pointers may be NULL.
+ */
+int cgo_self_terms(void *handle, int64_t N, const double *q, const double *mux, const double *muy, const double *muz,
+                   double volume, const double *field, double *scalars, double *self_field, double *torque);
+
 #ifdef __cplusplus
 }
 #endif

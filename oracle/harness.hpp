@@ -79,6 +79,8 @@ struct Iface {
                      const double *quadB, const double *r, double *out) = 0;
     virtual int spline_table(int k, int32_t *n_knots, double *r2, double *c) = 0;
     virtual int batched(const Batch &b) = 0;
+    virtual int self_terms(int64_t N, const double *q, const double *mx, const double *my, const double *mz, double volume,
+                           const double *field, double *scalars, double *self_field, double *torque) = 0;
 };
 
 // simple CPU cell list (cells >= cutoff, 27-cell stencil, periodic shifts or open walls)
@@ -206,6 +208,36 @@ template <class T, class VEC, class MAT> struct Impl : Iface {
         return 0;
     }
     int spline_table(int, int32_t *, double *, double *) override { return -1; }
+
+    // O(N) terms per particle through the scheme's own functions (reference core.hpp:794, 809-842); long double sums
+    int self_terms(int64_t N, const double *q, const double *mx, const double *my, const double *mz, double volume,
+                   const double *field, double *scalars, double *self_field, double *torque) override {
+        long double us = 0.0L, usa = 0.0L, zs = 0.0L;
+        std::vector<double> charges((size_t)N, 0.0);
+        const VEC zero(0, 0, 0);
+        for (int64_t i = 0; i < N; i++) {
+            const double z = q ? q[i] : 0.0;
+            const VEC mu = mx ? VEC(mx[i], my[i], mz[i]) : zero;
+            const double m2 = mu[0] * mu[0] + mu[1] * mu[1] + mu[2] * mu[2];
+            charges[(size_t)i] = z;
+            zs += z;
+            us += (long double)pot.self_energy({z * z, m2});
+            usa += (long double)(std::fabs(pot.self_energy({z * z, 0.0})) + std::fabs(pot.self_energy({0.0, m2})));
+            if (self_field) {
+                const VEC sf = pot.self_field({zero, mu});
+                for (int d = 0; d < 3; d++) self_field[3 * i + d] = sf[d];
+            }
+            if (torque && field) {
+                const VEC t = pot.dipole_torque(mu, VEC(field[3 * i], field[3 * i + 1], field[3 * i + 2]));
+                for (int d = 0; d < 3; d++) torque[3 * i + d] = t[d];
+            }
+        }
+        scalars[0] = (double)us;
+        scalars[1] = (double)usa;
+        scalars[2] = volume > 0.0 ? pot.neutralization_energy(charges, volume) : 0.0;
+        scalars[3] = (double)zs;
+        return 0;
+    }
 
     int batched(const Batch &b) override {
         CellList cl;
@@ -376,6 +408,10 @@ Iface *make(const cgo_params &p); // throws on invalid parameters
     void cgo_generate(int32_t n, double a, uint64_t seed, double *x, double *y, double *z, double *q,             \
                       double *mx, double *my, double *mz) {                                                        \
         cgo::generate(n, a, seed, x, y, z, q, mx, my, mz);                                                         \
+    }                                                                                                              \
+    int cgo_self_terms(void *h, int64_t N, const double *q, const double *mx, const double *my, const double *mz,  \
+                       double volume, const double *field, double *scalars, double *self_field, double *torque) {  \
+        return static_cast<cgo::Iface *>(h)->self_terms(N, q, mx, my, mz, volume, field, scalars, self_field, torque); \
     }                                                                                                              \
     int cgo_batched(void *h, int64_t N, const double *x, const double *y, const double *z, const double *q,       \
                     const double *mx, const double *my, const double *mz, const double *box, int32_t pbc,          \

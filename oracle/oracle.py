@@ -67,6 +67,8 @@ def load(kind="best"):
     lib.cgo_pair.argtypes = [C.c_void_p, C.c_double, C.c_double] + [_dp] * 6
     lib.cgo_spline_table.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int32), _dp, _dp]
     lib.cgo_generate.argtypes = [C.c_int32, C.c_double, C.c_uint64] + [_dp] * 7
+    lib.cgo_self_terms.argtypes = [C.c_void_p, C.c_int64] + [_dp] * 4 + [C.c_double] + [_dp] * 4
+    lib.cgo_self_terms.restype = C.c_int
     lib.cgo_generate.restype = None
     lib.cgo_batched.argtypes = ([C.c_void_p, C.c_int64] + [_dp] * 7 + [_dp, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int64, C.c_int64, C.c_int32, C.c_int32] + [_dp] * 8)
@@ -154,6 +156,24 @@ class Scheme:
         res.update(force=f, field=e, potential=p, energy_i=u, force_scale=fs, field_scale=es, potential_scale=ps,
                    energy=tot[0], energy_abs=tot[1], pairs=int(tot[2]))
         return res
+
+
+def _self_terms(self, q, mu, volume=0.0, field=None):
+    """O(N) terms: dict(self_energy, self_energy_abs, neutralization_energy, charge_sum, self_field (N,3), torque (N,3))."""
+    N = (q if q is not None else mu[0]).size
+    mx, my, mz = (None, None, None) if mu is None else mu
+    sc = np.zeros(4)
+    sf = np.zeros((N, 3))
+    tq = np.zeros((N, 3)) if field is not None else None
+    fld = None if field is None else np.ascontiguousarray(field, dtype=np.float64)
+    rc = self.lib.cgo_self_terms(self.h, N, _ptr(q), _ptr(mx), _ptr(my), _ptr(mz), C.c_double(volume), _ptr(fld), _ptr(sc), _ptr(sf),
+                                 _ptr(tq))
+    if rc != 0:
+        raise RuntimeError("cgo_self_terms failed rc=%d" % rc)
+    return dict(self_energy=sc[0], self_energy_abs=sc[1], neutralization_energy=sc[2], charge_sum=sc[3], self_field=sf, torque=tq)
+
+
+Scheme.self_terms = _self_terms
 
 
 def generate(n, a, seed, kind="best"):

@@ -12,6 +12,9 @@ reference's own double-precision outputs:
   tab/<scheme>/<k>/..   Andrea tables of the splined schemes (knots, coefficients)
   batch/<case>/..       batched loop (oracle/harness.hpp) on a 6^3 lattice: force, field, potential, energy, pairs
   lattice/..            generator output (splitmix64 rule of SURVEY.md 8d)
+  self/<scheme>/..      O(N) terms on the lattice with a non-neutral charge set (self_inputs): scalars = sum of
+                        self_energy, its absolute sum, neutralization_energy (V = 18^3), charge sum; self_field per
+                        particle; self/torque = dipole_torque(mu_i, E_i) for the seeded field of self_inputs
 """
 import os
 import sys
@@ -38,6 +41,14 @@ def pair_inputs(cutoff):
         out.append((float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2)), rng.normal(size=3), rng.normal(size=3), r,
                     rng.normal(size=(3, 3)), rng.normal(size=(3, 3))))
     return out
+
+
+def self_inputs(q):
+    """Charges with a net charge (so that the neutralisation term is exercised) and a seeded field for the torque."""
+    qn = q.copy()
+    qn[:10] = 1.7
+    field = np.random.default_rng(77).normal(size=(q.size, 3))
+    return qn, field
 
 
 def main():
@@ -75,6 +86,12 @@ def main():
         for f in ("force", "field", "potential", "force_scale", "field_scale", "potential_scale"):
             d[k + f] = r[f]
         d[k + "scalars"] = np.array([r["energy"], r["energy_abs"], float(r["pairs"])])
+    qn, fld = self_inputs(ch)
+    for name in ZOO:
+        r = O.Scheme(oracle_params(name), "ref").self_terms(qn, mu, 18.0 ** 3, field=fld)
+        d["self/%s/scalars" % name] = np.array([r["self_energy"], r["self_energy_abs"], r["neutralization_energy"], r["charge_sum"]])
+        d["self/%s/self_field" % name] = r["self_field"]
+        d["self/torque"] = r["torque"]
     np.savez_compressed(os.path.join(HERE, "reference_vectors.npz"), **d)
     print("wrote %d arrays, %.1f KB" % (len(d), os.path.getsize(os.path.join(HERE, "reference_vectors.npz")) / 1024))
 

@@ -140,6 +140,34 @@ def test_two_schemes_in_flight_with_caller_owned_buffers(oracle_kind):
         evs["wolf"].eval(cg.MODE_ION, cg.FORCE, out=dict(force=np.empty((3, 3))))
 
 
+@pytest.mark.parametrize("name", sorted(zoo()))
+def test_self_energy_self_field_neutralisation_and_torque(name, oracle_kind):
+    """the O(N) terms, against the oracle and against the committed reference run."""
+    from golden.make_golden import self_inputs
+    lat = GOLD["lattice/n6_a3_seed31337"]
+    x, y, z, q, mu = lat[0].copy(), lat[1].copy(), lat[2].copy(), lat[3].copy(), (lat[4].copy(), lat[5].copy(), lat[6].copy())
+    qn, fld = self_inputs(q)
+    mk, p = zoo()[name]
+    ev = cg.BatchedEvaluator(mk())
+    rc = ev.scheme.cutoff
+    box = [18.0] * 3 if rc <= 18.0 else None
+    ev.set_system(x, y, z, qn, mu, box, box is not None)
+    g = ev.self_terms(self_field=True)
+    tq = ev.dipole_torque(fld)
+    for ref in (O.Scheme(p, oracle_kind).self_terms(qn, mu, 18.0 ** 3 if box else 0.0, field=fld),
+                dict(zip(("self_energy", "self_energy_abs", "neutralization_energy", "charge_sum"), GOLD["self/%s/scalars" % name]),
+                     self_field=GOLD["self/%s/self_field" % name], torque=GOLD["self/torque"])):
+        assert abs(g["self_energy"] - ref["self_energy"]) <= TOL * max(ref["self_energy_abs"], 1e-300)
+        assert abs(g["charge_sum"] - ref["charge_sum"]) <= 1e-13 * np.abs(qn).sum()
+        if box:
+            assert abs(g["neutralization_energy"] - ref["neutralization_energy"]) <= TOL * abs(ref["neutralization_energy"])
+        else:
+            assert g["neutralization_energy"] == 0.0  # an open system has no unit cell to neutralise
+        assert np.max(np.abs(g["self_field"] - ref["self_field"])) <= TOL * max(np.max(np.abs(ref["self_field"])), 1e-300)
+        assert np.max(np.abs(tq - ref["torque"])) <= TOL * np.max(np.abs(ref["torque"]))
+    ev.close()
+
+
 def test_schemes_sharing_one_sorted_system(oracle_kind):
     """cg_share_system: the lender uploads and sorts once, borrowers of the same cut-off evaluate on its arrays."""
     x, y, z, q, mu = O.generate(14, 3.0, 5, oracle_kind)
