@@ -69,6 +69,7 @@ def _load():
         "cg_scheme_wolf": [C.c_double, C.c_double, D],
         "cg_scheme_ewald": [C.c_double, C.c_double, C.c_double, C.c_double, D],
         "cg_scheme_ewaldt": [C.c_double, C.c_double, C.c_double, C.c_double, D],
+        "cg_scheme_create": [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), _dp, D],
         "cg_scheme_splined": [D, C.c_double, _dp, D],
         "cg_scheme_splined_tables": [D, C.POINTER(C.c_int32), C.POINTER(_dp), C.POINTER(_dp), D],
         "cg_srf_host": [D, C.c_int64, _dp, _dp],
@@ -113,7 +114,7 @@ lib = _load()
 # every symbol include/cg_b200.h declares (checked by tests/test_capi_symbols.py against the header text)
 EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "cg_scheme_qpotential",
             "cg_scheme_qpotential5", "cg_scheme_fanourgakis", "cg_scheme_fennell", "cg_scheme_zerodipole",
-            "cg_scheme_zahn", "cg_scheme_wolf", "cg_scheme_ewald", "cg_scheme_ewaldt", "cg_spline_storage_doubles",
+            "cg_scheme_zahn", "cg_scheme_wolf", "cg_scheme_ewald", "cg_scheme_ewaldt", "cg_scheme_create", "cg_spline_storage_doubles",
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
             "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",

@@ -1,6 +1,7 @@
 // scheme_api.cpp -- the host-only part of the C ABI: descriptor constructors (cg_scheme_*) and cg_srf_host.
 // Thin wrappers over include/coulombgalore/detail/descriptor.hpp, the same code the header classes use.
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "cg_b200.h"
@@ -33,6 +34,57 @@ int cg_scheme_ewald(double cutoff, double alpha, double eps_sur, double debye_le
 }
 int cg_scheme_ewaldt(double cutoff, double alpha, double eps_sur, double debye_length, cg_scheme_desc *out) {
     return out ? cgd::make_ewaldt(cutoff, alpha, eps_sur, debye_length, *out) : CG_ERR_INVALID;
+}
+
+// The reference's run-time factory (createScheme, all.hpp:42-104) without the JSON dependency: `type` and the
+// (key, value) pairs are what the JSON object holds; keys and defaults are those of the reference's JSON constructors.
+int cg_scheme_create(const char *type, int nkeys, const char *const *keys, const double *values, cg_scheme_desc *out) {
+    if (!type || !out || nkeys < 0 || (nkeys > 0 && (!keys || !values))) return CG_ERR_INVALID;
+    bool missing = false;
+    auto find = [&](const char *k, double *v) {
+        for (int i = 0; i < nkeys; i++)
+            if (keys[i] && std::strcmp(keys[i], k) == 0) {
+                *v = values[i];
+                return true;
+            }
+        return false;
+    };
+    auto at = [&](const char *k) { // j.at(k): mandatory
+        double v = 0.0;
+        if (!find(k, &v)) missing = true;
+        return v;
+    };
+    auto value = [&](const char *k, double dflt) { // j.value(k, default)
+        double v = dflt;
+        find(k, &v);
+        return v;
+    };
+    const double inf = cgd::kInfinity;
+    const std::string t(type);
+    int rc = CG_ERR_INVALID;
+    if (t == "plain") rc = cgd::make_plain(value("debyelength", inf), *out);
+    else if (t == "wolf") { const double c = at("cutoff"), a = at("alpha"); if (!missing) rc = cgd::make_wolf(c, a, *out); }
+    else if (t == "zahn") { const double c = at("cutoff"), a = at("alpha"); if (!missing) rc = cgd::make_zahn(c, a, *out); }
+    else if (t == "fennell") { const double c = at("cutoff"), a = at("alpha"); if (!missing) rc = cgd::make_fennell(c, a, *out); }
+    else if (t == "zerodipole") { const double c = at("cutoff"), a = at("alpha"); if (!missing) rc = cgd::make_zerodipole(c, a, *out); }
+    else if (t == "fanourgakis") { const double c = at("cutoff"); if (!missing) rc = cgd::make_fanourgakis(c, *out); }
+    else if (t == "qpotential") { const double c = at("cutoff"), o = at("order"); if (!missing) rc = cgd::make_qpotential(c, (int)o, false, *out); }
+    else if (t == "ewald") {
+        const double c = at("cutoff"), a = at("alpha");
+        if (!missing) rc = cgd::make_ewald(c, a, value("epss", inf), value("debyelength", inf), *out);
+    } else if (t == "ewaldt") {
+        const double c = at("cutoff"), a = at("alpha");
+        if (!missing) rc = cgd::make_ewaldt(c, a, value("epss", inf), value("debyelength", inf), *out);
+    } else if (t == "poisson") {
+        const double c = at("cutoff"), C = at("C"), D = at("D");
+        if (!missing) rc = cgd::make_poisson(c, (int)C, (int)D, value("debyelength", inf), *out);
+    } else if (t == "reactionfield") {
+        const double c = at("cutoff"), erf = at("epsRF"), er = at("epsr"), sh = at("shifted");
+        if (!missing) rc = cgd::make_reactionfield(c, erf, er, sh != 0.0, *out);
+    } else if (t == "spline") {
+        rc = CG_ERR_UNSUPPORTED; // known keyword, but the reference's factory builds nothing for it either (all.hpp:98-100)
+    }
+    return rc;
 }
 
 int64_t cg_spline_storage_doubles(void) { return 4 * (CG_SPLINE_MAX_KNOTS + 6 * (CG_SPLINE_MAX_KNOTS - 1)); }

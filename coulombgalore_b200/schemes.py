@@ -85,6 +85,23 @@ class SchemeBase:
         return self.desc.chi / 2.0 / volume * s * s
 
 
+    # serialisation (core.hpp:223-243): the scheme's own keys, then cutoff / doi / type / debyelength
+    def _to_json(self):
+        return {}
+
+    def to_json(self):
+        j = dict(self._to_json())
+        if math.isfinite(self.cutoff):
+            j["cutoff"] = self.cutoff
+        if self.doi:
+            j["doi"] = self.doi
+        if self.name:
+            j["type"] = self.name
+        if math.isfinite(self.debye_length):
+            j["debyelength"] = self.debye_length
+        return j
+
+
 def _ctor(rc, what):
     if rc != 0:
         # the reference constructors throw std::runtime_error on the same conditions (poisson.hpp:81-86)
@@ -106,6 +123,9 @@ class ReactionField(SchemeBase):
         super().__init__()
         _ctor(lib.cg_scheme_reactionfield(cutoff, epsRF, epsr, int(bool(shifted)), C.byref(self.desc)), "ReactionField")
 
+    def _to_json(self):  # reactionfield.hpp:82-84
+        return {"epsr": self.desc.eps_r, "epsRF": self.desc.eps_rf, "shifted": bool(self.desc.shifted)}
+
 
 class Poisson(SchemeBase):
     name, doi = "poisson", "10/c5fr"
@@ -113,6 +133,9 @@ class Poisson(SchemeBase):
     def __init__(self, cutoff, C_, D, debye_length=infinity):
         super().__init__()
         _ctor(lib.cg_scheme_poisson(cutoff, int(C_), int(D), debye_length, C.byref(self.desc)), "Poisson")
+
+    def _to_json(self):  # poisson.hpp:230
+        return {"C": self.desc.C, "D": self.desc.D}
 
 
 class qPotential(SchemeBase):
@@ -122,6 +145,9 @@ class qPotential(SchemeBase):
         super().__init__()
         _ctor(lib.cg_scheme_qpotential(cutoff, int(order), C.byref(self.desc)), "qPotential")
 
+    def _to_json(self):  # qpotential.hpp:280
+        return {"order": self.desc.order}
+
 
 class qPotentialFixedOrder5(SchemeBase):
     """qPotentialFixedOrder<5> (qpotential.hpp:195-232)."""
@@ -130,6 +156,9 @@ class qPotentialFixedOrder5(SchemeBase):
     def __init__(self, cutoff):
         super().__init__()
         _ctor(lib.cg_scheme_qpotential5(cutoff, C.byref(self.desc)), "qPotentialFixedOrder<5>")
+
+    def _to_json(self):  # qpotential.hpp:230
+        return {"order": self.desc.order}
 
 
 class Fanourgakis(SchemeBase):
@@ -147,6 +176,9 @@ class Fennell(SchemeBase):
         super().__init__()
         _ctor(lib.cg_scheme_fennell(cutoff, alpha, C.byref(self.desc)), "Fennell")
 
+    def _to_json(self):  # fennell.hpp:80 -- the REDUCED alpha, under its own key
+        return {"alpha_red": self.desc.eta}
+
 
 class ZeroDipole(SchemeBase):
     name, doi = "ZeroDipole", "10.1063/1.3582791"
@@ -154,6 +186,9 @@ class ZeroDipole(SchemeBase):
     def __init__(self, cutoff, alpha):
         super().__init__()
         _ctor(lib.cg_scheme_zerodipole(cutoff, alpha, C.byref(self.desc)), "ZeroDipole")
+
+    def _to_json(self):  # zerodipole.hpp:88 -- the REDUCED alpha (alpha * cutoff) under the key "alpha", as the reference writes it
+        return {"alpha": self.desc.eta}
 
 
 class Zahn(SchemeBase):
@@ -163,6 +198,9 @@ class Zahn(SchemeBase):
         super().__init__()
         _ctor(lib.cg_scheme_zahn(cutoff, alpha, C.byref(self.desc)), "Zahn")
 
+    def _to_json(self):  # zahn.hpp:83 -- the REDUCED alpha (alpha * cutoff) under the key "alpha", as the reference writes it
+        return {"alpha": self.desc.eta}
+
 
 class Wolf(SchemeBase):
     name, doi = "Wolf", "10.1063/1.478738"
@@ -171,6 +209,9 @@ class Wolf(SchemeBase):
         super().__init__()
         _ctor(lib.cg_scheme_wolf(cutoff, alpha, C.byref(self.desc)), "Wolf")
 
+    def _to_json(self):  # wolf.hpp:78 -- the REDUCED alpha (alpha * cutoff) under the key "alpha", as the reference writes it
+        return {"alpha": self.desc.eta}
+
 
 class Ewald(SchemeBase):
     name, doi = "Ewald real-space", "10.1002/andp.19213690304"
@@ -178,6 +219,13 @@ class Ewald(SchemeBase):
     def __init__(self, cutoff, alpha, surface_dielectric_constant=infinity, debye_length=infinity):
         super().__init__()
         _ctor(lib.cg_scheme_ewald(cutoff, alpha, surface_dielectric_constant, debye_length, C.byref(self.desc)), "Ewald")
+        # the member keeps the value as passed: the reference's `< 1 -> infinity` fix-up assigns to the constructor
+        # parameter that shadows it (ewald.hpp:131-140), so to_json writes e.g. epss = 0.5 back out
+        self.surface_dielectric_constant = surface_dielectric_constant
+
+    def _to_json(self):  # ewald.hpp:203-210
+        eps = self.surface_dielectric_constant
+        return {"alpha": self.desc.eta / self.cutoff, "epss": "inf" if math.isinf(eps) else eps}
 
 
 class EwaldTruncated(SchemeBase):
@@ -187,6 +235,11 @@ class EwaldTruncated(SchemeBase):
         super().__init__()
         _ctor(lib.cg_scheme_ewaldt(cutoff, alpha, surface_dielectric_constant, debye_length, C.byref(self.desc)),
               "EwaldTruncated")
+        self.surface_dielectric_constant = surface_dielectric_constant
+
+    def _to_json(self):  # ewald_truncated.hpp:112-119
+        eps = self.surface_dielectric_constant
+        return {"alpha": self.desc.eta / self.cutoff, "epss": "inf" if math.isinf(eps) else eps}
 
 
 class Splined(SchemeBase):
@@ -236,3 +289,43 @@ class Splined(SchemeBase):
             out.append((np.ctypeslib.as_array(self.desc.spline_r2[k], (n,)).copy(),
                         np.ctypeslib.as_array(self.desc.spline_c[k], (6 * (n - 1),)).copy()))
         return out
+
+
+# ---- run-time factory (reference all.hpp:42-104) ----
+def _at(j, key):
+    if key not in j:
+        raise KeyError("key '%s' not found" % key)  # nlohmann::json::at throws out_of_range
+    return j[key]
+
+
+def _num(v):  # the reference's own to_json writes epss = "inf" as a string (ewald.hpp:206)
+    return math.inf if isinstance(v, str) and v.strip().lower() in ("inf", "infinity") else float(v)
+
+
+_FACTORY = {
+    "plain": lambda j: Plain(_num(j.get("debyelength", infinity))),
+    "wolf": lambda j: Wolf(_at(j, "cutoff"), _at(j, "alpha")),
+    "zahn": lambda j: Zahn(_at(j, "cutoff"), _at(j, "alpha")),
+    "fennell": lambda j: Fennell(_at(j, "cutoff"), _at(j, "alpha")),
+    "zerodipole": lambda j: ZeroDipole(_at(j, "cutoff"), _at(j, "alpha")),
+    "fanourgakis": lambda j: Fanourgakis(_at(j, "cutoff")),
+    "qpotential": lambda j: qPotential(_at(j, "cutoff"), _at(j, "order")),
+    "ewald": lambda j: Ewald(_at(j, "cutoff"), _at(j, "alpha"), _num(j.get("epss", infinity)), _num(j.get("debyelength", infinity))),
+    "ewaldt": lambda j: EwaldTruncated(_at(j, "cutoff"), _at(j, "alpha"), _num(j.get("epss", infinity)),
+                                       _num(j.get("debyelength", infinity))),
+    "poisson": lambda j: Poisson(_at(j, "cutoff"), _at(j, "C"), _at(j, "D"), _num(j.get("debyelength", infinity))),
+    "reactionfield": lambda j: ReactionField(_at(j, "cutoff"), _at(j, "epsRF"), _at(j, "epsr"), _at(j, "shifted")),
+    "spline": lambda j: None,  # a known keyword for which the reference's factory returns a null pointer (all.hpp:98-100)
+}
+
+
+def createScheme(j):
+    """The reference's createScheme(json) for a dict: j["type"] selects the class, the other keys are those of the
+    reference's JSON constructors.  Unknown type -> RuntimeError("unknown coulomb scheme ..."), missing key -> KeyError."""
+    name = _at(j, "type")
+    if name not in _FACTORY:
+        raise RuntimeError("unknown coulomb scheme " + str(name))
+    return _FACTORY[name](j)
+
+
+create_scheme = createScheme

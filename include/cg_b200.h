@@ -113,6 +113,13 @@ int cg_scheme_zahn(double cutoff, double alpha, cg_scheme_desc *out);           
 int cg_scheme_wolf(double cutoff, double alpha, cg_scheme_desc *out);                           /* wolf.hpp:44 */
 int cg_scheme_ewald(double cutoff, double alpha, double eps_sur, double debye_length, cg_scheme_desc *out); /* ewald.hpp:129 */
 int cg_scheme_ewaldt(double cutoff, double alpha, double eps_sur, double debye_length, cg_scheme_desc *out); /* ewald_truncated.hpp:47 */
+/* Run-time factory: the reference's createScheme(json) (all.hpp:42-104) with the JSON object spelled out as a type
+ * keyword ("plain", "wolf", "zahn", "fennell", "zerodipole", "fanourgakis", "qpotential", "ewald", "ewaldt",
+ * "poisson", "reactionfield") and (key, value) pairs with the reference's keys: cutoff, alpha, order, C, D, epsRF, epsr,
+ * shifted (0/1), epss, debyelength (the last two optional, default infinity).  CG_ERR_INVALID: unknown keyword, a
+ * mandatory key missing, or parameters the constructor rejects; CG_ERR_UNSUPPORTED: "spline" (the reference's factory
+ * returns a null pointer for it). */
+int cg_scheme_create(const char *type, int nkeys, const char *const *keys, const double *values, cg_scheme_desc *out);
 /*
  * Splined().spline<T>(...) (splined.hpp:340-367).  `inner` is the analytic scheme; the four tables are generated on
  * the host with the reference's Andrea algorithm (utol<=0 -> 1e-3).  The tables live in `storage`, which the caller

@@ -62,6 +62,22 @@ void put(double *o, const vec3 &v) {
 } // namespace
 
 extern "C" {
+// createScheme(type, {key: value}) -> 0 and the scheme, 1 = null pointer, 2 = unknown keyword, 3 = missing key
+int probe_factory(const char *type, int n, const char *const *keys, const double *values, void **out) {
+    std::map<std::string, double> j;
+    for (int i = 0; i < n; i++) j[keys[i]] = values[i];
+    try {
+        auto s = createScheme(type, j);
+        if (!s) return 1;
+        *out = new std::shared_ptr<SchemeBase>(s);
+        return 0;
+    } catch (const std::out_of_range &) {
+        return 3;
+    } catch (const std::runtime_error &) {
+        return 2;
+    }
+}
+
 
 const char *probe_vector_backend() {
 #ifdef COULOMBGALORE_HAVE_EIGEN

@@ -154,3 +154,88 @@ def test_constructor_errors_and_static_use(probe):
     w = O.Scheme(O.params(O.WOLF, cutoff=12.0, alpha=0.25), "port")
     want = w.pair(1.0, -1.0, (0, 0, 0), (0, 0, 0), (5.0, 0, 0))["ion_ion_energy"] + (-1.0) * w.info()["self_energy_ion"]
     assert probe.probe_static_wolf_energy(12.0, 0.25, 1.0, -1.0, 5.0) == pytest.approx(want, rel=1e-13)
+
+
+def test_runtime_factory_and_serialisation():
+    """createScheme / to_json of the reference (all.hpp:42-104, core.hpp:223-243), incl. its quirks: unknown keyword
+    throws, "spline" yields nothing, Wolf-like schemes serialise the REDUCED alpha under "alpha", Fennell under
+    "alpha_red", Ewald writes an infinite surface dielectric as the string "inf"."""
+    import ctypes as C
+    import coulombgalore_b200 as cg
+    from coulombgalore_b200 import _capi
+    cases = [
+        (dict(type="plain"), cg.Plain()),
+        (dict(type="plain", debyelength=23.0), cg.Plain(23.0)),
+        (dict(type="wolf", cutoff=12.0, alpha=0.25), cg.Wolf(12.0, 0.25)),
+        (dict(type="zahn", cutoff=12.0, alpha=0.25), cg.Zahn(12.0, 0.25)),
+        (dict(type="fennell", cutoff=12.0, alpha=0.25), cg.Fennell(12.0, 0.25)),
+        (dict(type="zerodipole", cutoff=12.0, alpha=0.25), cg.ZeroDipole(12.0, 0.25)),
+        (dict(type="fanourgakis", cutoff=11.0), cg.Fanourgakis(11.0)),
+        (dict(type="qpotential", cutoff=14.0, order=3), cg.qPotential(14.0, 3)),
+        (dict(type="ewald", cutoff=10.0, alpha=0.3), cg.Ewald(10.0, 0.3)),
+        (dict(type="ewald", cutoff=10.0, alpha=0.3, epss=80.0, debyelength=30.0), cg.Ewald(10.0, 0.3, 80.0, 30.0)),
+        (dict(type="ewaldt", cutoff=10.0, alpha=0.3, epss="inf"), cg.EwaldTruncated(10.0, 0.3)),
+        (dict(type="poisson", cutoff=12.0, C=4, D=3), cg.Poisson(12.0, 4, 3)),
+        (dict(type="poisson", cutoff=12.0, C=3, D=3, debyelength=30.0), cg.Poisson(12.0, 3, 3, 30.0)),
+        (dict(type="reactionfield", cutoff=12.0, epsRF=80.0, epsr=1.0, shifted=True), cg.ReactionField(12.0, 80.0, 1.0, True)),
+    ]
+    for j, direct in cases:
+        made = cg.createScheme(j)
+        assert type(made) is type(direct) and bytes(made.desc) == bytes(direct.desc), j
+        # the dependency-free C-ABI factory builds the same descriptor
+        keys = [k for k in j if k != "type"]
+        vals = (C.c_double * max(len(keys), 1))(*[float("inf") if j[k] == "inf" else float(j[k]) for k in keys])
+        karr = (C.c_char_p * max(len(keys), 1))(*[k.encode() for k in keys])
+        d = _capi.SchemeDesc()
+        assert _capi.lib.cg_scheme_create(j["type"].encode(), len(keys), karr, vals, C.byref(d)) == 0, j
+        assert bytes(d) == bytes(direct.desc), j
+    with pytest.raises(RuntimeError, match="unknown coulomb scheme"):
+        cg.createScheme(dict(type="coulomb"))
+    with pytest.raises(KeyError):
+        cg.createScheme(dict(type="wolf", cutoff=12.0))
+    with pytest.raises(ValueError):
+        cg.createScheme(dict(type="poisson", cutoff=12.0, C=0, D=3))  # the constructor's own check (poisson.hpp:81-86)
+    assert cg.createScheme(dict(type="spline")) is None
+    d = _capi.SchemeDesc()
+    assert _capi.lib.cg_scheme_create(b"wolf", 0, None, None, C.byref(d)) == -1
+    assert _capi.lib.cg_scheme_create(b"nonsense", 0, None, None, C.byref(d)) == -1
+    assert _capi.lib.cg_scheme_create(b"spline", 0, None, None, C.byref(d)) == -5
+    # serialisation
+    assert cg.Wolf(12.0, 0.25).to_json() == {"alpha": 3.0, "cutoff": 12.0, "doi": "10.1063/1.478738", "type": "Wolf"}
+    assert cg.Fennell(12.0, 0.25).to_json()["alpha_red"] == 3.0
+    assert cg.Poisson(12.0, 3, 3, 30.0).to_json() == {"C": 3, "D": 3, "cutoff": 12.0, "doi": "10/c5fr", "type": "poisson", "debyelength": 30.0}
+    je = cg.Ewald(10.0, 0.3, cg.infinity, 30.0).to_json()
+    assert je["epss"] == "inf" and abs(je["alpha"] - 0.3) < 1e-15 and "debyelength" not in je  # Ewald hides kappa from the base
+    assert cg.Ewald(10.0, 0.3, 80.0).to_json()["epss"] == 80.0
+    jr = cg.ReactionField(12.0, 80.0, 1.0, False).to_json()
+    assert (jr["epsr"], jr["epsRF"], jr["shifted"], jr["type"]) == (1.0, 80.0, False, "Reaction-field")
+    assert cg.qPotential(14.0, 3).to_json()["order"] == 3 and cg.qPotentialFixedOrder5(14.0).to_json()["order"] == 5
+    jp = cg.Plain().to_json()
+    assert jp["type"] == "plain" and jp["cutoff"] > 1e150 and "debyelength" not in jp
+    # round trip where the reference's own keys allow it
+    back = cg.createScheme(cg.Poisson(12.0, 4, 3).to_json())
+    assert bytes(back.desc) == bytes(cg.Poisson(12.0, 4, 3).desc)
+
+
+def test_cpp_factory(probe):
+    """createScheme(type, {key: value}) of include/coulombgalore/all.hpp: same schemes as direct construction."""
+    probe.probe_factory.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), _dp, C.POINTER(C.c_void_p)]
+
+    def make(type_, **kv):
+        keys = (C.c_char_p * max(len(kv), 1))(*[k.encode() for k in kv])
+        vals = (C.c_double * max(len(kv), 1))(*[float(v) for v in kv.values()])
+        h = C.c_void_p()
+        return probe.probe_factory(type_.encode(), len(kv), keys, vals, C.byref(h)), h
+
+    q = np.linspace(0.05, 0.95, 7)
+    for name, kv in (("wolf", dict(cutoff=12.0, alpha=0.25)), ("poisson43", dict(cutoff=12.0, C=4, D=3)),
+                     ("reactionfield", dict(cutoff=12.0, epsRF=80.0, epsr=1.0, shifted=0)),
+                     ("ewald_screened", dict(cutoff=10.0, alpha=0.3, debyelength=30.0)), ("qpotential3", dict(cutoff=14.0, order=3))):
+        p = oracle_params(name)
+        type_ = {"poisson43": "poisson", "ewald_screened": "ewald", "qpotential3": "qpotential"}.get(name, name)
+        rc, h = make(type_, **kv)
+        assert rc == 0, name
+        made, direct = Host.__new__(Host), Host(probe, p)
+        made.lib, made.h = probe, h
+        assert np.array_equal(made.srf(q), direct.srf(q)) and np.array_equal(made.info(), direct.info()), name
+    assert make("spline")[0] == 1 and make("coulomb")[0] == 2 and make("wolf", cutoff=12.0)[0] == 3
