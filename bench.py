@@ -134,7 +134,8 @@ def main():
     workload = ("configs[1]: Wolf(12,0.25) + Fennell(12,0.25) ion-ion forces, cell list, N=%d^3=%d charges, a=3, periodic, "
                 "R_c=12, fp64; step = spatial sort of the configuration + one Wolf + one Fennell evaluation on it" % (n_side, N))
     config = {"workload": workload, "n_particles": N, "cutoff": CFG["cutoff"], "l2_policy": "L2 flushed (512 MiB write) before every timed step",
-              "parallelism": "i-group sharding x%d, NCCL all-gather of SoA inputs" % world if world > 1 else "single GPU"}
+              "parallelism": ("i-group sharding x%d, exchange of the SoA inputs by a pull kernel over NVLink peer memory "
+                              "(NCCL all-gather if CUDA IPC is unavailable or CG_EXCHANGE=nccl)" % world) if world > 1 else "single GPU"}
 
     from oracle import oracle as O
     okind = "ref" if O.available("ref") else "port"
@@ -193,10 +194,14 @@ def main():
     full = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
     evs["wolf"].generate_lattice_device(n_side, CFG["a"], CFG["seed"], full[0], full[1], full[2], full[3])
     torch.cuda.synchronize()
-    from coulombgalore_b200.distributed import ShardedStep, owned_range
+    from coulombgalore_b200.distributed import PeerExchange, ShardedStep, owned_range
     lo, hi = owned_range(N, rank, world)
     owned = [t[lo:hi].clone() for t in full]  # this rank's particles
-    exchange = ShardedStep(N, 4, dev) if world > 1 else None
+    exchange = None
+    if world > 1:  # the exchange step: this repo's pull kernel over peer memory, or the collective library's all-gather
+        exchange = ShardedStep(N, 4, dev) if os.environ.get("CG_EXCHANGE") == "nccl" else PeerExchange.create(evs["wolf"], N, 4, dev)
+        if isinstance(exchange, PeerExchange):
+            owned = torch.stack(owned)
     gathered = exchange.full if world > 1 else full
     force = torch.empty((N, 3), dtype=torch.float64, device=dev)
     scal = {k: torch.zeros(2, dtype=torch.float64, device=dev) for k in evs}
@@ -205,7 +210,8 @@ def main():
     def step_device():
         launches = 0
         if world > 1:
-            exchange.gather(owned)  # the exchange step: NCCL all-gather of positions + charges of every rank
+            exchange.gather(owned)  # positions + charges of every rank
+            launches += 2 if isinstance(exchange, PeerExchange) else 0  # publish copy + cg_peer_gather (NCCL's kernels are not ours)
         evs["wolf"].set_system_device(gathered[0], gathered[1], gathered[2], gathered[3], None, box, True)
         for name, ev in evs.items():  # wolf first: it owns (bins, sorts) the system fennell borrows
             ev.eval_device(cg.MODE_ION, cg.FORCE, force=force, scalars=scal[name])
@@ -285,6 +291,12 @@ def main():
         for ev in evh.values():
             ev.close()
 
+    exchange_kind = None
+    if world > 1:
+        exchange_kind = "peer-memory pull kernel (cg_peer_gather)" if isinstance(exchange, PeerExchange) else \
+            "NCCL all-gather (%s)" % (getattr(exchange, "fallback_reason", None) or "CG_EXCHANGE=nccl")
+        if isinstance(exchange, PeerExchange):
+            exchange.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -323,7 +335,7 @@ def main():
 
     line = {"metric": "pair interactions/s (fp64)", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": config, "pairs_per_step": pairs_per_step, "e2e": e2e,
+            "dtype": "f64", "data": "synthetic", "config": config, "pairs_per_step": pairs_per_step, "exchange": exchange_kind, "e2e": e2e,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "counters": evs["wolf"].counters()}
     print(json.dumps(line))

@@ -93,6 +93,11 @@ def _load():
         "cg_srf_device": [H, C.c_int64, C.c_void_p, C.c_void_p],
         "cg_last_timings": [H, _dp],
         "cg_last_counters": [H, C.POINTER(C.c_int64)],
+        "cg_peer_alloc": [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p],
+        "cg_peer_free": [C.c_void_p],
+        "cg_peer_open": [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)],
+        "cg_peer_close": [C.c_void_p],
+        "cg_peer_gather": [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p)],
         "cg_generate_lattice_device": [H, C.c_int32, C.c_double, C.c_uint64] + [C.c_void_p] * 7,
         "cg_fp64_peak_probe": [H, _dp, _dp],
     }
@@ -118,7 +123,7 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
             "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",
-            "cg_last_counters", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
+            "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
 
 
 def check(rc, where, handle=None):

@@ -497,6 +497,32 @@ __global__ void torque_kernel(int n, const double *mx, const double *my, const d
     torque[3 * (size_t)i + 2] = ax * by - ay * bx;
 }
 
+// ---- exchange step over peer memory: every rank pulls the other ranks' owned SoA blocks over NVLink ----
+constexpr int kMaxPeers = 16, kMaxPeerArrays = 8;
+struct PeerGather {
+    int nranks, narrays;
+    const double *src[kMaxPeers];  // rank r's block: narrays arrays of count[r] doubles each (array-major), peer-mapped
+    long long count[kMaxPeers], offset[kMaxPeers];
+    double *dst[kMaxPeerArrays];   // the full arrays of this rank
+};
+
+// grid: (chunks, narrays, nranks); plain coalesced 8- or 16-byte loads from the peer mapping, stores to local HBM
+__global__ void peer_gather_kernel(const __grid_constant__ PeerGather g) {
+    const int a = blockIdx.y, r = blockIdx.z;
+    const long long n = g.count[r];
+    const double *s = g.src[r] + (long long)a * n;
+    double *d = g.dst[a] + g.offset[r];
+    const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if ((((size_t)s | (size_t)d) & 15) == 0) {
+        const double2 *s2 = reinterpret_cast<const double2 *>(s);
+        double2 *d2 = reinterpret_cast<double2 *>(d);
+        for (long long k = t0; k < n / 2; k += stride) d2[k] = s2[k];
+        if ((n & 1) && t0 == 0) d[n - 1] = s[n - 1];
+    } else {
+        for (long long k = t0; k < n; k += stride) d[k] = s[k];
+    }
+}
+
 template <class T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
@@ -1469,6 +1495,75 @@ int cg_last_counters(cg_handle *h, int64_t c[8]) {
         h->counters[2] = h->h_counts_async[1];
     }
     for (int k = 0; k < 8; k++) c[k] = h->counters[k];
+    return CG_OK;
+}
+
+// ---- peer-memory exchange (one process per GPU; the handles travel through the caller's process group) ----
+int cg_peer_alloc(int device, size_t bytes, void **ptr, void *handle64) {
+    if (!ptr || !handle64 || bytes == 0) return CG_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return CG_ERR_NO_DEVICE;
+    if (cudaMalloc(ptr, bytes) != cudaSuccess) {
+        g_create_error = std::string("cg_peer_alloc: ") + cudaGetErrorString(cudaGetLastError());
+        return CG_ERR_ALLOC;
+    }
+    cudaIpcMemHandle_t hd;
+    const cudaError_t e = cudaIpcGetMemHandle(&hd, *ptr);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e);
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        return CG_ERR_CUDA;
+    }
+    std::memcpy(handle64, &hd, 64);
+    return CG_OK;
+}
+
+int cg_peer_free(void *ptr) { return (!ptr || cudaFree(ptr) == cudaSuccess) ? CG_OK : CG_ERR_CUDA; }
+
+int cg_peer_open(int device, const void *handle64, void **ptr) {
+    if (!handle64 || !ptr) return CG_ERR_INVALID;
+    if (device >= 0 && cudaSetDevice(device) != cudaSuccess) return CG_ERR_NO_DEVICE;
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, 64);
+    const cudaError_t e = cudaIpcOpenMemHandle(ptr, hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        cudaGetLastError();
+        return CG_ERR_CUDA;
+    }
+    return CG_OK;
+}
+
+int cg_peer_close(void *ptr) { return (!ptr || cudaIpcCloseMemHandle(ptr) == cudaSuccess) ? CG_OK : CG_ERR_CUDA; }
+
+int cg_peer_gather(cg_handle *h, int nranks, const void *const *blocks, const int64_t *counts, int narrays, double *const *full) {
+    if (!h || !blocks || !counts || !full || nranks < 1 || nranks > kMaxPeers || narrays < 1 || narrays > kMaxPeerArrays) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    PeerGather g;
+    std::memset(&g, 0, sizeof(g));
+    g.nranks = nranks;
+    g.narrays = narrays;
+    long long off = 0, cmax = 0;
+    for (int r = 0; r < nranks; r++) {
+        if (!blocks[r] || counts[r] < 0) return CG_ERR_INVALID;
+        g.src[r] = static_cast<const double *>(blocks[r]);
+        g.count[r] = counts[r];
+        g.offset[r] = off;
+        off += counts[r];
+        cmax = std::max<long long>(cmax, counts[r]);
+    }
+    for (int a = 0; a < narrays; a++) {
+        if (!full[a]) return CG_ERR_INVALID;
+        g.dst[a] = full[a];
+    }
+    if (cmax == 0) return CG_OK;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    // enough CTAs in total to keep every NVLink direction busy, never more than the data needs
+    const int per = (int)std::max<long long>(1, std::min<long long>((cmax / 2 + 255) / 256, std::max(1, 8 * sms / (nranks * narrays))));
+    peer_gather_kernel<<<dim3((unsigned)per, (unsigned)narrays, (unsigned)nranks), 256, 0, h->stream>>>(g);
+    CG_CUDA(h, cudaGetLastError());
     return CG_OK;
 }
 

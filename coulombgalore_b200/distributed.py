@@ -58,3 +58,114 @@ class ShardedStep:
         if self.world > 1:
             dist.all_reduce(scalars, op=dist.ReduceOp.SUM, group=self.group)
         return scalars
+
+
+class _DeviceBlock:
+    """Zero-copy torch view of device memory owned by the library (numba-style __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 2, "strides": None}
+
+
+class PeerExchange(ShardedStep):
+    """ShardedStep whose gather is this repo's own kernel over peer memory instead of an NCCL all-gather.
+
+    Every rank keeps its owned SoA slices in a block of IPC-shareable device memory (two blocks, used alternately); the
+    other ranks map it (cudaIpcOpenMemHandle through cg_peer_open) and `gather` PULLS all blocks over NVLink / NVSwitch
+    with one kernel (cg_peer_gather) on the evaluator's stream.  One small all-reduce per step orders the ranks: after
+    it, every rank has written block (step % 2) and has finished reading block ((step - 1) % 2) -- the pull of step
+    s-1 precedes the all-reduce of step s in stream order -- so the owner may rewrite that one in step s + 1.
+    Needs equal slices, one process per GPU on one node and CUDA IPC; `PeerExchange.create` falls back to the NCCL
+    ShardedStep (with the reason in `.fallback_reason`) where that is not available."""
+
+    def __init__(self, evaluator, n_total, n_arrays, device, group=None):
+        import ctypes as C
+        from ._capi import check, lib
+        super().__init__(n_total, n_arrays, device, group=group)
+        if not self.even:
+            raise RuntimeError("PeerExchange needs equal slices on all ranks")
+        self.ev, self.lib, self.C = evaluator, lib, C
+        self.device = torch.device(device)
+        self.count = self.counts[self.rank]
+        nbytes = max(16, n_arrays * self.count * 8)
+        self.own_ptr, handles = [], []
+        for _ in range(2):
+            p, h = C.c_void_p(), C.create_string_buffer(64)
+            check(lib.cg_peer_alloc(self.device.index, nbytes, C.byref(p), h), "cg_peer_alloc")
+            self.own_ptr.append(p)
+            handles.append(h.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=self.group)
+        self.block_ptrs = []  # [buffer][rank] -> device pointer valid in this process
+        self._opened = []
+        for b in range(2):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append(self.own_ptr[b].value)
+                else:
+                    p = C.c_void_p()
+                    check(lib.cg_peer_open(self.device.index, everyone[r][b], C.byref(p)), "cg_peer_open")
+                    self._opened.append(p)
+                    row.append(p.value)
+            self.block_ptrs.append((C.c_void_p * self.world)(*row))
+        self.counts_c = (C.c_int64 * self.world)(*self.counts)
+        self.full_c = (C.c_void_p * n_arrays)(*[t.data_ptr() for t in self.full])
+        # torch views of the two owned blocks: [n_arrays, count]
+        self.owned_blocks = [torch.as_tensor(_DeviceBlock(self.own_ptr[b].value, (n_arrays, max(self.count, 1))), device=self.device)
+                             for b in range(2)]
+        self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.step = 0
+        self.fallback_reason = None
+
+    @staticmethod
+    def create(evaluator, n_total, n_arrays, device, group=None):
+        """PeerExchange where CUDA IPC works and slices are equal, else the NCCL ShardedStep (all ranks decide alike)."""
+        reason = None
+        try:
+            ex = PeerExchange(evaluator, n_total, n_arrays, device, group=group)
+        except Exception as e:  # noqa: BLE001 -- any failure means: use the collective library
+            ex, reason = None, "%s: %s" % (type(e).__name__, e)
+        ok = torch.tensor([0.0 if ex is None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() < 1.0:
+            if ex is not None:
+                ex.close()
+            ex = ShardedStep(n_total, n_arrays, device, group=group)
+            ex.fallback_reason = reason or "a peer rank could not map the blocks"
+        return ex
+
+    def gather(self, owned):
+        b = self.step & 1
+        self.step += 1
+        blk = self.owned_blocks[b]
+        # publish: this rank's new positions / charges / dipoles go into its block (one copy for a stacked
+        # [n_arrays, count] tensor; an integrator would write them there directly: see next_block())
+        if owned is None:
+            pass
+        elif torch.is_tensor(owned):
+            blk[:, : owned.shape[1]].copy_(owned)
+        else:
+            for a, o in enumerate(owned):
+                blk[a, : o.numel()].copy_(o)
+        dist.all_reduce(self.flag, group=self.group)  # everyone has published b and is done reading the other block
+        from ._capi import check
+        check(self.lib.cg_peer_gather(self.ev.h, self.world, self.block_ptrs[b], self.counts_c, len(self.full), self.full_c),
+              "cg_peer_gather", self.ev.h)
+        return self.full
+
+    def next_block(self):
+        """The [n_arrays, count] view of the block the next gather() publishes: write the new owned data here and call
+        gather(None) to skip the copy."""
+        return self.owned_blocks[self.step & 1]
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        if dist.is_initialized():
+            dist.barrier(group=self.group)  # nobody reads a block that is about to be freed
+        for p in self._opened:
+            self.lib.cg_peer_close(p)
+        self._opened = []
+        for p in self.own_ptr:
+            self.lib.cg_peer_free(p)
+        self.own_ptr = []

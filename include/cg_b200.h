@@ -33,6 +33,7 @@
  */
 #ifndef CG_B200_H
 #define CG_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -200,6 +201,21 @@ int cg_last_timings(cg_handle *h, double ms[4]);
 /* counters of the last evaluation: [0] sorted entries incl. periodic images, [1] cells, [2] i-groups,
  * [3] pair-kernel launches, [4] total kernel launches, [5] j-split factor, [6] candidate tests (if counted) */
 int cg_last_counters(cg_handle *h, int64_t c[8]);
+
+/* Exchange step over peer memory, one process per GPU: each rank keeps its owned particles in a block
+ * obtained from cg_peer_alloc (layout: narrays arrays of count doubles, array-major), publishes the 64-byte handle
+ * through its process group, and maps the other ranks' blocks with cg_peer_open.  cg_peer_gather then PULLS all
+ * blocks over NVLink / NVSwitch with one kernel on the handle's stream into this rank's full SoA arrays
+ * (full[a][offset_r .. offset_r + counts[r]) = block r, array a) -- the all-gather of the inputs without a collective
+ * library call.  Ordering between ranks (blocks written before they are read, not rewritten while being read) is the
+ * caller's: coulombgalore_b200.distributed.PeerExchange uses two alternating blocks and one small all-reduce per step.
+ * blocks[rank] may be the local pointer.  device < 0: the current device. */
+int cg_peer_alloc(int device, size_t bytes, void **ptr, void *handle64);
+int cg_peer_free(void *ptr);
+int cg_peer_open(int device, const void *handle64, void **ptr);
+int cg_peer_close(void *ptr);
+int cg_peer_gather(cg_handle *h, int nranks, const void *const *blocks, const int64_t *counts, int narrays,
+                   double *const *full);
 
 /* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,

@@ -1,0 +1,65 @@
+"""Run under torchrun by tests/test_gpu_system.py: PeerExchange.gather must reproduce the NCCL all-gather bit for bit,
+over several steps (both blocks of the double buffer), and the sharded evaluation on the gathered arrays must add up."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import coulombgalore_b200 as cg  # noqa: E402
+from coulombgalore_b200.distributed import PeerExchange, ShardedStep, owned_range  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    n_side = 12
+    N = n_side ** 3
+    ev = cg.BatchedEvaluator(cg.Wolf(12.0, 0.25), local)
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ev.set_stream(stream.cuda_stream)
+    ev.set_shard(rank, world)
+    arr = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
+    ev.generate_lattice_device(n_side, 3.0, 99, arr[0], arr[1], arr[2], arr[3])
+    lo, hi = owned_range(N, rank, world)
+    peer = PeerExchange.create(ev, N, 4, dev)
+    assert isinstance(peer, PeerExchange), getattr(peer, "fallback_reason", None)
+    nccl = ShardedStep(N, 4, dev)
+    L = n_side * 3.0
+    f = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+    sc = torch.zeros(2, dtype=torch.float64, device=dev)
+    for step in range(5):
+        owned = [((a + 0.01 * step) % L if k < 3 else a)[lo:hi].clone() for k, a in enumerate(arr)]  # positions move every step
+        got = peer.gather(owned)
+        ref = nccl.gather(owned)
+        stream.synchronize()
+        for g, r in zip(got, ref):
+            assert torch.equal(g, r), "step %d" % step
+        ev.set_system_device(got[0], got[1], got[2], got[3], None, [L] * 3, True)
+        f.zero_()
+        ev.eval_device(cg.MODE_ION, cg.ENERGY | cg.FORCE, force=f, scalars=sc)
+        peer.reduce_scalars(sc)
+        dist.all_reduce(f)
+        stream.synchronize()
+        if step == 0:
+            single = cg.BatchedEvaluator(cg.Wolf(12.0, 0.25), local)
+            single.set_system(*[t.cpu().numpy() for t in ref], None, [L] * 3, True)
+            want = single.eval(cg.MODE_ION, cg.ENERGY | cg.FORCE)
+            assert int(sc[1].item()) == want["pairs"] and abs(sc[0].item() - want["energy"]) <= 1e-12 * abs(want["energy"]) + 1e-9
+            assert np.max(np.abs(f.cpu().numpy() - want["force"])) <= 1e-12 * np.max(np.abs(want["force"]))
+            single.close()
+    peer.close()
+    ev.close()
+    dist.barrier()
+    if rank == 0:
+        print("PEER_EXCHANGE_OK world=%d" % world, flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -285,3 +285,19 @@ def test_full_size_properties_one_million(oracle_kind):
         dn = np.linalg.norm(F[lo:hi] - r["force"], axis=1)
         assert np.max(dn / np.maximum(np.linalg.norm(r["force"], axis=1), r["force_scale"])) <= TOL
         ev.close()
+
+
+def test_peer_exchange_single_rank_and_two_ranks_if_available():
+    """cg_peer_alloc / cg_peer_gather: the exchange step as this repo's own kernel over (peer-mapped) device memory.
+    With one GPU the rank pulls from its own block (the kernel, the torch view of the block and the double buffering are
+    exercised); with two or more GPUs a 2-rank torchrun job checks the real peer mapping against the NCCL all-gather."""
+    import subprocess
+    import sys
+    import torch
+    script = os.path.join(ROOT, "tests", "peer_exchange_check.py")
+    n = min(2, torch.cuda.device_count())
+    for world in sorted({1, n}):
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", str(29650 + world), script]
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0 and "PEER_EXCHANGE_OK world=%d" % world in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

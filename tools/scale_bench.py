@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 import coulombgalore_b200 as cg
-from coulombgalore_b200.distributed import ShardedStep, owned_range
+from coulombgalore_b200.distributed import PeerExchange, ShardedStep, owned_range
 
 INF = float("inf")
 CONFIGS = {
@@ -41,20 +41,32 @@ def main():
         use = [0, 1, 2] + ([3] if c["mode"] != cg.MODE_DIPOLE else []) + ([4, 5, 6] if c["mode"] != cg.MODE_ION else [])
         lo, hi = owned_range(N, rank, world)
         owned = [arr[k][lo:hi].clone() for k in use]
-        ex = ShardedStep(N, len(use), dev)
+        # CG_EXCHANGE=nccl: the all-gather of the collective library; default: this repo's pull kernel over peer memory
+        ex = ShardedStep(N, len(use), dev) if (world == 1 or os.environ.get("CG_EXCHANGE") == "nccl") else PeerExchange.create(ev, N, len(use), dev)
         del arr
         f = torch.empty((N, 3), dtype=torch.float64, device=dev)
         e = torch.empty((N, 3), dtype=torch.float64, device=dev) if c["what"] & cg.FIELD else None
         sc = torch.zeros(2, dtype=torch.float64, device=dev)
         flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
-        def step():
+        marks = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+
+        if isinstance(ex, PeerExchange):
+            owned = torch.stack(owned)  # one publish copy per step instead of one per array
+
+        def step(mk=None):
             full = ex.gather(owned)
+            if mk:
+                mk[0].record()
             g = dict(zip(use, full))
             mu = (g[4], g[5], g[6]) if 4 in g else None
             ev.set_system_device(g[0], g[1], g[2], g.get(3), mu, [L] * 3, True)
             ev.eval_device(c["mode"], c["what"], force=f, field=e, scalars=sc)
+            if mk:
+                mk[1].record()
             ex.reduce_scalars(sc)
+            if mk:
+                mk[2].record()
 
         def barrier():
             if world > 1:
@@ -71,23 +83,31 @@ def main():
             flush.fill_(s & 255)
             barrier()
             e0[s].record()
-            step()
+            step(marks[s])
             e1[s].record()
             e1[s].synchronize()
             t = ev.timings()
             pair_ms.append(t["pair_ms"])
             sort_ms.append(t["sort_ms"])
         barrier()
-        ms = torch.tensor([statistics.mean(e0[s].elapsed_time(e1[s]) for s in range(steps)), statistics.mean(pair_ms), statistics.mean(sort_ms)],
+        ms = torch.tensor([statistics.mean(e0[s].elapsed_time(e1[s]) for s in range(steps)), statistics.mean(pair_ms), statistics.mean(sort_ms),
+                           statistics.mean(e0[s].elapsed_time(marks[s][0]) for s in range(steps)),
+                           statistics.mean(marks[s][0].elapsed_time(marks[s][1]) for s in range(steps)),
+                           statistics.mean(marks[s][1].elapsed_time(marks[s][2]) for s in range(steps))],
                           dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         pairs = sc[1].item()  # all-reduced total
         if rank == 0:
             print(json.dumps({"cfg": nm, "n_gpus": world, "n_particles": N, "pairs_per_step": pairs, "ms_per_step": ms[0].item(),
-                              "pair_kernel_ms_max": ms[1].item(), "sort_ms_max": ms[2].item(), "pairs_per_s": pairs / ms[0].item() * 1e3,
+                              "pair_kernel_ms_max": ms[1].item(), "sort_ms_max": ms[2].item(),
+                              "gather_ms_max": ms[3].item(), "eval_ms_max": ms[4].item(), "allreduce_ms_max": ms[5].item(), "pairs_per_s": pairs / ms[0].item() * 1e3,
                               "tflops_alg": pairs * c["falg"] / ms[0].item() * 1e3 / 1e12, "energy": sc[0].item(),
-                              "exchange": "all-gather of %d fp64 arrays (%d B/particle) + all-reduce of 2 scalars" % (len(use), 8 * len(use))}), flush=True)
+                              "exchange": "%s of %d fp64 arrays (%d B/particle) + all-reduce of 2 scalars" %
+                              ("peer-memory pull kernel" if isinstance(ex, PeerExchange) else "NCCL all-gather", len(use), 8 * len(use)),
+                              "exchange_fallback": getattr(ex, "fallback_reason", None)}), flush=True)
+        if isinstance(ex, PeerExchange):
+            ex.close()
         ev.close()
         del f, e, flush, ex, owned
         torch.cuda.empty_cache()
