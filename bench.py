@@ -124,6 +124,10 @@ def cpu_reference_rate(kind, n_side, target_seconds, nthreads=0):
     return pairs / dt, cores, "first %d of %d i-particles, Wolf + Fennell force, %.1f s incl. cell-list build" % (m, N, dt), schemes[0].kind
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one Wolf pair_kernel launch (profiles/ncu_r1_pair_kernel_wolf_v5.txt)
+NCU_DRAM_BYTES_PER_LAUNCH = 65406976 + 7085568
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -322,7 +326,9 @@ def main():
                 "unit": "TFLOP/s", "frac": ach / peak_tf if peak_tf else None,
                 "peak_source": "measured here: register-resident DFMA chain (cg_fp64_peak_probe); MEASURED_PEAKS.json has no fp64 entry",
                 "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": ach / NOMINAL_FP64_TFLOPS,
-                "flops_per_pair": F_ALG, "traffic": None,
+                "flops_per_pair": F_ALG, "traffic": NCU_DRAM_BYTES_PER_LAUNCH if world == 1 else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one Wolf pair_kernel launch at N=10^6, ncu --set full, "
+                                  "profiles/ncu_r1_pair_kernel_wolf_v5.txt (65.41 MB + 7.09 MB); algorithmic bytes per launch: 88 MB",
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (kms * 1e-3) / 1e9,
                         "peak_gbs": hbm_peak, "frac": (alg_bytes / (kms * 1e-3) / 1e9 / hbm_peak) if hbm_peak else None,
                         "note": "shown only to establish that the path is not HBM-bound"},

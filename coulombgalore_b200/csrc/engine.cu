@@ -342,7 +342,17 @@ __global__ void reduce_items_kernel(const int *counts, int split, const double *
     const int items = counts[1] * split;
     double e = 0.0;
     unsigned long long c = 0;
-    for (int k = threadIdx.x; k < items; k += 1024) {
+    int k = threadIdx.x;
+    for (; k + 3 * 1024 < items; k += 4 * 1024) { // four loads in flight, added in the order of the plain loop
+        const double e0 = item_energy[k], e1 = item_energy[k + 1024], e2 = item_energy[k + 2048], e3 = item_energy[k + 3072];
+        const unsigned long long c0 = item_pairs[k], c1 = item_pairs[k + 1024], c2 = item_pairs[k + 2048], c3 = item_pairs[k + 3072];
+        e += e0;
+        e += e1;
+        e += e2;
+        e += e3;
+        c += c0 + c1 + c2 + c3;
+    }
+    for (; k < items; k += 1024) {
         e += item_energy[k];
         c += item_pairs[k];
     }
