@@ -17,7 +17,7 @@ STATUS = {0: "CG_OK", -1: "CG_ERR_INVALID", -2: "CG_ERR_NO_DEVICE", -3: "CG_ERR_
 # cg_scheme_id
 (PLAIN, EWALD, EWALDT, REACTIONFIELD, WOLF, POISSON, QPOTENTIAL, FANOURGAKIS, ZERODIPOLE, ZAHN, FENNELL, QPOTENTIAL5,
  SPLINE) = range(13)
-MODE_ION, MODE_DIPOLE, MODE_MULTIPOLE = 0, 1, 2
+MODE_ION, MODE_DIPOLE, MODE_MULTIPOLE, MODE_MULTIPOLE_QUAD = 0, 1, 2, 3
 ENERGY, FORCE, FIELD, POTENTIAL = 1, 2, 4, 8
 MAX_POISSON_C = 12
 SPLINE_MAX_KNOTS = 64
@@ -86,6 +86,8 @@ def _load():
         "cg_eval_begin": [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p],
         "cg_eval_end": [H, _dp, C.POINTER(C.c_int64)],
         "cg_eval_device": [H, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "cg_set_quadrupoles": [H, C.c_void_p],
+        "cg_set_quadrupoles_device": [H, C.c_void_p],
         "cg_self_terms": [H, _dp, C.c_void_p],
         "cg_self_terms_device": [H, C.c_void_p, C.c_void_p],
         "cg_dipole_torque": [H, C.c_void_p, C.c_void_p],
@@ -122,7 +124,7 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_scheme_zahn", "cg_scheme_wolf", "cg_scheme_ewald", "cg_scheme_ewaldt", "cg_scheme_create", "cg_spline_storage_doubles",
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
-            "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",
+            "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_set_quadrupoles", "cg_set_quadrupoles_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",
             "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
 
 

@@ -76,6 +76,16 @@ class BatchedEvaluator:
         check(lib.cg_set_system(self.h, self.n, _hp(x), _hp(y), _hp(z), _hp(q), _hp(mx), _hp(my), _hp(mz),
                                 None if b is None else b.ctypes.data_as(_capi._dp), int(bool(pbc))), "cg_set_system", self.h)
 
+    def set_quadrupoles(self, quad):
+        """(n, 3, 3) or (n, 9) quadrupole tensors of the system just set (MODE_MULTIPOLE_QUAD); None clears them."""
+        q = None if quad is None else np.ascontiguousarray(quad, dtype=np.float64).reshape(self.n, 9)
+        self._keep_quad = q
+        check(lib.cg_set_quadrupoles(self.h, _hp(q)), "cg_set_quadrupoles", self.h)
+
+    def set_quadrupoles_device(self, quad):
+        self._keep_quad = quad
+        check(lib.cg_set_quadrupoles_device(self.h, _devptr(quad)), "cg_set_quadrupoles_device", self.h)
+
     def _outputs(self, what, out):
         n, out = (self._source.n if self._source is not None else self.n), out or {}
 

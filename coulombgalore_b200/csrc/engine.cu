@@ -96,6 +96,7 @@ static int functor_for(const cg_scheme_desc &d) {
 struct SortParams {
     int n;
     const double *x, *y, *z, *q, *mx, *my, *mz;
+    const double *quad; // [n][9] row-major quadrupole tensors, or null
     double lo[3];     // lower corner of the primary region (0 for periodic boxes, min coordinate for open ones)
     double box[3];    // periodic lengths (or extent for open boundaries)
     double gw[3];     // ghost width = ghost layers * cell size (0 for open boundaries)
@@ -175,7 +176,7 @@ __global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int 
 }
 
 __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, double4 *pos,
-                              double4 *mu, float4 *pos32, int *orig, double far) {
+                              double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     int n_sorted = counts[0];
     if (n_sorted > cap - 1) { // no room (the dummy entry needs one slot too): flag it, stay inside the arrays
@@ -186,6 +187,7 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts
     if (k == n_sorted) { // dummy entry far outside the system: chargeless, momentless, beyond every cut-off
         pos[k] = make_double4(far, far, far, 0.0);
         if (mu) mu[k] = make_double4(0.0, 0.0, 0.0, 0.0);
+        if (quad) quad[2 * k] = quad[2 * k + 1] = make_double4(0.0, 0.0, 0.0, 0.0);
         return;
     }
     const unsigned int key = keys[k];
@@ -196,6 +198,11 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts
     const double X = sp.x[p] + (double)sx * sp.box[0], Y = sp.y[p] + (double)sy * sp.box[1], Z = sp.z[p] + (double)sz * sp.box[2];
     pos[k] = make_double4(X, Y, Z, sp.q ? sp.q[p] : 0.0);
     if (mu) mu[k] = sp.mx ? make_double4(sp.mx[p], sp.my[p], sp.mz[p], 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
+    if (quad) { // the pair formulas need S = Q + Q^T and trace(Q) only (detail/pair.hpp: QuadT)
+        const double *Q = sp.quad + 9 * (size_t)p;
+        quad[2 * k] = make_double4(2.0 * Q[0], 2.0 * Q[4], 2.0 * Q[8], Q[0] + Q[4] + Q[8]);
+        quad[2 * k + 1] = make_double4(Q[1] + Q[3], Q[2] + Q[6], Q[5] + Q[7], 0.0);
+    }
     const float fx = (float)(X - (sp.lo[0] - sp.gw[0])), fy = (float)(Y - (sp.lo[1] - sp.gw[1])), fz = (float)(Z - (sp.lo[2] - sp.gw[2]));
     // w = |c|^2 of the ROUNDED coordinates (formed in fp64, rounded once): the prefilter expands |c - x_i|^2 around it
     pos32[k] = make_float4(fx, fy, fz, (float)((double)fx * fx + (double)fy * fy + (double)fz * fz));
@@ -557,7 +564,7 @@ template <class T> struct DevBuf {
 struct Sorted {
     SortParams sp;
     int ncell = 0, nrows_prim = 0, cap_sorted = 0, ng_bound = 0, ng_guess = 0;
-    bool has_mu = false, fast = false, valid = false;
+    bool has_mu = false, has_quad = false, fast = false, valid = false;
     double rc = 0.0; // the cut-off the cell grid was built for
 };
 
@@ -584,7 +591,9 @@ struct cg_handle {
     // sorted system
     DevBuf<int> cell_count, cell_start, scan_tmp, row_ngroups, row_gstart, orig;
     DevBuf<unsigned int> keys;
-    DevBuf<double4> pos, mu;
+    DevBuf<double4> pos, mu, quad;
+    const double *in_quad = nullptr; // device [n][9] (own copy or the caller's); reset by cg_set_system*
+    DevBuf<double> own_quad;
     DevBuf<float4> pos32;
     DevBuf<int2> groups;
     DevBuf<double> minmax_partial, self_partial;
@@ -764,6 +773,8 @@ int cg_destroy(cg_handle *h) {
     h->keys.release();
     h->pos.release();
     h->mu.release();
+    h->quad.release();
+    h->own_quad.release();
     h->pos32.release();
     h->groups.release();
     h->minmax_partial.release();
@@ -858,6 +869,7 @@ static int set_system_common(cg_handle *h, int64_t n, const double *box, int pbc
         }
     }
     h->n = n;
+    h->in_quad = nullptr; // quadrupoles belong to one configuration: cg_set_quadrupoles* after every cg_set_system*
     h->have_system = true;
     h->sorted.valid = false; // borrowers must wait for this handle's next evaluation
     return CG_OK;
@@ -899,7 +911,7 @@ int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double 
 }
 
 // ---- binning, spatial sort and i-groups of the handle's own system (steps 0-5); the result is described by h->sorted ----
-static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
+static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches_out) {
     cudaStream_t st = h->stream;
     const int n = (int)h->n;
     const double rc = h->desc.cutoff;
@@ -919,6 +931,7 @@ static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
     sp.mx = h->in[4];
     sp.my = h->in[5];
     sp.mz = h->in[6];
+    sp.quad = h->in_quad;
     sp.pbc = h->pbc ? 1 : 0;
     double ext[3];
     if (h->pbc) {
@@ -1065,6 +1078,7 @@ static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
     CG_CUDA(h, h->keys.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->pos.ensure((size_t)cap_sorted));
     if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)cap_sorted));
+    if (need_quad) CG_CUDA(h, h->quad.ensure(2 * (size_t)cap_sorted));
     CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->groups.ensure((size_t)ng_bound + 1));
@@ -1080,7 +1094,7 @@ static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
         }
         far_coord = lo - 4.0 * span - 4.0 * std::min(rc, 1e9) - 1.0;
     }
-    gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, h->pos32.p,
+    gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p,
                                                          h->orig.p, far_coord);
     row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p, ng_bound);
     *launches_out += 4;
@@ -1094,6 +1108,7 @@ static int sort_system(cg_handle *h, bool need_mu, int *launches_out) {
     S.ng_bound = ng_bound;
     S.ng_guess = ng_guess;
     S.has_mu = need_mu;
+    S.has_quad = need_quad;
     S.fast = fast;
     S.valid = true;
     CG_CUDA(h, cudaEventRecord(h->sorted_ev, st));
@@ -1107,7 +1122,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         h->err = "cg_eval before cg_set_system";
         return CG_ERR_STATE;
     }
-    if (mode < 0 || mode > 2 || (what & ~15) || what == 0) return CG_ERR_INVALID;
+    if (mode < 0 || mode > CG_MODE_MULTIPOLE_QUAD || (what & ~15) || what == 0) return CG_ERR_INVALID;
     cudaSetDevice(h->device);
     cudaStream_t st = h->stream;
     int launches = 0, pair_launches = 0;
@@ -1129,11 +1144,16 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     cg_handle *s = h->share_from ? h->share_from : h;
     if (s == h) {
         const bool need_mu = h->in[4] != nullptr && (mode != CG_MODE_ION || !h->borrowers.empty());
+        const bool need_quad = h->in_quad != nullptr && (mode == CG_MODE_MULTIPOLE_QUAD || !h->borrowers.empty());
         if (mode != CG_MODE_ION && !need_mu) {
             h->err = "dipole / multipole evaluation of a system without dipole moments";
             return CG_ERR_STATE;
         }
-        const int rcs = sort_system(h, need_mu, &launches);
+        if (mode == CG_MODE_MULTIPOLE_QUAD && !need_quad) {
+            h->err = "CG_MODE_MULTIPOLE_QUAD without quadrupoles: call cg_set_quadrupoles after cg_set_system";
+            return CG_ERR_STATE;
+        }
+        const int rcs = sort_system(h, need_mu, need_quad, &launches);
         if (rcs != CG_OK) return rcs;
     } else {
         if (!s->sorted.valid || s->sorted.rc != D.cutoff) {
@@ -1142,6 +1162,10 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         }
         if (mode != CG_MODE_ION && !s->sorted.has_mu) {
             h->err = "cg_share_system: the source handle's system has no dipole moments";
+            return CG_ERR_STATE;
+        }
+        if (mode == CG_MODE_MULTIPOLE_QUAD && !s->sorted.has_quad) {
+            h->err = "cg_share_system: the source handle's system has no quadrupoles";
             return CG_ERR_STATE;
         }
         CG_CUDA(h, cudaStreamWaitEvent(st, s->sorted_ev, 0));
@@ -1183,6 +1207,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     std::memset(&kp, 0, sizeof(kp));
     kp.pos = s->pos.p;
     kp.mu = need_mu ? s->mu.p : nullptr;
+    kp.quad = mode == CG_MODE_MULTIPOLE_QUAD ? s->quad.p : nullptr;
     kp.pos32 = s->pos32.p;
     kp.orig = s->orig.p;
     kp.cell_start = s->cell_start.p;
@@ -1368,7 +1393,7 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
         s->fast.valid = false;
         if (s != h) { // borrowed arrays: sort the lender's system again, exactly
             int l = 0;
-            const int rcs = sort_system(s, s->sorted.has_mu, &l);
+            const int rcs = sort_system(s, s->sorted.has_mu, s->sorted.has_quad, &l);
             if (rcs != CG_OK) {
                 h->err = s->err;
                 return rcs;
@@ -1386,6 +1411,33 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
 int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
     const int rc = cg_eval_begin(h, mode, what, force, field, potential);
     return rc != CG_OK ? rc : cg_eval_end(h, energy, pairs);
+}
+
+int cg_set_quadrupoles(cg_handle *h, const double *quad) {
+    if (!h) return CG_ERR_INVALID;
+    if (h->share_from || !h->have_system) {
+        h->err = "cg_set_quadrupoles: needs a handle with its own system (after cg_set_system)";
+        return CG_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    h->in_quad = nullptr;
+    h->sorted.valid = false;
+    if (!quad || h->n == 0) return CG_OK;
+    CG_CUDA(h, h->own_quad.ensure(9 * (size_t)h->n));
+    CG_CUDA(h, cudaMemcpyAsync(h->own_quad.p, quad, 9 * (size_t)h->n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->in_quad = h->own_quad.p;
+    return CG_OK;
+}
+
+int cg_set_quadrupoles_device(cg_handle *h, const double *quad) {
+    if (!h) return CG_ERR_INVALID;
+    if (h->share_from || !h->have_system) {
+        h->err = "cg_set_quadrupoles: needs a handle with its own system (after cg_set_system)";
+        return CG_ERR_STATE;
+    }
+    h->in_quad = quad;
+    h->sorted.valid = false;
+    return CG_OK;
 }
 
 int cg_self_terms_device(cg_handle *h, double *out3, double *self_field) {

@@ -33,6 +33,7 @@ constexpr int kSlots = CG_SLOTS; // candidate batches (of 32) whose per-lane hit
 struct KParams {
     const double4 *pos;   // x, y, z, charge            [n_sorted + 1]
     const double4 *mu;    // mu_x, mu_y, mu_z, 0        [n_sorted + 1]  (may be null when no dipoles are needed)
+    const double4 *quad;  // two per entry: {S_xx, S_yy, S_zz, trace}, {S_xy, S_xz, S_yz, 0}, S = Q + Q^T  [2 (n_sorted + 1)] (quadrupole mode)
     const float4 *pos32;  // position relative to the grid origin in fp32, w = |xyz|^2   [n_sorted]
     const int *orig;      // original particle index of a sorted entry               [n_sorted]
     const int *cell_start; // first sorted entry of each cell, x fastest             [ncell + 1]
@@ -66,7 +67,7 @@ typedef cudaError_t (*srf_launch_fn)(const cg_scheme_desc &desc, const double *d
 struct Combo {
     int mode, what;
 };
-constexpr int kNumCombos = 8;
+constexpr int kNumCombos = 10;
 __host__ __device__ constexpr Combo combo(int i) {
     return i == 0   ? Combo{cgd::kModeIon, 2}
            : i == 1 ? Combo{cgd::kModeIon, 3}
@@ -75,12 +76,14 @@ __host__ __device__ constexpr Combo combo(int i) {
            : i == 4 ? Combo{cgd::kModeDipole, 15}
            : i == 5 ? Combo{cgd::kModeMultipole, 3}
            : i == 6 ? Combo{cgd::kModeMultipole, 15}
-                    : Combo{cgd::kModeIon, 1};
+           : i == 7 ? Combo{cgd::kModeIon, 1}
+           : i == 8 ? Combo{cgd::kModeMultipoleQuad, 3}
+                    : Combo{cgd::kModeMultipoleQuad, 15};
 }
 
 struct FunctorEntry {
     pair_launch_fn pair[kNumCombos];   // fp64 pair arithmetic
-    pair_launch_fn pair32[kNumCombos]; // fp32 pair arithmetic (CG_FP32)
+    pair_launch_fn pair32[kNumCombos]; // fp32 pair arithmetic (CG_FP32); the quadrupole combinations are fp64 in both tables
     srf_launch_fn srf;
     int table_kind; // cgd::kTableNone / kTableSpline / kTableErfc: which table the engine must pass
 };

@@ -51,7 +51,8 @@ __device__ __forceinline__ double4 ldg256(const double4 *p) {
     return v;
 }
 
-template <int MODE> constexpr int min_blocks_per_sm() { return CG_MINB; }
+// the quadrupole mode carries two tensors per pair in registers: one CTA per SM (255 registers) instead of spilling at 128
+template <int MODE> constexpr int min_blocks_per_sm() { return MODE == cgd::kModeMultipoleQuad ? 1 : CG_MINB; }
 #ifndef CG_ILP_DIP
 #define CG_ILP_DIP 1
 #endif
@@ -101,6 +102,11 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         mui = {(T)m.x, (T)m.y, (T)m.z};
     }
     const T zi = (T)pi.w;
+    cgd::QuadT<T> quadi = {};
+    if constexpr (MODE == cgd::kModeMultipoleQuad) {
+        const double4 a = ldg256(p.quad + 2 * i), b = ldg256(p.quad + 2 * i + 1);
+        quadi = {(T)a.x, (T)a.y, (T)a.z, (T)a.w, (T)b.x, (T)b.y, (T)b.z};
+    }
     const float4 pf = p.pos32[i];
     // bounding box of the group (coordinates relative to the grid origin are >= 0: float order == int order)
     const float xmin = __int_as_float(__reduce_min_sync(full, __float_as_int(pf.x)));
@@ -244,12 +250,14 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             return j;
         };
         bool hh[2][kIlp];
+        int jj[2][kIlp]; // quadrupole mode: the tensors of j are fetched in the compute step (no room for a prefetched set)
         double4 pp[2][kIlp], mm[2][kIlp];
         auto fetch = [&](auto S) {
             constexpr int s = decltype(S)::value;
 #pragma unroll
             for (int u = 0; u < kIlp; u++) {
                 const int j = pop(hh[s][u]);
+                jj[s][u] = j;
                 pp[s][u] = ldg256(p.pos + j);
                 if constexpr (MODE != cgd::kModeIon) mm[s][u] = ldg256(p.mu + j);
             }
@@ -268,7 +276,13 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                 // a lane that ran dry evaluates a harmless in-range distance (its contribution is zeroed by `pass`);
                 // rejected real pairs lie within the prefilter margin of the cut-off and are harmless as they are
                 const T r2e = hh[s][u] ? (T)r2 : (T)p.rc2_safe;
-                cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, r2e, zi, (T)pp[s][u].w, mui, muj, acc, pass);
+                if constexpr (MODE == cgd::kModeMultipoleQuad) {
+                    const double4 a = ldg256(p.quad + 2 * jj[s][u]), b = ldg256(p.quad + 2 * jj[s][u] + 1);
+                    const cgd::QuadT<T> quadj = {(T)a.x, (T)a.y, (T)a.z, (T)a.w, (T)b.x, (T)b.y, (T)b.z};
+                    cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, r2e, zi, (T)pp[s][u].w, mui, muj, acc, pass, &quadi, &quadj);
+                } else {
+                    cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, r2e, zi, (T)pp[s][u].w, mui, muj, acc, pass);
+                }
             }
         };
         using I0 = std::integral_constant<int, 0>;
@@ -393,12 +407,14 @@ cudaError_t launch_srf(const cg_scheme_desc &desc, const double *dev_table, int 
     return cudaGetLastError();
 }
 
-// table of launchers for one functor: the eight instantiated (mode, what) combinations, in fp64 and fp32
+// table of launchers for one functor: the ten instantiated (mode, what) combinations, in fp64 and fp32
+// (the two quadrupole combinations exist in fp64 only)
 #define CGB_PAIR_ROW(FUNCTOR, YUK, T)                                                                                          \
     {launch_pair<FUNCTOR, YUK, combo(0).mode, combo(0).what, T>, launch_pair<FUNCTOR, YUK, combo(1).mode, combo(1).what, T>,   \
      launch_pair<FUNCTOR, YUK, combo(2).mode, combo(2).what, T>, launch_pair<FUNCTOR, YUK, combo(3).mode, combo(3).what, T>,   \
      launch_pair<FUNCTOR, YUK, combo(4).mode, combo(4).what, T>, launch_pair<FUNCTOR, YUK, combo(5).mode, combo(5).what, T>,   \
-     launch_pair<FUNCTOR, YUK, combo(6).mode, combo(6).what, T>, launch_pair<FUNCTOR, YUK, combo(7).mode, combo(7).what, T>}
+     launch_pair<FUNCTOR, YUK, combo(6).mode, combo(6).what, T>, launch_pair<FUNCTOR, YUK, combo(7).mode, combo(7).what, T>,   \
+     launch_pair<FUNCTOR, YUK, combo(8).mode, combo(8).what, double>, launch_pair<FUNCTOR, YUK, combo(9).mode, combo(9).what, double>}
 #define CGB_DEFINE_FUNCTOR_ENTRY(NAME, FUNCTOR, YUK)                                                                  \
     namespace cgb {                                                                                                   \
     const FunctorEntry *NAME() {                                                                                      \

@@ -25,7 +25,8 @@
  * Batched semantics (identical to oracle/harness.hpp): for every particle i, sum over j != i with
  * |d| < cutoff, d = r_i - r_j (minimum image when pbc): potential/field use d; the ion force on i is
  * ion_ion_force(z_j, z_i, d); the dipole force on i is dipole_dipole_force(mu_i, mu_j, -d); multipole energy and
- * force are the reference functions called with A = i, B = j, r = r_j - r_i and zero quadrupoles; U = 1/2 sum u_ij.
+ * force are the reference functions called with A = i, B = j, r = r_j - r_i and zero quadrupoles (the given ones with
+ * CG_MODE_MULTIPOLE_QUAD, where the potential also adds quadrupole_potential(quad_j, d)); U = 1/2 sum u_ij.
  *
  * All entry points return CG_OK (0) or a negative cg_status; none throws.  A handle owns its device buffers and one
  * CUDA stream; it is not safe to call one handle from two threads at once, separate handles are independent.
@@ -135,7 +136,10 @@ int cg_scheme_splined_tables(const cg_scheme_desc *inner, const int32_t n_knots[
 /* host evaluation of S..S''' from a descriptor (same code path as the header classes): out[k*n+i] */
 int cg_srf_host(const cg_scheme_desc *d, int64_t n, const double *q, double *out);
 
-typedef enum cg_mode { CG_MODE_ION = 0, CG_MODE_DIPOLE = 1, CG_MODE_MULTIPOLE = 2 } cg_mode;
+/* CG_MODE_MULTIPOLE_QUAD: CG_MODE_MULTIPOLE with the quadrupole tensors of cg_set_quadrupoles* (the reference's
+ * quadrupole_potential core.hpp:320, the quad branches of multipole_field :477-481, multipole_multipole_energy :603-609 and
+ * multipole_multipole_force :767-773, i.e. the ion-quadrupole terms; fp64 arithmetic in both precisions) */
+typedef enum cg_mode { CG_MODE_ION = 0, CG_MODE_DIPOLE = 1, CG_MODE_MULTIPOLE = 2, CG_MODE_MULTIPOLE_QUAD = 3 } cg_mode;
 enum cg_what { CG_ENERGY = 1, CG_FORCE = 2, CG_FIELD = 4, CG_POTENTIAL = 8 };
 enum cg_precision { CG_FP64 = 0, CG_FP32 = 1 }; /* CG_FP32: fp32 pair arithmetic, fp64 positions/accumulators */
 
@@ -183,6 +187,11 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs);
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,
                    double *scalars);
 
+/* Quadrupole tensors of the current system for CG_MODE_MULTIPOLE_QUAD: quad[n][9], row-major 3x3 per particle, not
+ * necessarily symmetric or traceless (reference mat33 arguments).  Call after every cg_set_system* (which clears them);
+ * NULL clears.  The _device form keeps the caller's device pointer (zero copy). */
+int cg_set_quadrupoles(cg_handle *h, const double *quad);
+int cg_set_quadrupoles_device(cg_handle *h, const double *quad);
 /* O(N) terms of the current system, per particle as the reference's scheme functions give them
  * (core.hpp:124-145, 809-842): out[0] = sum_i self_energy({z_i^2, |mu_i|^2}), out[1] = neutralization_energy(charges,
  * box volume) (0 for an open system), out[2] = sum_i z_i; self_field[3n] (may be NULL) = self_field({0, mu_i}).

@@ -34,6 +34,8 @@ class BatchedEvaluator {
 
     cg_handle *handle() const { return h_; }
     void set_stream(void *cuda_stream) { check(cg_set_stream(h_, cuda_stream), "cg_set_stream"); }
+    // quad[n][9]: row-major 3x3 tensors for CG_MODE_MULTIPOLE_QUAD; call after set_system
+    void set_quadrupoles(const double *quad) { check(cg_set_quadrupoles(h_, quad), "cg_set_quadrupoles"); }
     // evaluate on `source`'s system (same cut-off): one upload + sort per configuration for several schemes
     void share_system(BatchedEvaluator &source) { check(cg_share_system(h_, source.h_), "cg_share_system"); }
     void set_shard(int rank, int nranks) { check(cg_set_shard(h_, rank, nranks), "cg_set_shard"); }

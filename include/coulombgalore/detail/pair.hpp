@@ -18,7 +18,7 @@ namespace CoulombGalore {
 namespace detail {
 
 enum { kWhatEnergy = 1, kWhatForce = 2, kWhatField = 4, kWhatPotential = 8 };
-enum { kModeIon = 0, kModeDipole = 1, kModeMultipole = 2 };
+enum { kModeIon = 0, kModeDipole = 1, kModeMultipole = 2, kModeMultipoleQuad = 3 };
 
 struct CoreParams {
     double inverse_cutoff, cutoff_squared, kappa; // core.hpp:116-118
@@ -26,7 +26,8 @@ struct CoreParams {
 
 // highest S-derivative a (mode, what) combination needs
 constexpr int derivatives_needed(int mode, int what) {
-    return mode == kModeIon ? ((what & (kWhatForce | kWhatField)) ? 1 : 0)
+    return mode == kModeMultipoleQuad ? ((what & (kWhatForce | kWhatField)) ? 3 : 2) // quadrupole field / force need r3corr
+           : mode == kModeIon ? ((what & (kWhatForce | kWhatField)) ? 1 : 0)
                             : ((what & kWhatForce) ? 3 : ((what & (kWhatField | kWhatEnergy)) ? 2 : 1));
 }
 
@@ -81,13 +82,24 @@ template <class T> struct AccumT {
 };
 typedef AccumT<double> Accum;
 
+// A quadrupole tensor Q as the pair formulas use it: only r^T Q r, (Q + Q^T) r and trace(Q) occur
+// (core.hpp:320-336, 412-436, 603-609, 767-773), so the symmetrised S = Q + Q^T and the trace are stored.
+template <class T> struct QuadT {
+    T xx, yy, zz, tr; // S_xx, S_yy, S_zz, trace(Q)
+    T xy, xz, yz;     // S_xy, S_xz, S_yz
+};
+template <class T> CG_HD Vec3T<T> quad_times(const QuadT<T> &s, const Vec3T<T> &d) { // (Q + Q^T) d
+    return {s.xx * d.x + s.xy * d.y + s.xz * d.z, s.xy * d.x + s.yy * d.y + s.yz * d.z, s.xz * d.x + s.yz * d.y + s.zz * d.z};
+}
+
 // One in-cutoff ordered pair (i <- j), d = r_i - r_j, r2 = |d|^2 < cutoff^2 already established by the caller.
 // Conventions: SURVEY.md 8b / oracle/harness.hpp.
 // `pass` = the pair is inside the cut-off.  The kernels evaluate branch-free (the radial arithmetic must then stay
 // finite for rejected / absent pairs): every contribution carries a scalar factor that is zeroed by a select.
 template <class F, bool YUK, int MODE, int WHAT, class T = double>
 CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const Vec3T<T> &d, T r2, T zi, T zj,
-                           const Vec3T<T> &mui, const Vec3T<T> &muj, AccumT<T> &acc, bool pass = true) {
+                           const Vec3T<T> &mui, const Vec3T<T> &muj, AccumT<T> &acc, bool pass = true,
+                           const QuadT<T> *quadi = nullptr, const QuadT<T> *quadj = nullptr) {
     constexpr int ND = derivatives_needed(MODE, WHAT);
     constexpr bool kAngcorOnly = F::kHasAngcor && !YUK && MODE == kModeIon && (WHAT & (kWhatEnergy | kWhatPotential)) == 0;
     const RadialT<T> R = radial_terms<F, YUK, ND, kAngcorOnly, T>(f, cp, r2, tab);
@@ -178,6 +190,48 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, 
             acc.Fx += cd * d.x + ci * mui.x + cj * muj.x;
             acc.Fy += cd * d.y + ci * mui.y + cj * muj.y;
             acc.Fz += cd * d.z + ci * mui.z + cj * muj.z;
+        }
+    }
+    if (MODE == kModeMultipoleQuad) {
+        // the ion-quadrupole terms of quadrupole_potential :320-336, multipole_field :477-481, multipole_multipole_energy
+        // :603-609 and multipole_multipole_force :767-773 (A = i, B = j, r = -d).  With qf = rhat^T Q rhat:
+        //   potential   1/2 ((3 qf_j - tr_j) totcor + tr_j unicor) e^{-kr} / r^3
+        //   field       1/2 ((3 (5 qf_j - tr_j) totcor + qf_j r3corr) d - 3 totcor S_j d) e^{-kr} / r^5
+        //   energy      z_i * (potential term of j) + z_j * (potential term of i)
+        //   force       1/2 (z_i (3 (5 qf_j - tr_j) totcor + qf_j r3corr) - z_j (3 (5 qf_i - tr_i) totcor + qf_i r3corr)) d e^{-kr} / r^5
+        //               + 3/2 totcor (z_j S_i d - z_i S_j d) e^{-kr} / r^5
+        const QuadT<T> &Qi = *quadi, &Qj = *quadj;
+        const Vec3T<T> sdj = quad_times(Qj, d);
+        const T half = T(0.5);
+        const T qfj = half * dot(d, sdj) * rinv2;
+        const T e5 = ek3 * rinv2; // exp(-kr) / r^5
+        if (WHAT & (kWhatPotential | kWhatEnergy)) {
+            const T pj = half * ((T(3) * qfj - Qj.tr) * R.totcor + Qj.tr * R.unicor) * ek3;
+            if (WHAT & kWhatPotential) acc.phi += pj;
+            if (WHAT & kWhatEnergy) {
+                const T qfi = half * dot(d, quad_times(Qi, d)) * rinv2;
+                acc.U += zi * pj + zj * half * ((T(3) * qfi - Qi.tr) * R.totcor + Qi.tr * R.unicor) * ek3;
+            }
+        }
+        if (WHAT & (kWhatField | kWhatForce)) {
+            const T t3 = T(3) * R.totcor;
+            const T gj = t3 * (T(5) * qfj - Qj.tr) + qfj * R.r3corr;
+            if (WHAT & kWhatField) {
+                const T cd = half * gj * e5, cs = -half * t3 * e5;
+                acc.Ex += cd * d.x + cs * sdj.x;
+                acc.Ey += cd * d.y + cs * sdj.y;
+                acc.Ez += cd * d.z + cs * sdj.z;
+            }
+            if (WHAT & kWhatForce) {
+                const Vec3T<T> sdi = quad_times(Qi, d);
+                const T qfi = half * dot(d, sdi) * rinv2;
+                const T gi = t3 * (T(5) * qfi - Qi.tr) + qfi * R.r3corr;
+                const T cd = half * (zi * gj - zj * gi) * e5;
+                const T ci = half * t3 * zj * e5, cj = -half * t3 * zi * e5;
+                acc.Fx += cd * d.x + ci * sdi.x + cj * sdj.x;
+                acc.Fy += cd * d.y + ci * sdi.y + cj * sdj.y;
+                acc.Fz += cd * d.z + ci * sdi.z + cj * sdj.z;
+            }
         }
     }
 }

@@ -99,6 +99,15 @@ int cgo_batched(void *handle, int64_t N, const double *x, const double *y, const
                 double *force, double *field, double *potential, double *energy_i, double *force_scale,
                 double *field_scale, double *potential_scale, double *totals);
 
+/* cgo_batched in multipole mode with quadrupole tensors quad[N][9] (row-major, not necessarily symmetric or traceless):
+ * potential += quadrupole_potential(quad_j, d); field = multipole_field(z_j, mu_j, quad_j, d); energy / force =
+ * multipole_multipole_energy / _force(z_i, z_j, mu_i, mu_j, quad_i, quad_j, -d)  (core.hpp:320, 457, 581, 737). */
+int cgo_batched_quad(void *handle, int64_t N, const double *x, const double *y, const double *z, const double *q,
+                     const double *mux, const double *muy, const double *muz, const double *quad, const double *box,
+                     int32_t pbc, int32_t what, int64_t i_begin, int64_t i_end, int32_t nthreads, int32_t want_scales,
+                     double *force, double *field, double *potential, double *energy_i, double *force_scale,
+                     double *field_scale, double *potential_scale, double *totals);
+
 /*
  * O(N) terms of a configuration, per particle through the scheme's own functions (reference core.hpp:794, 809-842):
  * scalars[0] = sum_i self_energy({z_i^2, |mu_i|^2}), scalars[1] = sum of the absolute terms (tolerance scale),

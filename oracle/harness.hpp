@@ -64,6 +64,7 @@ inline void generate(int32_t n, double a, uint64_t seed, double *x, double *y, d
 struct Batch {
     int64_t N;
     const double *x, *y, *z, *q, *mux, *muy, *muz;
+    const double *quad; // [N][9] row-major quadrupole tensors (multipole mode only), or null = zero quadrupoles
     double box[3];
     int pbc, mode, what;
     int64_t i_begin, i_end;
@@ -288,6 +289,7 @@ template <class T, class VEC, class MAT> struct Impl : Iface {
                             const double zj = b.q ? b.q[j] : 0.0;
                             const VEC muj = b.mux ? VEC(b.mux[j], b.muy[j], b.muz[j]) : VEC(0, 0, 0);
                             const VEC md = -d; // r_j - r_i
+                            const MAT quadi = b.quad ? mat(b.quad + 9 * i) : zeroquad, quadj = b.quad ? mat(b.quad + 9 * j) : zeroquad;
                             if (b.mode == CGO_MODE_ION) {
                                 const double r1 = std::sqrt(r2);
                                 if (b.what & CGO_POTENTIAL) {
@@ -333,22 +335,23 @@ template <class T, class VEC, class MAT> struct Impl : Iface {
                                 }
                             } else {
                                 if (b.what & CGO_POTENTIAL) {
-                                    const double t = pot.ion_potential(zj, std::sqrt(r2)) + pot.dipole_potential(muj, d);
+                                    const double t = pot.ion_potential(zj, std::sqrt(r2)) + pot.dipole_potential(muj, d) +
+                                                     (b.quad ? pot.quadrupole_potential(quadj, d) : 0.0);
                                     phi += t;
                                     ps += std::fabs(t);
                                 }
                                 if (b.what & CGO_FIELD) {
-                                    const VEC t = pot.multipole_field(zj, muj, zeroquad, d);
+                                    const VEC t = pot.multipole_field(zj, muj, quadj, d);
                                     for (int a = 0; a < 3; a++) E[a] += t[a];
                                     if (b.want_scales) Es += norm3(t);
                                 }
                                 if (b.what & CGO_FORCE) {
-                                    const VEC t = pot.multipole_multipole_force(zi, zj, mui, muj, zeroquad, zeroquad, md);
+                                    const VEC t = pot.multipole_multipole_force(zi, zj, mui, muj, quadi, quadj, md);
                                     for (int a = 0; a < 3; a++) F[a] += t[a];
                                     if (b.want_scales) Fs += norm3(t);
                                 }
                                 if (b.what & CGO_ENERGY) {
-                                    const double t = pot.multipole_multipole_energy(zi, zj, mui, muj, zeroquad, zeroquad, md);
+                                    const double t = pot.multipole_multipole_energy(zi, zj, mui, muj, quadi, quadj, md);
                                     u += t;
                                     uabs += std::fabs(t);
                                 }
@@ -418,8 +421,17 @@ Iface *make(const cgo_params &p); // throws on invalid parameters
                     int32_t mode, int32_t what, int64_t i0, int64_t i1, int32_t nthr, int32_t scales,              \
                     double *force, double *field, double *pot, double *en, double *fs, double *es, double *ps,     \
                     double *totals) {                                                                              \
-        cgo::Batch b{N, x, y, z, q, mx, my, mz, {box[0], box[1], box[2]}, pbc, mode, what, i0, i1, nthr, scales,    \
-                     force, field, pot, en, fs, es, ps, totals};                                                   \
+        cgo::Batch b{N, x, y, z, q, mx, my, mz, nullptr, {box[0], box[1], box[2]}, pbc, mode, what, i0, i1, nthr,   \
+                     scales, force, field, pot, en, fs, es, ps, totals};                                           \
+        return static_cast<cgo::Iface *>(h)->batched(b);                                                           \
+    }                                                                                                              \
+    int cgo_batched_quad(void *h, int64_t N, const double *x, const double *y, const double *z, const double *q,  \
+                         const double *mx, const double *my, const double *mz, const double *quad,                 \
+                         const double *box, int32_t pbc, int32_t what, int64_t i0, int64_t i1, int32_t nthr,       \
+                         int32_t scales, double *force, double *field, double *pot, double *en, double *fs,        \
+                         double *es, double *ps, double *totals) {                                                 \
+        cgo::Batch b{N, x, y, z, q, mx, my, mz, quad, {box[0], box[1], box[2]}, pbc, CGO_MODE_MULTIPOLE, what, i0,  \
+                     i1, nthr, scales, force, field, pot, en, fs, es, ps, totals};                                 \
         return static_cast<cgo::Iface *>(h)->batched(b);                                                           \
     }                                                                                                              \
     }

@@ -72,6 +72,8 @@ def load(kind="best"):
     lib.cgo_generate.restype = None
     lib.cgo_batched.argtypes = ([C.c_void_p, C.c_int64] + [_dp] * 7 + [_dp, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_int64, C.c_int64, C.c_int32, C.c_int32] + [_dp] * 8)
+    lib.cgo_batched_quad.argtypes = ([C.c_void_p, C.c_int64] + [_dp] * 8 + [_dp, C.c_int32, C.c_int32,
+                                     C.c_int64, C.c_int64, C.c_int32, C.c_int32] + [_dp] * 8)
     _libs[kind] = lib
     return lib
 
@@ -133,7 +135,8 @@ class Scheme:
             out.append((r2, c))
         return out
 
-    def batched(self, x, y, z, q, mu, box, pbc, mode, what, i_begin=0, i_end=None, nthreads=0, scales=True):
+    def batched(self, x, y, z, q, mu, box, pbc, mode, what, i_begin=0, i_end=None, nthreads=0, scales=True, quad=None):
+        """quad: optional (N, 3, 3) / (N, 9) quadrupole tensors; multipole mode only (core.hpp:320, 457, 581, 737)."""
         N = x.size
         i_end = N if i_end is None else i_end
         n = i_end - i_begin
@@ -148,9 +151,17 @@ class Scheme:
         tot = np.zeros(3)
         boxa = np.ascontiguousarray(box, dtype=np.float64)
         mx, my, mz = (None, None, None) if mu is None else mu
-        rc = self.lib.cgo_batched(self.h, N, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz),
-                                  _ptr(boxa), int(pbc), mode, what, i_begin, i_end, nthreads, int(scales), _ptr(f),
-                                  _ptr(e), _ptr(p), _ptr(u), _ptr(fs), _ptr(es), _ptr(ps), _ptr(tot))
+        if quad is not None:
+            if mode not in (MODE_MULTIPOLE, 3):
+                raise ValueError("quadrupoles need the multipole mode")
+            qd = np.ascontiguousarray(quad, dtype=np.float64).reshape(N, 9)
+            rc = self.lib.cgo_batched_quad(self.h, N, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz), _ptr(qd),
+                                           _ptr(boxa), int(pbc), what, i_begin, i_end, nthreads, int(scales), _ptr(f),
+                                           _ptr(e), _ptr(p), _ptr(u), _ptr(fs), _ptr(es), _ptr(ps), _ptr(tot))
+        else:
+            rc = self.lib.cgo_batched(self.h, N, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz),
+                                      _ptr(boxa), int(pbc), mode, what, i_begin, i_end, nthreads, int(scales), _ptr(f),
+                                      _ptr(e), _ptr(p), _ptr(u), _ptr(fs), _ptr(es), _ptr(ps), _ptr(tot))
         if rc != 0:
             raise RuntimeError("cgo_batched failed rc=%d" % rc)
         res.update(force=f, field=e, potential=p, energy_i=u, force_scale=fs, field_scale=es, potential_scale=ps,

@@ -12,6 +12,7 @@ reference's own double-precision outputs:
   tab/<scheme>/<k>/..   Andrea tables of the splined schemes (knots, coefficients)
   batch/<case>/..       batched loop (oracle/harness.hpp) on a 6^3 lattice: force, field, potential, energy, pairs
   lattice/..            generator output (splitmix64 rule of SURVEY.md 8d)
+  batch_quad/<case>/..  the same loop in multipole mode with seeded, non-symmetric quadrupole tensors (quad_inputs)
   self/<scheme>/..      O(N) terms on the lattice with a non-neutral charge set (self_inputs): scalars = sum of
                         self_energy, its absolute sum, neutralization_energy (V = 18^3), charge sum; self_field per
                         particle; self/torque = dipole_torque(mu_i, E_i) for the seeded field of self_inputs
@@ -41,6 +42,11 @@ def pair_inputs(cutoff):
         out.append((float(rng.uniform(-2, 2)), float(rng.uniform(-2, 2)), rng.normal(size=3), rng.normal(size=3), r,
                     rng.normal(size=(3, 3)), rng.normal(size=(3, 3))))
     return out
+
+
+def quad_inputs(n):
+    """Seeded general (non-symmetric, not traceless) 3x3 quadrupole tensors."""
+    return np.random.default_rng(4242).normal(size=(n, 3, 3))
 
 
 def self_inputs(q):
@@ -83,6 +89,13 @@ def main():
         # cut-offs of the zoo (10-14) exceed L/2 = 9: the loop then sums the nearest images, which is what the product does too
         r = s.batched(x, y, z, ch, mu, [L] * 3, pbc, mode, ALL)
         k = "batch/%s_mode%d_pbc%d/" % (name, mode, int(pbc))
+        for f in ("force", "field", "potential", "force_scale", "field_scale", "potential_scale"):
+            d[k + f] = r[f]
+        d[k + "scalars"] = np.array([r["energy"], r["energy_abs"], float(r["pairs"])])
+    quad = quad_inputs(x.size)
+    for name, pbc in (("wolf", True), ("poisson33_yukawa", True), ("ewald_screened", True), ("qpotential3", False), ("plain", False)):
+        r = O.Scheme(oracle_params(name), "ref").batched(x, y, z, ch, mu, [18.0] * 3, pbc, O.MODE_MULTIPOLE, ALL, quad=quad)
+        k = "batch_quad/%s_pbc%d/" % (name, int(pbc))
         for f in ("force", "field", "potential", "force_scale", "field_scale", "potential_scale"):
             d[k + f] = r[f]
         d[k + "scalars"] = np.array([r["energy"], r["energy_abs"], float(r["pairs"])])

@@ -52,16 +52,18 @@ def compare(gpu, ref, what, tol=TOL):
     return out
 
 
-def run_case(pot, osch, x, y, z, q, mu, box, pbc, mode, what, shard=None, precision=None):
+def run_case(pot, osch, x, y, z, q, mu, box, pbc, mode, what, shard=None, precision=None, quad=None):
     ev = cg.BatchedEvaluator(pot)
     if shard:
         ev.set_shard(*shard)
     if precision:
         ev.set_precision(precision)
     ev.set_system(x, y, z, q, mu, box, pbc)
+    if quad is not None:
+        ev.set_quadrupoles(quad)
     g = ev.eval(mode, what)
     g["counters"] = ev.counters()
     g["timings"] = ev.timings()
     ev.close()
-    r = osch.batched(x, y, z, q, mu, box, pbc, mode, what)
+    r = osch.batched(x, y, z, q, mu, box, pbc, cg.MODE_MULTIPOLE if quad is not None else mode, what, quad=quad)
     return g, r

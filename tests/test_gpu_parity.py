@@ -76,6 +76,69 @@ def test_every_scheme_every_mode(name, mode, oracle_kind):
     assert_parity(compare(g, r, ALL))
 
 
+@pytest.mark.parametrize("name", sorted(zoo().keys()))
+@pytest.mark.parametrize("what", [cg.ENERGY | cg.FORCE, ALL])
+def test_every_scheme_with_quadrupoles(name, what, oracle_kind):
+    """quadrupole_potential, the quadrupole branches of multipole_field and of
+    multipole_multipole_energy / _force (core.hpp:320, 477-481, 603-609, 767-773) with general 3x3 tensors."""
+    x, y, z, q, mu = lattice(10, 3.0, 77, oracle_kind)
+    quad = np.random.default_rng(5).normal(size=(x.size, 3, 3))
+    mk, p = zoo()[name]
+    pot = mk()
+    pbc = pot.cutoff <= 30.0
+    g, r = run_case(pot, O.Scheme(p, oracle_kind), x, y, z, q, mu, [30.0] * 3, pbc, cg.MODE_MULTIPOLE_QUAD, what, quad=quad)
+    assert_parity(compare(g, r, what))
+
+
+def test_quadrupole_mode_properties_and_golden(oracle_kind):
+    """Zero tensors reproduce CG_MODE_MULTIPOLE, only the symmetric part and the trace matter, quadrupoles are cleared
+    by set_system, borrowers see the lender's tensors; and the committed reference run."""
+    import os
+    from golden.make_golden import quad_inputs
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+    lat = gold["lattice/n6_a3_seed31337"]
+    x, y, z, q, mu = lat[0].copy(), lat[1].copy(), lat[2].copy(), lat[3].copy(), (lat[4].copy(), lat[5].copy(), lat[6].copy())
+    quad = quad_inputs(x.size)
+    for key in [k for k in gold.files if k.startswith("batch_quad/") and k.endswith("/scalars")]:
+        case = key.split("/")[1]
+        name, pbc = case.rsplit("_pbc", 1)[0], case.endswith("pbc1")
+        ev = cg.BatchedEvaluator(zoo()[name][0]())
+        ev.set_system(x, y, z, q, mu, [18.0] * 3, pbc)
+        ev.set_quadrupoles(quad)
+        g = ev.eval(cg.MODE_MULTIPOLE_QUAD, ALL)
+        sc = gold[key]
+        ref = dict(energy=sc[0], energy_abs=sc[1], pairs=int(sc[2]))
+        for f in ("force", "field", "potential", "force_scale", "field_scale", "potential_scale"):
+            ref[f] = gold["batch_quad/%s/%s" % (case, f)]
+        assert_parity(compare(g, ref, ALL))
+        ev.close()
+    ev = cg.BatchedEvaluator(cg.Wolf(12.0, 0.25))
+    ev.set_system(x, y, z, q, mu, [18.0] * 3, True)
+    base = ev.eval(cg.MODE_MULTIPOLE, ALL)
+    with pytest.raises(cg.CgError):
+        ev.eval(cg.MODE_MULTIPOLE_QUAD, ALL)  # no tensors given
+    ev.set_quadrupoles(np.zeros((x.size, 9)))
+    zero = ev.eval(cg.MODE_MULTIPOLE_QUAD, ALL)
+    assert zero["pairs"] == base["pairs"] and abs(zero["energy"] - base["energy"]) <= 1e-13 * abs(base["energy"])
+    assert np.max(np.abs(zero["force"] - base["force"])) <= 1e-13 * np.max(np.abs(base["force"]))
+    ev.set_quadrupoles(quad)
+    full = ev.eval(cg.MODE_MULTIPOLE_QUAD, ALL)
+    bor = cg.BatchedEvaluator(cg.Fennell(12.0, 0.25))
+    bor.share_system(ev)
+    own = cg.BatchedEvaluator(cg.Fennell(12.0, 0.25))
+    own.set_system(x, y, z, q, mu, [18.0] * 3, True)
+    own.set_quadrupoles(quad)
+    assert np.array_equal(bor.eval(cg.MODE_MULTIPOLE_QUAD, ALL)["force"], own.eval(cg.MODE_MULTIPOLE_QUAD, ALL)["force"])
+    ev.set_quadrupoles(0.5 * (quad + quad.transpose(0, 2, 1)))
+    sym = ev.eval(cg.MODE_MULTIPOLE_QUAD, ALL)
+    assert np.max(np.abs(sym["force"] - full["force"])) <= 1e-12 * np.max(np.abs(full["force"]))
+    ev.set_system(x, y, z, q, mu, [18.0] * 3, True)
+    with pytest.raises(cg.CgError):
+        ev.eval(cg.MODE_MULTIPOLE_QUAD, ALL)  # set_system cleared them
+    for e in (ev, bor, own):
+        e.close()
+
+
 @pytest.mark.parametrize("name", ["wolf", "ewald_screened", "qpotential3", "plain_yukawa", "reactionfield"])
 def test_splined_schemes(name, oracle_kind):
     pot, osch = splined_pair(name, oracle_kind)
