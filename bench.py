@@ -138,8 +138,8 @@ def main():
     workload = ("configs[1]: Wolf(12,0.25) + Fennell(12,0.25) ion-ion forces, cell list, N=%d^3=%d charges, a=3, periodic, "
                 "R_c=12, fp64; step = spatial sort of the configuration + one Wolf + one Fennell evaluation on it" % (n_side, N))
     config = {"workload": workload, "n_particles": N, "cutoff": CFG["cutoff"], "l2_policy": "L2 flushed (512 MiB write) before every timed step",
-              "parallelism": ("i-group sharding x%d, exchange of the SoA inputs by a pull kernel over NVLink peer memory "
-                              "(NCCL all-gather if CUDA IPC is unavailable or CG_EXCHANGE=nccl)" % world) if world > 1 else "single GPU"}
+              "parallelism": ("i-group sharding x%d; exchange: every rank pulls the particles of its window over NVLink peer memory "
+                              "(CG_EXCHANGE=peer: all particles; =nccl or no CUDA IPC: NCCL all-gather)" % world) if world > 1 else "single GPU"}
 
     from oracle import oracle as O
     okind = "ref" if O.available("ref") else "port"
@@ -198,27 +198,48 @@ def main():
     full = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
     evs["wolf"].generate_lattice_device(n_side, CFG["a"], CFG["seed"], full[0], full[1], full[2], full[3])
     torch.cuda.synchronize()
-    from coulombgalore_b200.distributed import PeerExchange, ShardedStep, owned_range
+    from coulombgalore_b200.distributed import HaloExchange, PeerExchange, ShardedStep, owned_range
     lo, hi = owned_range(N, rank, world)
     owned = [t[lo:hi].clone() for t in full]  # this rank's particles
-    exchange = None
-    if world > 1:  # the exchange step: this repo's pull kernel over peer memory, or the collective library's all-gather
-        exchange = ShardedStep(N, 4, dev) if os.environ.get("CG_EXCHANGE") == "nccl" else PeerExchange.create(evs["wolf"], N, 4, dev)
-        if isinstance(exchange, PeerExchange):
+    exchange = halo = None
+    if world > 1:
+        # the exchange step.  halo (default): every rank pulls, over NVLink peer memory, only the particles of its window;
+        # peer: it pulls all of them (both are this repo's kernels); nccl: the collective library's all-gather
+        xmode = os.environ.get("CG_EXCHANGE", "halo")
+        if xmode == "halo":
+            try:
+                halo = HaloExchange(evs["wolf"], N, box, 4, dev)
+            except Exception as ex_:  # noqa: BLE001 -- no CUDA IPC here: use the collective library
+                halo, xmode, halo_reason = None, "nccl", "%s: %s" % (type(ex_).__name__, ex_)
+            ok = torch.tensor([0.0 if halo is None else 1.0], device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if ok.item() < 1.0 and halo is not None:
+                halo.close()
+                halo, xmode = None, "nccl"
+        if halo is None:
+            exchange = ShardedStep(N, 4, dev) if xmode == "nccl" else PeerExchange.create(evs["wolf"], N, 4, dev)
+        if halo is not None or isinstance(exchange, PeerExchange):
             owned = torch.stack(owned)
-    gathered = exchange.full if world > 1 else full
+    gathered = exchange.full if exchange is not None else full
     force = torch.empty((N, 3), dtype=torch.float64, device=dev)
     scal = {k: torch.zeros(2, dtype=torch.float64, device=dev) for k in evs}
     flush_buf = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     def step_device():
         launches = 0
-        if world > 1:
-            exchange.gather(owned)  # positions + charges of every rank
-            launches += 2 if isinstance(exchange, PeerExchange) else 0  # publish copy + cg_peer_gather (NCCL's kernels are not ours)
-        evs["wolf"].set_system_device(gathered[0], gathered[1], gathered[2], gathered[3], None, box, True)
+        fo = force
+        if halo is not None:
+            sub, ids, n_out = halo.gather(owned)  # positions + charges of the particles this rank's window holds
+            halo.set_system(evs["wolf"], sub, has_q=True, has_mu=False)
+            fo = force[: sub[0].numel()]
+            launches += 4  # cg_halo_publish (3 kernels) + cg_halo_pull
+        else:
+            if world > 1:
+                exchange.gather(owned)  # positions + charges of every rank
+                launches += 2 if isinstance(exchange, PeerExchange) else 0  # publish copy + cg_peer_gather (NCCL's kernels are not ours)
+            evs["wolf"].set_system_device(gathered[0], gathered[1], gathered[2], gathered[3], None, box, True)
         for name, ev in evs.items():  # wolf first: it owns (bins, sorts) the system fennell borrows
-            ev.eval_device(cg.MODE_ION, cg.FORCE, force=force, scalars=scal[name])
+            ev.eval_device(cg.MODE_ION, cg.FORCE, force=fo, scalars=scal[name])
             launches += ev.counters()["launches"]
         return launches
 
@@ -297,10 +318,15 @@ def main():
 
     exchange_kind = None
     if world > 1:
-        exchange_kind = "peer-memory pull kernel (cg_peer_gather)" if isinstance(exchange, PeerExchange) else \
-            "NCCL all-gather (%s)" % (getattr(exchange, "fallback_reason", None) or "CG_EXCHANGE=nccl")
-        if isinstance(exchange, PeerExchange):
-            exchange.close()
+        if halo is not None:
+            exchange_kind = "halo pull over peer memory (cg_halo_publish + cg_halo_pull): %d of %d particles received by rank %d" % (
+                halo.check_overflow(), N, rank)
+            halo.close()
+        else:
+            exchange_kind = "peer-memory pull kernel (cg_peer_gather)" if isinstance(exchange, PeerExchange) else \
+                "NCCL all-gather (%s)" % (getattr(exchange, "fallback_reason", None) or "CG_EXCHANGE=nccl")
+            if isinstance(exchange, PeerExchange):
+                exchange.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

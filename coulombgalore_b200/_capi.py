@@ -100,6 +100,12 @@ def _load():
         "cg_peer_open": [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)],
         "cg_peer_close": [C.c_void_p],
         "cg_peer_gather": [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p)],
+        "cg_set_grid_count": [H, C.c_int64],
+        "cg_set_count_device": [H, C.c_void_p],
+        "cg_shard_window": [H, _dp, C.c_int, C.c_int, C.c_int64, _dp],
+        "cg_halo_publish": [H, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_void_p), _dp, _dp, C.c_double, C.c_void_p],
+        "cg_halo_pull": [H, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.c_int, C.POINTER(C.c_void_p), C.c_int64,
+                         C.c_void_p],
         "cg_generate_lattice_device": [H, C.c_int32, C.c_double, C.c_uint64] + [C.c_void_p] * 7,
         "cg_fp64_peak_probe": [H, _dp, _dp],
     }
@@ -107,6 +113,8 @@ def _load():
         fn = getattr(lib, name)  # AttributeError here == the library does not export what the header declares
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.cg_halo_block_bytes.argtypes = [C.c_int, C.c_int, C.c_int64]
+    lib.cg_halo_block_bytes.restype = C.c_size_t
     lib.cg_spline_storage_doubles.argtypes = []
     lib.cg_spline_storage_doubles.restype = C.c_int64
     lib.cg_last_error.argtypes = [H]
@@ -125,7 +133,8 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
             "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_set_quadrupoles", "cg_set_quadrupoles_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",
-            "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
+            "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_set_grid_count", "cg_set_count_device", "cg_shard_window", "cg_halo_block_bytes", "cg_halo_publish",
+            "cg_halo_pull", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
 
 
 def check(rc, where, handle=None):

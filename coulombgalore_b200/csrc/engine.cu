@@ -95,6 +95,7 @@ static int functor_for(const cg_scheme_desc &d) {
 // ---------------------------------------------------------------------------------------------------------------
 struct SortParams {
     int n;
+    const int *n_dev; // when set: the number of valid particles (<= n) lives on the device (halo exchange)
     const double *x, *y, *z, *q, *mx, *my, *mz;
     const double *quad; // [n][9] row-major quadrupole tensors, or null
     double lo[3];     // lower corner of the primary region (0 for periodic boxes, min coordinate for open ones)
@@ -138,7 +139,7 @@ template <bool SCATTER>
 __global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int cap,
                            int *counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= sp.n) return;
+    if (p >= (sp.n_dev ? min(*sp.n_dev, sp.n) : sp.n)) return;
     int sx[3], cx[3], sy[3], cy[3], sz[3], cz[3];
     const int mx = images_1d(sp, 0, sp.x[p] - sp.lo[0], sx, cx);
     const int my = images_1d(sp, 1, sp.y[p] - sp.lo[1], sy, cy);
@@ -540,6 +541,128 @@ __global__ void peer_gather_kernel(const __grid_constant__ PeerGather g) {
     }
 }
 
+// ---- halo exchange: the owner sorts its particles into one segment per destination rank (those inside the destination's
+// z-window, periodic images included), the destination pulls only its segments.  Block layout (one per rank, peer-mapped):
+//   [0, 256) bytes : int counts[kMaxPeers]      particles of this owner destined to rank t
+//   then           : double seg[nranks][narrays][cap]   (cap = the owner's particle count)
+constexpr int kHaloThreads = 256;
+struct HaloPlan {
+    int nranks, narrays, n;          // n = owned particles
+    long long cap;
+    const double *src[kMaxPeerArrays]; // owned SoA arrays; src[zindex] is z
+    int zindex;
+    double zlo[kMaxPeers], zhi[kMaxPeers], period; // window of rank t: zlo <= z + k period < zhi for some k in {-1, 0, 1}
+    unsigned char *block;
+    int *block_counts;               // [nblocks][nranks] scratch, then exclusive block offsets
+};
+__device__ __forceinline__ unsigned halo_mask(const HaloPlan &hp, double z) {
+    unsigned m = 0;
+    for (int t = 0; t < hp.nranks; t++) {
+        const double lo = hp.zlo[t], hi = hp.zhi[t];
+        bool in = z >= lo && z < hi;
+        if (hp.period > 0.0) in = in || (z - hp.period >= lo && z - hp.period < hi) || (z + hp.period >= lo && z + hp.period < hi);
+        m |= in ? (1u << t) : 0u;
+    }
+    return m;
+}
+// pass 1: per block and destination, how many of the block's particles go there
+__global__ void halo_count_kernel(const __grid_constant__ HaloPlan hp) {
+    __shared__ int cnt[kMaxPeers];
+    if (threadIdx.x < kMaxPeers) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int p = blockIdx.x * kHaloThreads + threadIdx.x;
+    const unsigned m = p < hp.n ? halo_mask(hp, hp.src[hp.zindex][p]) : 0u;
+    for (int t = 0; t < hp.nranks; t++) {
+        const unsigned b = __ballot_sync(0xffffffffu, (m >> t) & 1u);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt[t], __popc(b)); // integer adds: order-independent
+    }
+    __syncthreads();
+    if (threadIdx.x < hp.nranks) hp.block_counts[blockIdx.x * hp.nranks + threadIdx.x] = cnt[threadIdx.x];
+}
+// pass 2 (one CTA per destination): exclusive scan over the blocks; the total goes to the header of the peer block
+__global__ void __launch_bounds__(1024) halo_scan_kernel(const __grid_constant__ HaloPlan hp, int nblocks) {
+    __shared__ int warp_sum[32];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = (nblocks + 1023) / 1024;
+    const int b0 = min(tid * chunk, nblocks), b1 = min(b0 + chunk, nblocks);
+    int sum = 0;
+    for (int b = b0; b < b1; b++) sum += hp.block_counts[b * hp.nranks + t];
+    int incl = sum; // inclusive scan of the per-thread sums: warp shuffles, then the warp totals
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = warp_sum[lane];
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, off);
+            if (lane >= off) w += v;
+        }
+        warp_sum[lane] = w;
+    }
+    __syncthreads();
+    int run = incl - sum + (warp > 0 ? warp_sum[warp - 1] : 0);
+    for (int b = b0; b < b1; b++) {
+        const int c = hp.block_counts[b * hp.nranks + t];
+        hp.block_counts[b * hp.nranks + t] = run;
+        run += c;
+    }
+    if (tid == 1023) reinterpret_cast<int *>(hp.block)[t] = warp_sum[31];
+}
+// pass 3: stable scatter (particle order is kept inside every segment -> bit-reproducible downstream)
+__global__ void halo_scatter_kernel(const __grid_constant__ HaloPlan hp) {
+    __shared__ int warp_cnt[kMaxPeers][kHaloThreads / 32];
+    const int p = blockIdx.x * kHaloThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = p < hp.n ? halo_mask(hp, hp.src[hp.zindex][p]) : 0u;
+    unsigned ball[kMaxPeers];
+    for (int t = 0; t < hp.nranks; t++) {
+        ball[t] = __ballot_sync(0xffffffffu, (m >> t) & 1u);
+        if (lane == 0) warp_cnt[t][warp] = __popc(ball[t]);
+    }
+    __syncthreads();
+    double *seg0 = reinterpret_cast<double *>(hp.block + 256);
+    for (int t = 0; t < hp.nranks; t++) {
+        if (!((m >> t) & 1u)) continue;
+        int pos = hp.block_counts[blockIdx.x * hp.nranks + t] + __popc(ball[t] & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; w++) pos += warp_cnt[t][w];
+        double *seg = seg0 + (long long)t * hp.narrays * hp.cap;
+        for (int a = 0; a < hp.narrays; a++) seg[(long long)a * hp.cap + pos] = hp.src[a][p];
+    }
+}
+
+struct HaloPull {
+    int nranks, narrays, rank;
+    const unsigned char *block[kMaxPeers];
+    long long cap[kMaxPeers]; // per source rank: its segment capacity (= its particle count)
+    double *dst[kMaxPeerArrays];
+    long long dst_cap;
+    int *n_out; // [0] particles received, [1] overflow flag
+};
+// grid: (chunks, narrays, nranks).  Every CTA reads the nranks counts from the peer headers (a few NVLink words).
+__global__ void halo_pull_kernel(const __grid_constant__ HaloPull g) {
+    const int a = blockIdx.y, r = blockIdx.z;
+    long long off = 0;
+    int mine = 0;
+    for (int s = 0; s < g.nranks; s++) {
+        const int c = reinterpret_cast<const int *>(g.block[s])[g.rank];
+        if (s < r) off += c;
+        if (s == r) mine = c;
+    }
+    if (a == 0 && r == g.nranks - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
+        g.n_out[0] = (int)min(off + mine, g.dst_cap);
+        g.n_out[1] = off + mine > g.dst_cap ? 1 : 0;
+    }
+    long long n = mine;
+    if (off + n > g.dst_cap) n = max(0LL, g.dst_cap - off);
+    const double *s = reinterpret_cast<const double *>(g.block[r] + 256) + ((long long)g.rank * g.narrays + a) * g.cap[r];
+    double *d = g.dst[a] + off;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) d[k] = s[k];
+}
+
 template <class T> struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;
@@ -580,6 +703,8 @@ struct cg_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     int precision = CG_FP64;
     int shard_rank = 0, shard_n = 1;
+    int64_t grid_count = 0;            // particle count for the cell-size heuristic (0: the system's own n)
+    const int *n_dev = nullptr;        // optional device-side particle count (<= n), cleared by cg_set_system*
     std::string err;
     // system
     int64_t n = 0;
@@ -602,7 +727,7 @@ struct cg_handle {
     DevBuf<unsigned long long> item_pairs;
     int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
     int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
-    DevBuf<int> d_counts;
+    DevBuf<int> d_counts, halo_counts;
     cudaEvent_t counts_ev = nullptr;
     bool counts_pending = false;
     // sync-free path: valid while (n, box, pbc, shard) are unchanged and the arrays sized by the last exact run still fit
@@ -795,6 +920,7 @@ int cg_destroy(cg_handle *h) {
     if (h->pair_done_ev) cudaEventDestroy(h->pair_done_ev);
     if (h->inputs_ev) cudaEventDestroy(h->inputs_ev);
     h->d_counts.release();
+    h->halo_counts.release();
     if (h->h_minmax) cudaFreeHost(h->h_minmax);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
     for (auto &e : h->ev)
@@ -869,6 +995,7 @@ static int set_system_common(cg_handle *h, int64_t n, const double *box, int pbc
         }
     }
     h->n = n;
+    h->n_dev = nullptr;
     h->in_quad = nullptr; // quadrupoles belong to one configuration: cg_set_quadrupoles* after every cg_set_system*
     h->have_system = true;
     h->sorted.valid = false; // borrowers must wait for this handle's next evaluation
@@ -910,6 +1037,60 @@ int cg_set_system_device(cg_handle *h, int64_t n, const double *x, const double 
     return CG_OK;
 }
 
+// ---- cell grid and shard window: a function of (cut-off, box, particle count, shard) only, so that every rank of a
+// multi-GPU run -- and the exchange step that decides which particles a rank needs -- derive the same layout ----
+static void layout_grid(double rc, bool pbc, const double ext[3], double n_grid, int shard_rank, int shard_n, SortParams &sp) {
+    // target cell edge: half the cut-off along x (the storage direction), but not so small that cells are nearly empty
+    // or the grid explodes (an unbounded cut-off, i.e. Plain, still gets cells of ~32 particles: they only provide the
+    // sorted order).  CG_CELL_DIV / CG_CELL_DIV_YZ: cells per cut-off along x / along y and z (tuning).
+    static const double cell_div = [] {
+        const char *e = std::getenv("CG_CELL_DIV");
+        const double v = e ? std::atof(e) : 2.0;
+        return (v >= 0.5 && v <= 8.0) ? v : 2.0;
+    }();
+    static const double cell_div_yz = [] {
+        const char *e = std::getenv("CG_CELL_DIV_YZ");
+        const double v = e ? std::atof(e) : 0.0;
+        return (v >= 0.5 && v <= 8.0) ? v : 0.0;
+    }();
+    const double vol = ext[0] * ext[1] * ext[2];
+    double cs0 = std::min(rc / cell_div, std::cbrt(32.0 * vol / n_grid));
+    cs0 = std::max(cs0, std::cbrt(2.0 * vol / n_grid)); // >= ~2 particles per cell on average
+    for (;;) {
+        double ncell = 1.0;
+        for (int d = 0; d < 3; d++) {
+            double target = cs0;
+            if (d > 0 && cell_div_yz > 0.0 && rc < 1e100) target = std::max(cs0 * cell_div / cell_div_yz, cs0 * 0.25);
+            int np = (int)std::min(4096.0, std::max(1.0, std::floor(ext[d] / target)));
+            sp.nprim[d] = np;
+            const double cs = ext[d] / np;
+            sp.box[d] = ext[d];
+            sp.inv_cs[d] = 1.0 / cs;
+            sp.ghost[d] = pbc ? (int)std::ceil(rc / cs - 1e-9) : 0;
+            sp.gw[d] = sp.ghost[d] * cs;
+            sp.ntot[d] = np + 2 * sp.ghost[d];
+            ncell *= sp.ntot[d];
+        }
+        if (ncell <= 48e6) break;
+        cs0 *= 1.26;
+    }
+    // ---- shard: a contiguous block of primary cell rows (z-major), plus the cell layers within one cut-off of it ----
+    {
+        const int nrows_all = sp.nprim[1] * sp.nprim[2];
+        sp.row0 = (int)((int64_t)nrows_all * shard_rank / shard_n);
+        sp.row1 = (int)((int64_t)nrows_all * (shard_rank + 1) / shard_n);
+        sp.z0 = 0;
+        sp.nzl = sp.ntot[2];
+        if (shard_n > 1 && sp.row1 > sp.row0) {
+            const int halo = (int)std::ceil(rc * sp.inv_cs[2] - 1e-9) + 1; // +1: fp32 slack of the kernel's cell ranges
+            const int lz0 = sp.row0 / sp.nprim[1] + sp.ghost[2], lz1 = (sp.row1 - 1) / sp.nprim[1] + sp.ghost[2];
+            const int za = std::max(0, lz0 - halo), zb = std::min(sp.ntot[2] - 1, lz1 + halo);
+            sp.z0 = za;
+            sp.nzl = zb - za + 1;
+        }
+    }
+}
+
 // ---- binning, spatial sort and i-groups of the handle's own system (steps 0-5); the result is described by h->sorted ----
 static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches_out) {
     cudaStream_t st = h->stream;
@@ -932,6 +1113,7 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     sp.my = h->in[5];
     sp.mz = h->in[6];
     sp.quad = h->in_quad;
+    sp.n_dev = h->n_dev;
     sp.pbc = h->pbc ? 1 : 0;
     double ext[3];
     if (h->pbc) {
@@ -957,55 +1139,7 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
             ext[d] *= (1.0 + 1e-12);
         }
     }
-    // target cell edge: half the cut-off along x (the storage direction), but not so small that cells are nearly empty
-    // or the grid explodes (an unbounded cut-off, i.e. Plain, still gets cells of ~32 particles: they only provide the
-    // sorted order).  CG_CELL_DIV / CG_CELL_DIV_YZ: cells per cut-off along x / along y and z (tuning).
-    static const double cell_div = [] {
-        const char *e = std::getenv("CG_CELL_DIV");
-        const double v = e ? std::atof(e) : 2.0;
-        return (v >= 0.5 && v <= 8.0) ? v : 2.0;
-    }();
-    static const double cell_div_yz = [] {
-        const char *e = std::getenv("CG_CELL_DIV_YZ");
-        const double v = e ? std::atof(e) : 0.0;
-        return (v >= 0.5 && v <= 8.0) ? v : 0.0;
-    }();
-    const double vol = ext[0] * ext[1] * ext[2];
-    double cs0 = std::min(rc / cell_div, std::cbrt(32.0 * vol / (double)n));
-    cs0 = std::max(cs0, std::cbrt(2.0 * vol / (double)n)); // >= ~2 particles per cell on average
-    for (;;) {
-        double ncell = 1.0;
-        for (int d = 0; d < 3; d++) {
-            double target = cs0;
-            if (d > 0 && cell_div_yz > 0.0 && rc < 1e100) target = std::max(cs0 * cell_div / cell_div_yz, cs0 * 0.25);
-            int np = (int)std::min(4096.0, std::max(1.0, std::floor(ext[d] / target)));
-            sp.nprim[d] = np;
-            const double cs = ext[d] / np;
-            sp.box[d] = ext[d];
-            sp.inv_cs[d] = 1.0 / cs;
-            sp.ghost[d] = h->pbc ? (int)std::ceil(rc / cs - 1e-9) : 0;
-            sp.gw[d] = sp.ghost[d] * cs;
-            sp.ntot[d] = np + 2 * sp.ghost[d];
-            ncell *= sp.ntot[d];
-        }
-        if (ncell <= 48e6) break;
-        cs0 *= 1.26;
-    }
-    // ---- shard: a contiguous block of primary cell rows (z-major), plus the cell layers within one cut-off of it ----
-    {
-        const int nrows_all = sp.nprim[1] * sp.nprim[2];
-        sp.row0 = (int)((int64_t)nrows_all * h->shard_rank / h->shard_n);
-        sp.row1 = (int)((int64_t)nrows_all * (h->shard_rank + 1) / h->shard_n);
-        sp.z0 = 0;
-        sp.nzl = sp.ntot[2];
-        if (h->shard_n > 1 && sp.row1 > sp.row0) {
-            const int halo = (int)std::ceil(rc * sp.inv_cs[2] - 1e-9) + 1; // +1: fp32 slack of the kernel's cell ranges
-            const int lz0 = sp.row0 / sp.nprim[1] + sp.ghost[2], lz1 = (sp.row1 - 1) / sp.nprim[1] + sp.ghost[2];
-            const int za = std::max(0, lz0 - halo), zb = std::min(sp.ntot[2] - 1, lz1 + halo);
-            sp.z0 = za;
-            sp.nzl = zb - za + 1;
-        }
-    }
+    layout_grid(rc, h->pbc, ext, h->grid_count > 0 ? (double)h->grid_count : (double)n, h->shard_rank, h->shard_n, sp);
     const int ncell = sp.ntot[0] * sp.ntot[1] * sp.nzl;
     const int nrows_prim = sp.row1 - sp.row0;
     S.ncell = ncell;
@@ -1625,6 +1759,102 @@ int cg_peer_gather(cg_handle *h, int nranks, const void *const *blocks, const in
     // enough CTAs in total to keep every NVLink direction busy, never more than the data needs
     const int per = (int)std::max<long long>(1, std::min<long long>((cmax / 2 + 255) / 256, std::max(1, 8 * sms / (nranks * narrays))));
     peer_gather_kernel<<<dim3((unsigned)per, (unsigned)narrays, (unsigned)nranks), 256, 0, h->stream>>>(g);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+// ---- halo exchange (spatial pull): see the kernels above and coulombgalore_b200.distributed.HaloExchange ----
+int cg_set_grid_count(cg_handle *h, int64_t n_global) {
+    if (!h || n_global < 0) return CG_ERR_INVALID;
+    h->grid_count = n_global;
+    h->fast.valid = false;
+    return CG_OK;
+}
+
+int cg_set_count_device(cg_handle *h, const int *n_dev) {
+    if (!h) return CG_ERR_INVALID;
+    h->n_dev = n_dev;
+    return CG_OK;
+}
+
+int cg_shard_window(cg_handle *h, const double *box, int rank, int nranks, int64_t n_global, double window[2]) {
+    if (!h || !box || !window || nranks < 1 || rank < 0 || rank >= nranks || n_global < 1) return CG_ERR_INVALID;
+    SortParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    const double ext[3] = {box[0], box[1], box[2]};
+    layout_grid(h->desc.cutoff, true, ext, (double)n_global, rank, nranks, sp);
+    const double cs = 1.0 / sp.inv_cs[2];
+    window[0] = (sp.z0 - sp.ghost[2]) * cs - 1e-6 * cs;
+    window[1] = (sp.z0 + sp.nzl - sp.ghost[2]) * cs + 1e-6 * cs;
+    return CG_OK;
+}
+
+size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count) {
+    return 256 + sizeof(double) * (size_t)nranks * (size_t)narrays * (size_t)std::max<int64_t>(count, 1);
+}
+
+int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned, const double *zlo,
+                    const double *zhi, double period, void *block) {
+    if (!h || !owned || !zlo || !zhi || !block || nranks < 1 || nranks > kMaxPeers || narrays < 1 || narrays > kMaxPeerArrays ||
+        zindex < 0 || zindex >= narrays || count < 0 || count > 0x7fffffff)
+        return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    HaloPlan hp;
+    std::memset(&hp, 0, sizeof(hp));
+    hp.nranks = nranks;
+    hp.narrays = narrays;
+    hp.n = (int)count;
+    hp.cap = std::max<int64_t>(count, 1);
+    hp.zindex = zindex;
+    hp.period = period;
+    for (int a = 0; a < narrays; a++) {
+        if (!owned[a]) return CG_ERR_INVALID;
+        hp.src[a] = owned[a];
+    }
+    for (int t = 0; t < nranks; t++) {
+        hp.zlo[t] = zlo[t];
+        hp.zhi[t] = zhi[t];
+    }
+    hp.block = static_cast<unsigned char *>(block);
+    const int nblocks = std::max(1, (int)((count + kHaloThreads - 1) / kHaloThreads));
+    CG_CUDA(h, h->halo_counts.ensure((size_t)nblocks * nranks));
+    hp.block_counts = h->halo_counts.p;
+    cudaStream_t st = h->stream;
+    halo_count_kernel<<<nblocks, kHaloThreads, 0, st>>>(hp);
+    halo_scan_kernel<<<nranks, 1024, 0, st>>>(hp, nblocks);
+    halo_scatter_kernel<<<nblocks, kHaloThreads, 0, st>>>(hp);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays, double *const *dst,
+                 int64_t dst_cap, int *n_out) {
+    if (!h || !blocks || !counts || !dst || !n_out || nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks || narrays < 1 ||
+        narrays > kMaxPeerArrays || dst_cap < 1)
+        return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    HaloPull g;
+    std::memset(&g, 0, sizeof(g));
+    g.nranks = nranks;
+    g.narrays = narrays;
+    g.rank = rank;
+    long long cmax = 1;
+    for (int r = 0; r < nranks; r++) {
+        if (!blocks[r]) return CG_ERR_INVALID;
+        g.block[r] = static_cast<const unsigned char *>(blocks[r]);
+        g.cap[r] = std::max<int64_t>(counts[r], 1);
+        cmax = std::max<long long>(cmax, counts[r]);
+    }
+    for (int a = 0; a < narrays; a++) {
+        if (!dst[a]) return CG_ERR_INVALID;
+        g.dst[a] = dst[a];
+    }
+    g.dst_cap = dst_cap;
+    g.n_out = n_out;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int per = (int)std::max<long long>(1, std::min<long long>((cmax + 255) / 256, std::max(1, 8 * sms / (nranks * narrays))));
+    halo_pull_kernel<<<dim3((unsigned)per, (unsigned)narrays, (unsigned)nranks), 256, 0, h->stream>>>(g);
     CG_CUDA(h, cudaGetLastError());
     return CG_OK;
 }

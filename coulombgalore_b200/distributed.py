@@ -169,3 +169,115 @@ class PeerExchange(ShardedStep):
         for p in self.own_ptr:
             self.lib.cg_peer_free(p)
         self.own_ptr = []
+
+
+class HaloExchange:
+    """Exchange step that moves only what a rank needs (SURVEY.md 8e "halo-only exchange").
+
+    Rank t evaluates a block of cell rows and touches only the particles in the cell layers within one cut-off of it
+    (`cg_shard_window`).  Per step every rank sorts its owned particles into one segment per destination inside its
+    peer-mapped block (`cg_halo_publish`), one small all-reduce orders the ranks (same two-block protocol as
+    PeerExchange) and every rank pulls just its segments over NVLink (`cg_halo_pull`).  The evaluator then works on the
+    received subset; `ids` maps subset entries back to global particle indices.
+
+        ex = HaloExchange(ev, n_total, box, n_payload)         # payload arrays: x, y, z first, then q / mu as needed
+        arrays, ids, n_dev = ex.gather(owned2d)                # owned2d: [n_payload, count] of this rank
+        ex.set_system(ev, arrays, ...)                         # cg_set_system_device + cg_set_count_device
+    """
+
+    def __init__(self, evaluator, n_total, box, n_payload, device, group=None, capacity=None):
+        import ctypes as C
+        from ._capi import check, lib
+        self.ev, self.lib, self.C, self.check = evaluator, lib, C, check
+        self.group, self.device = group, torch.device(device)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.n_total, self.n_payload, self.narrays = n_total, n_payload, n_payload + 1  # + the global index
+        self.counts = [owned_range(n_total, r, self.world)[1] - owned_range(n_total, r, self.world)[0] for r in range(self.world)]
+        self.count = self.counts[self.rank]
+        self.lo = owned_range(n_total, self.rank, self.world)[0]
+        self.box = [float(b) for b in box]
+        check(lib.cg_set_grid_count(evaluator.h, n_total), "cg_set_grid_count", evaluator.h)
+        boxc = (C.c_double * 3)(*self.box)
+        zlo, zhi = (C.c_double * self.world)(), (C.c_double * self.world)()
+        for t in range(self.world):
+            w = (C.c_double * 2)()
+            check(lib.cg_shard_window(evaluator.h, boxc, t, self.world, n_total, w), "cg_shard_window", evaluator.h)
+            zlo[t], zhi[t] = w[0], w[1]
+        self.zlo, self.zhi = zlo, zhi
+        nbytes = lib.cg_halo_block_bytes(self.world, self.narrays, self.count)
+        self.own_ptr, handles = [], []
+        for _ in range(2):
+            p, h = C.c_void_p(), C.create_string_buffer(64)
+            check(lib.cg_peer_alloc(self.device.index, nbytes, C.byref(p), h), "cg_peer_alloc")
+            self.own_ptr.append(p)
+            handles.append(h.raw)
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=group)
+        self.block_ptrs, self._opened = [], []
+        for b in range(2):
+            row = []
+            for r in range(self.world):
+                if r == self.rank:
+                    row.append(self.own_ptr[b].value)
+                else:
+                    p = C.c_void_p()
+                    check(lib.cg_peer_open(self.device.index, everyone[r][b], C.byref(p)), "cg_peer_open")
+                    self._opened.append(p)
+                    row.append(p.value)
+            self.block_ptrs.append((C.c_void_p * self.world)(*row))
+        self.counts_c = (C.c_int64 * self.world)(*self.counts)
+        # what this rank receives: at most everything; the engine is told a tighter bound after the first step
+        self.capacity = int(capacity or n_total)
+        self.recv = torch.zeros((self.narrays, self.capacity), dtype=torch.float64, device=self.device)
+        self.recv_c = (C.c_void_p * self.narrays)(*[self.recv[a].data_ptr() for a in range(self.narrays)])
+        self.n_out = torch.zeros(2, dtype=torch.int32, device=self.device)
+        self.ids_owned = torch.arange(self.lo, self.lo + self.count, dtype=torch.float64, device=self.device)
+        self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.step, self.n_bound = 0, None
+
+    def gather(self, owned2d):
+        """owned2d: [n_payload, count] float64 on the device (row 2 = z).  -> (list of payload arrays [bound], ids [bound],
+        n_out int32[2] on the device: particles received, overflow flag).  `bound` >= the received count."""
+        C = self.C
+        b = self.step & 1
+        self.step += 1
+        src = (C.c_void_p * self.narrays)(*([owned2d[a].data_ptr() for a in range(self.n_payload)] + [self.ids_owned.data_ptr()]))
+        self._keep = owned2d
+        self.check(self.lib.cg_halo_publish(self.ev.h, self.world, self.narrays, 2, self.count, src, self.zlo, self.zhi, self.box[2],
+                                            self.own_ptr[b]), "cg_halo_publish", self.ev.h)
+        dist.all_reduce(self.flag, group=self.group)  # every owner has published block b; nobody still reads the other block
+        self.check(self.lib.cg_halo_pull(self.ev.h, self.world, self.rank, self.block_ptrs[b], self.counts_c, self.narrays, self.recv_c,
+                                         self.capacity, self.n_out.data_ptr()), "cg_halo_pull", self.ev.h)
+        if self.n_bound is None:  # first step: one host read to size the engine's launches (later steps reuse it)
+            got = self.n_out.cpu()
+            if int(got[1]) != 0:
+                raise RuntimeError("HaloExchange: capacity %d too small" % self.capacity)
+            self.n_bound = min(self.capacity, int(got[0]) + int(got[0]) // 8 + 1024)
+        nb = self.n_bound
+        return [self.recv[a, :nb] for a in range(self.n_payload)], self.recv[self.n_payload, :nb], self.n_out
+
+    def set_system(self, ev, arrays, has_q=True, has_mu=False, pbc=True):
+        """Hand the received subset to the evaluator: arrays = x, y, z[, q][, mux, muy, muz]."""
+        k = 3
+        q = arrays[k] if has_q else None
+        k += 1 if has_q else 0
+        mu = (arrays[k], arrays[k + 1], arrays[k + 2]) if has_mu else None
+        ev.set_system_device(arrays[0], arrays[1], arrays[2], q, mu, self.box, pbc)
+        self.check(self.lib.cg_set_count_device(ev.h, self.n_out.data_ptr()), "cg_set_count_device", ev.h)
+
+    def check_overflow(self):
+        """Host read of the overflow flag and the received count (synchronises)."""
+        got = self.n_out.cpu()
+        if int(got[1]) != 0 or (self.n_bound is not None and int(got[0]) > self.n_bound):
+            raise RuntimeError("HaloExchange: received %d particles, bound %s, capacity %d" % (int(got[0]), self.n_bound, self.capacity))
+        return int(got[0])
+
+    def close(self):
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)
+        for p in self._opened:
+            self.lib.cg_peer_close(p)
+        self._opened = []
+        for p in self.own_ptr:
+            self.lib.cg_peer_free(p)
+        self.own_ptr = []

@@ -226,6 +226,25 @@ int cg_peer_close(void *ptr);
 int cg_peer_gather(cg_handle *h, int nranks, const void *const *blocks, const int64_t *counts, int narrays,
                    double *const *full);
 
+/* Halo exchange -- the same pull, but only of the particles a rank needs.  A shard evaluates a block of cell rows and
+ * touches only the cell layers within one cut-off of it; cg_shard_window gives that z-interval [window[0], window[1]) for
+ * any rank (box coordinates; periodic images count, i.e. test z - L, z, z + L).  Per step every owner sorts its particles
+ * into one segment per destination rank inside its peer block (cg_halo_publish: three small kernels, stable order,
+ * counts in the block header; block size cg_halo_block_bytes), and every rank pulls just its segments from all blocks
+ * (cg_halo_pull: one kernel over NVLink; n_out[0] = particles received, n_out[1] = 1 if dst_cap was too small).  The
+ * received subset is then evaluated as usual: cg_set_system_device(h, dst_cap, ...) + cg_set_count_device(h, n_out)
+ * (the valid count stays on the device) with cg_set_grid_count(h, N_global) so that all ranks lay out the same cell
+ * grid.  Arrays are SoA of doubles; carry the global particle index as one more array to map the outputs back.
+ * zindex = which of the arrays is z.  counts[r] = particles owned by rank r (= its segment capacity). */
+int cg_set_grid_count(cg_handle *h, int64_t n_global);
+int cg_set_count_device(cg_handle *h, const int *n_dev);
+int cg_shard_window(cg_handle *h, const double *box, int rank, int nranks, int64_t n_global, double window[2]);
+size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count);
+int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned,
+                    const double *zlo, const double *zhi, double period, void *block);
+int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays,
+                 double *const *dst, int64_t dst_cap, int *n_out);
+
 /* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,
                                double *q, double *mux, double *muy, double *muz);

@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import coulombgalore_b200 as cg  # noqa: E402
-from coulombgalore_b200.distributed import PeerExchange, ShardedStep, owned_range  # noqa: E402
+from coulombgalore_b200.distributed import HaloExchange, PeerExchange, ShardedStep, owned_range  # noqa: E402
 
 
 def main():
@@ -54,6 +54,52 @@ def main():
             assert np.max(np.abs(f.cpu().numpy() - want["force"])) <= 1e-12 * np.max(np.abs(want["force"]))
             single.close()
     peer.close()
+    ev.close()
+
+    # ---- halo exchange: every rank receives only the particles of its window; results must not change ----
+    n_side, L = 32, 96.0  # slab 48 + 2 x (cut-off + slack layers) < 96: a 2-rank window is a true subset
+    N = n_side ** 3
+    pot = cg.ReactionField(12.0, 80.0, 1.0, False)
+    ev = cg.BatchedEvaluator(pot, local)
+    ev.set_stream(stream.cuda_stream)
+    ev.set_shard(rank, world)
+    arr = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(7)]
+    ev.generate_lattice_device(n_side, 3.0, 7, arr[0], arr[1], arr[2], arr[3], (arr[4], arr[5], arr[6]))
+    lo, hi = owned_range(N, rank, world)
+    halo = HaloExchange(ev, N, [L] * 3, 7, dev)
+    single = cg.BatchedEvaluator(pot, local)
+    single.set_system(*[t.cpu().numpy() for t in arr[:4]], tuple(t.cpu().numpy() for t in arr[4:]), [L] * 3, True)
+    w = cg.ENERGY | cg.FORCE | cg.FIELD
+    want = single.eval(cg.MODE_MULTIPOLE, w)
+    single.close()
+    received = []
+    for step in range(3):
+        owned = torch.stack([a[lo:hi] for a in arr])
+        sub, ids, n_out = halo.gather(owned)
+        halo.set_system(ev, sub, has_q=True, has_mu=True)
+        f = torch.zeros((sub[0].numel(), 3), dtype=torch.float64, device=dev)
+        e = torch.zeros_like(f)
+        sc2 = torch.zeros(2, dtype=torch.float64, device=dev)
+        ev.eval_device(cg.MODE_MULTIPOLE, w, force=f, field=e, scalars=sc2)
+        stream.synchronize()
+        n_got = halo.check_overflow()
+        received.append(n_got)
+        full_f = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+        full_e = torch.zeros_like(full_f)
+        idx = ids[:n_got].long()
+        assert idx.unique().numel() == n_got  # no particle twice
+        full_f[idx] = f[:n_got]
+        full_e[idx] = e[:n_got]
+        dist.all_reduce(full_f)
+        dist.all_reduce(full_e)
+        dist.all_reduce(sc2)
+        assert int(sc2[1].item()) == want["pairs"], (int(sc2[1].item()), want["pairs"])
+        assert abs(sc2[0].item() - want["energy"]) <= 1e-12 * abs(want["energy"]) + 1e-9
+        assert np.max(np.abs(full_f.cpu().numpy() - want["force"])) <= 1e-12 * np.max(np.abs(want["force"]))
+        assert np.max(np.abs(full_e.cpu().numpy() - want["field"])) <= 1e-12 * np.max(np.abs(want["field"]))
+    if world > 1:
+        assert received[0] < N, "a rank of a multi-rank run must receive a true subset"
+    halo.close()
     ev.close()
     dist.barrier()
     if rank == 0:

@@ -8,7 +8,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 import coulombgalore_b200 as cg
-from coulombgalore_b200.distributed import PeerExchange, ShardedStep, owned_range
+from coulombgalore_b200.distributed import HaloExchange, PeerExchange, ShardedStep, owned_range
 
 INF = float("inf")
 CONFIGS = {
@@ -41,8 +41,11 @@ def main():
         use = [0, 1, 2] + ([3] if c["mode"] != cg.MODE_DIPOLE else []) + ([4, 5, 6] if c["mode"] != cg.MODE_ION else [])
         lo, hi = owned_range(N, rank, world)
         owned = [arr[k][lo:hi].clone() for k in use]
-        # CG_EXCHANGE=nccl: the all-gather of the collective library; default: this repo's pull kernel over peer memory
-        ex = ShardedStep(N, len(use), dev) if (world == 1 or os.environ.get("CG_EXCHANGE") == "nccl") else PeerExchange.create(ev, N, len(use), dev)
+        # CG_EXCHANGE = halo (default): pull only the particles of the rank's window; peer: pull everything (own kernel);
+        # nccl: the collective library's all-gather
+        mode_x = os.environ.get("CG_EXCHANGE", "halo") if world > 1 else "nccl"
+        hx = HaloExchange(ev, N, [L] * 3, len(use), dev) if mode_x == "halo" else None
+        ex = ShardedStep(N, len(use), dev) if mode_x != "peer" else PeerExchange.create(ev, N, len(use), dev)
         del arr
         f = torch.empty((N, 3), dtype=torch.float64, device=dev)
         e = torch.empty((N, 3), dtype=torch.float64, device=dev) if c["what"] & cg.FIELD else None
@@ -51,17 +54,25 @@ def main():
 
         marks = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
 
-        if isinstance(ex, PeerExchange):
+        if isinstance(ex, PeerExchange) or hx is not None:
             owned = torch.stack(owned)  # one publish copy per step instead of one per array
 
         def step(mk=None):
-            full = ex.gather(owned)
-            if mk:
-                mk[0].record()
-            g = dict(zip(use, full))
-            mu = (g[4], g[5], g[6]) if 4 in g else None
-            ev.set_system_device(g[0], g[1], g[2], g.get(3), mu, [L] * 3, True)
-            ev.eval_device(c["mode"], c["what"], force=f, field=e, scalars=sc)
+            if hx is not None:
+                sub, ids, n_out = hx.gather(owned)
+                if mk:
+                    mk[0].record()
+                hx.set_system(ev, sub, has_q=3 in use, has_mu=4 in use)
+                nb = sub[0].numel()
+                ev.eval_device(c["mode"], c["what"], force=f[:nb], field=None if e is None else e[:nb], scalars=sc)
+            else:
+                full = ex.gather(owned)
+                if mk:
+                    mk[0].record()
+                g = dict(zip(use, full))
+                mu = (g[4], g[5], g[6]) if 4 in g else None
+                ev.set_system_device(g[0], g[1], g[2], g.get(3), mu, [L] * 3, True)
+                ev.eval_device(c["mode"], c["what"], force=f, field=e, scalars=sc)
             if mk:
                 mk[1].record()
             ex.reduce_scalars(sc)
@@ -104,10 +115,13 @@ def main():
                               "gather_ms_max": ms[3].item(), "eval_ms_max": ms[4].item(), "allreduce_ms_max": ms[5].item(), "pairs_per_s": pairs / ms[0].item() * 1e3,
                               "tflops_alg": pairs * c["falg"] / ms[0].item() * 1e3 / 1e12, "energy": sc[0].item(),
                               "exchange": "%s of %d fp64 arrays (%d B/particle) + all-reduce of 2 scalars" %
-                              ("peer-memory pull kernel" if isinstance(ex, PeerExchange) else "NCCL all-gather", len(use), 8 * len(use)),
+                              ("halo pull (%d of %d particles received)" % (hx.check_overflow(), N) if hx is not None else
+                               "peer-memory pull kernel" if isinstance(ex, PeerExchange) else "NCCL all-gather", len(use), 8 * len(use)),
                               "exchange_fallback": getattr(ex, "fallback_reason", None)}), flush=True)
         if isinstance(ex, PeerExchange):
             ex.close()
+        if hx is not None:
+            hx.close()
         ev.close()
         del f, e, flush, ex, owned
         torch.cuda.empty_cache()
