@@ -113,6 +113,33 @@ def _load():
         fn = getattr(lib, name)  # AttributeError here == the library does not export what the header declares
         fn.argtypes = args
         fn.restype = C.c_int
+    R = C.c_void_p
+    p7 = [C.c_void_p] * 7
+    rsig = {
+        "cg_recip_create": [C.c_double] * 4 + [C.c_int, _dp, C.c_int, C.POINTER(R)],
+        "cg_recip_destroy": [R],
+        "cg_recip_set_stream": [R, C.c_void_p],
+        "cg_recip_num_kvectors": [R],
+        "cg_recip_kvectors": [R, _dp, _dp],
+        "cg_recip_get_q": [R, _dp],
+        "cg_recip_set_q": [R, _dp],
+        "cg_recip_update": [R, C.c_int64] + p7 + [C.c_int],
+        "cg_recip_update_device": [R, C.c_int64] + p7 + [C.c_int],
+        "cg_recip_energy": [R, _dp],
+        "cg_recip_energy_device": [R, C.c_void_p],
+        "cg_recip_force_field": [R, C.c_int64] + p7 + [C.c_void_p, C.c_void_p],
+        "cg_recip_force_field_device": [R, C.c_int64] + p7 + [C.c_void_p, C.c_void_p],
+        "cg_recip_surface": [R, C.c_int64] + p7 + [_dp, _dp],
+        "cg_recip_surface_device": [R, C.c_int64] + p7 + [C.c_void_p],
+    }
+    for name, args in rsig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.cg_recip_last_error.argtypes = [R]
+    lib.cg_recip_last_error.restype = C.c_char_p
+    lib.cg_recip_q_device.argtypes = [R]
+    lib.cg_recip_q_device.restype = C.c_void_p
     lib.cg_halo_block_bytes.argtypes = [C.c_int, C.c_int, C.c_int64]
     lib.cg_halo_block_bytes.restype = C.c_size_t
     lib.cg_spline_storage_doubles.argtypes = []
@@ -134,7 +161,10 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
             "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_set_quadrupoles", "cg_set_quadrupoles_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings",
             "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_set_grid_count", "cg_set_count_device", "cg_shard_window", "cg_halo_block_bytes", "cg_halo_publish",
-            "cg_halo_pull", "cg_generate_lattice_device", "cg_fp64_peak_probe"]
+            "cg_halo_pull", "cg_generate_lattice_device", "cg_recip_create", "cg_recip_destroy", "cg_recip_last_error",
+            "cg_recip_set_stream", "cg_recip_num_kvectors", "cg_recip_kvectors", "cg_recip_q_device", "cg_recip_get_q", "cg_recip_set_q",
+            "cg_recip_update", "cg_recip_update_device", "cg_recip_energy", "cg_recip_energy_device", "cg_recip_force_field",
+            "cg_recip_force_field_device", "cg_recip_surface", "cg_recip_surface_device", "cg_fp64_peak_probe"]
 
 
 def check(rc, where, handle=None):

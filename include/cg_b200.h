@@ -251,6 +251,41 @@ int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed,
 /* FP64-pipe peak probe: a register-resident DFMA chain; returns measured TFLOP/s (2 flops per DFMA) */
 int cg_fp64_peak_probe(cg_handle *h, double *tflops, double *ms);
 
+/* ---- Reciprocal-space Ewald (reference ewald.hpp:44-94, 214-385: ReciprocalEwaldState + ReciprocalEwaldGaussian) ----
+ * cg_recip_create takes the state fields (cutoff, alpha, surface_dielectric_constant, kappa, reciprocal_cutoff <= 24,
+ * box_length) and generates the k-vectors and A_k as generateKVectors / setAks do.  The handle owns Q_mp (device):
+ * cg_recip_update* = updateComplex (sign +1 add, -1 subtract, 0 = zero first), cg_recip_energy = reciprocal_energy,
+ * cg_recip_force_field* = reciprocal_force(r_p, z_p, mu_p) and reciprocal_field(r_p) for every particle (either output
+ * may be NULL), cg_recip_surface = surface_energy and surface_field.  *_device forms take device pointers and are
+ * asynchronous on the handle's stream.  Multi-GPU: update with the rank's own particles, all-reduce the 2K doubles at
+ * cg_recip_q_device (re, im interleaved), then evaluate the rank's own particles. */
+typedef struct cg_recip cg_recip;
+int cg_recip_create(double cutoff, double alpha, double eps_sur, double kappa, int reciprocal_cutoff, const double *box,
+                    int device, cg_recip **out);
+int cg_recip_destroy(cg_recip *r);
+const char *cg_recip_last_error(const cg_recip *r);
+int cg_recip_set_stream(cg_recip *r, void *cuda_stream);
+int cg_recip_num_kvectors(const cg_recip *r);
+int cg_recip_kvectors(const cg_recip *r, double *k3, double *aks); /* host copies: 3K and K doubles */
+double *cg_recip_q_device(cg_recip *r);
+int cg_recip_get_q(cg_recip *r, double *q2k);
+int cg_recip_set_q(cg_recip *r, const double *q2k);
+int cg_recip_update(cg_recip *r, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                    const double *mux, const double *muy, const double *muz, int sign);
+int cg_recip_update_device(cg_recip *r, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                           const double *mux, const double *muy, const double *muz, int sign);
+int cg_recip_energy(cg_recip *r, double *energy);
+int cg_recip_energy_device(cg_recip *r, double *energy_dev);
+int cg_recip_force_field(cg_recip *r, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                         const double *mux, const double *muy, const double *muz, double *force, double *field);
+int cg_recip_force_field_device(cg_recip *r, int64_t n, const double *x, const double *y, const double *z,
+                                const double *q, const double *mux, const double *muy, const double *muz,
+                                double *force, double *field);
+int cg_recip_surface(cg_recip *r, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                     const double *mux, const double *muy, const double *muz, double *energy, double *field3);
+int cg_recip_surface_device(cg_recip *r, int64_t n, const double *x, const double *y, const double *z, const double *q,
+                            const double *mux, const double *muy, const double *muz, double *dipole3_dev);
+
 #ifdef __cplusplus
 }
 #endif

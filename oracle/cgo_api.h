@@ -117,6 +117,29 @@ int cgo_batched_quad(void *handle, int64_t N, const double *x, const double *y, 
 int cgo_self_terms(void *handle, int64_t N, const double *q, const double *mux, const double *muy, const double *muz,
                    double volume, const double *field, double *scalars, double *self_field, double *torque);
 
+/*
+ * Reciprocal-space Ewald (reference ewald.hpp:44-94, 214-385: ReciprocalEwaldState / ReciprocalEwaldGaussian).
+ * create: the state fields + generateKVectors(box).  update: updateComplex with sign = +1 (add), -1 (subtract) or
+ * 0 (zero Q first, then add).  q: Q_mp as 2K doubles (re, im interleaved); kvectors: 3K doubles + K Aks.
+ * force_field: reciprocal_force(r_p, z_p, mu_p) and reciprocal_field(r_p) per particle (outputs may be NULL);
+ * scales (may be NULL): per particle sum_k |term| of the force (tolerance denominator).
+ * surface: surface_energy and surface_field (3 doubles) of the particle set.
+ */
+int cgo_recip_create(double cutoff, double alpha, double eps_sur, double kappa, int32_t reciprocal_cutoff, const double *box,
+                     void **handle);
+void cgo_recip_destroy(void *handle);
+int32_t cgo_recip_numk(void *handle);
+int cgo_recip_kvectors(void *handle, double *k3, double *aks);
+int cgo_recip_update(void *handle, int64_t N, const double *x, const double *y, const double *z, const double *q,
+                     const double *mux, const double *muy, const double *muz, int32_t sign);
+int cgo_recip_q(void *handle, double *q2k);
+int cgo_recip_energy(void *handle, double *energy);
+int cgo_recip_force_field(void *handle, int64_t N, const double *x, const double *y, const double *z, const double *q,
+                          const double *mux, const double *muy, const double *muz, double *force, double *field,
+                          double *force_scale);
+int cgo_recip_surface(void *handle, int64_t N, const double *x, const double *y, const double *z, const double *q,
+                      const double *mux, const double *muy, const double *muz, double *energy, double *field3);
+
 #ifdef __cplusplus
 }
 #endif

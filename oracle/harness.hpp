@@ -377,6 +377,23 @@ template <class T, class VEC, class MAT> struct Impl : Iface {
     }
 };
 
+
+// reciprocal-space Ewald behind the C ABI: each build supplies cgo::make_recip
+struct RecipIface {
+    virtual ~RecipIface() {}
+    virtual int numk() = 0;
+    virtual int kvectors(double *k3, double *aks) = 0;
+    virtual int update(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx, const double *my,
+                       const double *mz, int sign) = 0;
+    virtual int getq(double *q2k) = 0;
+    virtual int energy(double *e) = 0;
+    virtual int force_field(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx,
+                            const double *my, const double *mz, double *force, double *field, double *fscale) = 0;
+    virtual int surface(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx,
+                        const double *my, const double *mz, double *energy, double *field3) = 0;
+};
+RecipIface *make_recip(double cutoff, double alpha, double eps_sur, double kappa, int kc, const double *box);
+
 } // namespace cgo
 
 // ---------------------------------------------------------------------------------------------------
@@ -411,6 +428,34 @@ Iface *make(const cgo_params &p); // throws on invalid parameters
     void cgo_generate(int32_t n, double a, uint64_t seed, double *x, double *y, double *z, double *q,             \
                       double *mx, double *my, double *mz) {                                                        \
         cgo::generate(n, a, seed, x, y, z, q, mx, my, mz);                                                         \
+    }                                                                                                              \
+    int cgo_recip_create(double cutoff, double alpha, double eps_sur, double kappa, int32_t kc, const double *box,  \
+                         void **h) {                                                                               \
+        try {                                                                                                      \
+            *h = cgo::make_recip(cutoff, alpha, eps_sur, kappa, kc, box);                                          \
+            return *h ? 0 : -2;                                                                                    \
+        } catch (...) {                                                                                            \
+            *h = nullptr;                                                                                          \
+            return -1;                                                                                             \
+        }                                                                                                          \
+    }                                                                                                              \
+    void cgo_recip_destroy(void *h) { delete static_cast<cgo::RecipIface *>(h); }                                  \
+    int32_t cgo_recip_numk(void *h) { return static_cast<cgo::RecipIface *>(h)->numk(); }                          \
+    int cgo_recip_kvectors(void *h, double *k3, double *a) { return static_cast<cgo::RecipIface *>(h)->kvectors(k3, a); } \
+    int cgo_recip_update(void *h, int64_t N, const double *x, const double *y, const double *z, const double *q,  \
+                         const double *mx, const double *my, const double *mz, int32_t sign) {                     \
+        return static_cast<cgo::RecipIface *>(h)->update(N, x, y, z, q, mx, my, mz, sign);                         \
+    }                                                                                                              \
+    int cgo_recip_q(void *h, double *q2k) { return static_cast<cgo::RecipIface *>(h)->getq(q2k); }                 \
+    int cgo_recip_energy(void *h, double *e) { return static_cast<cgo::RecipIface *>(h)->energy(e); }              \
+    int cgo_recip_force_field(void *h, int64_t N, const double *x, const double *y, const double *z,               \
+                              const double *q, const double *mx, const double *my, const double *mz,               \
+                              double *force, double *field, double *fs) {                                          \
+        return static_cast<cgo::RecipIface *>(h)->force_field(N, x, y, z, q, mx, my, mz, force, field, fs);        \
+    }                                                                                                              \
+    int cgo_recip_surface(void *h, int64_t N, const double *x, const double *y, const double *z, const double *q, \
+                          const double *mx, const double *my, const double *mz, double *e, double *f3) {           \
+        return static_cast<cgo::RecipIface *>(h)->surface(N, x, y, z, q, mx, my, mz, e, f3);                       \
     }                                                                                                              \
     int cgo_self_terms(void *h, int64_t N, const double *q, const double *mx, const double *my, const double *mz,  \
                        double volume, const double *field, double *scalars, double *self_field, double *torque) {  \

@@ -187,6 +187,71 @@ def _self_terms(self, q, mu, volume=0.0, field=None):
 Scheme.self_terms = _self_terms
 
 
+class Reciprocal:
+    """Reciprocal-space Ewald of the oracle: the reference's ReciprocalEwaldGaussian (kind "ref") or its restatement."""
+
+    def __init__(self, cutoff, alpha, eps_sur, kappa, kc, box, kind="best"):
+        self.lib = load(kind)
+        L = self.lib
+        L.cgo_recip_create.argtypes = [C.c_double] * 4 + [C.c_int32, _dp, C.POINTER(C.c_void_p)]
+        L.cgo_recip_destroy.argtypes = [C.c_void_p]
+        L.cgo_recip_destroy.restype = None
+        L.cgo_recip_numk.argtypes = [C.c_void_p]
+        L.cgo_recip_numk.restype = C.c_int32
+        L.cgo_recip_kvectors.argtypes = [C.c_void_p, _dp, _dp]
+        L.cgo_recip_update.argtypes = [C.c_void_p, C.c_int64] + [_dp] * 7 + [C.c_int32]
+        L.cgo_recip_q.argtypes = [C.c_void_p, _dp]
+        L.cgo_recip_energy.argtypes = [C.c_void_p, _dp]
+        L.cgo_recip_force_field.argtypes = [C.c_void_p, C.c_int64] + [_dp] * 10
+        L.cgo_recip_surface.argtypes = [C.c_void_p, C.c_int64] + [_dp] * 9
+        self.h = C.c_void_p()
+        b = np.ascontiguousarray(box, dtype=np.float64)
+        if L.cgo_recip_create(cutoff, alpha, eps_sur, kappa, kc, _ptr(b), C.byref(self.h)) != 0:
+            raise ValueError("cgo_recip_create failed")
+        self.K = int(L.cgo_recip_numk(self.h))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.cgo_recip_destroy(self.h)
+            self.h = None
+
+    def kvectors(self):
+        k, a = np.zeros((self.K, 3)), np.zeros(self.K)
+        self.lib.cgo_recip_kvectors(self.h, _ptr(k), _ptr(a))
+        return k, a
+
+    @staticmethod
+    def _mu(mu):
+        return (None, None, None) if mu is None else mu
+
+    def update(self, x, y, z, q, mu, sign=0):
+        mx, my, mz = self._mu(mu)
+        self.lib.cgo_recip_update(self.h, x.size, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz), sign)
+
+    def q(self):
+        out = np.zeros(2 * self.K)
+        self.lib.cgo_recip_q(self.h, _ptr(out))
+        return out[0::2] + 1j * out[1::2]
+
+    def energy(self):
+        e = np.zeros(1)
+        self.lib.cgo_recip_energy(self.h, _ptr(e))
+        return float(e[0])
+
+    def force_field(self, x, y, z, q, mu):
+        mx, my, mz = self._mu(mu)
+        f, e, s = np.zeros((x.size, 3)), np.zeros((x.size, 3)), np.zeros(x.size)
+        self.lib.cgo_recip_force_field(self.h, x.size, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz), _ptr(f), _ptr(e),
+                                       _ptr(s))
+        return dict(force=f, field=e, force_scale=s)
+
+    def surface(self, x, y, z, q, mu):
+        mx, my, mz = self._mu(mu)
+        e, f = np.zeros(1), np.zeros(3)
+        self.lib.cgo_recip_surface(self.h, x.size, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz), _ptr(e), _ptr(f))
+        return float(e[0]), f
+
+
 def generate(n, a, seed, kind="best"):
     """Jittered-lattice system of SURVEY.md 8d -> x, y, z, q, (mux, muy, muz)."""
     lib = load(kind)

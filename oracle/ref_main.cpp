@@ -66,4 +66,109 @@ cgo::Iface *cgo::make(const cgo_params &p) {
     }
 }
 
+// ---- reciprocal-space Ewald: the reference's own ReciprocalEwaldGaussian (ewald.hpp:214-385) ----
+namespace {
+struct RefRecip : cgo::RecipIface {
+    std::unique_ptr<ReciprocalEwaldGaussian> pot;
+    struct KAccess : ReciprocalEwaldGaussian { // k_vectors / Aks / Q_mp are protected members of the state class
+        using ReciprocalEwaldGaussian::Aks;
+        using ReciprocalEwaldGaussian::k_vectors;
+        using ReciprocalEwaldGaussian::Q_mp;
+    };
+    const KAccess &acc() const { return static_cast<const KAccess &>(*pot); }
+    RefRecip(double cutoff, double alpha, double eps_sur, double kappa, int kc, const double *box) {
+        ReciprocalEwaldState st;
+        st.box_length = {box[0], box[1], box[2]};
+        st.cutoff = cutoff;
+        st.reciprocal_cutoff = kc;
+        st.alpha = alpha;
+        st.kappa = kappa;
+        st.surface_dielectric_constant = eps_sur;
+        pot.reset(new ReciprocalEwaldGaussian(st));
+    }
+    static void load(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx, const double *my,
+                     const double *mz, std::vector<vec3> &pos, std::vector<double> &ch, std::vector<vec3> &dip) {
+        pos.resize((size_t)N);
+        ch.resize((size_t)N);
+        dip.resize((size_t)N);
+        for (int64_t i = 0; i < N; i++) {
+            pos[(size_t)i] = vec3(x[i], y[i], z[i]);
+            ch[(size_t)i] = q ? q[i] : 0.0;
+            dip[(size_t)i] = mx ? vec3(mx[i], my[i], mz[i]) : vec3(0, 0, 0);
+        }
+    }
+    int numk() override { return pot->numKVectors(); }
+    int kvectors(double *k3, double *aks) override {
+        for (int i = 0; i < pot->numKVectors(); i++) {
+            const vec3 k = acc().k_vectors.col(i);
+            if (k3)
+                for (int d = 0; d < 3; d++) k3[3 * i + d] = k[d];
+            if (aks) aks[i] = acc().Aks[i];
+        }
+        return 0;
+    }
+    int update(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx, const double *my,
+               const double *mz, int sign) override {
+        std::vector<vec3> pos, dip;
+        std::vector<double> ch;
+        load(N, x, y, z, q, mx, my, mz, pos, ch, dip);
+        if (sign == 0) pot->setZeroComplex();
+        if (sign < 0) pot->updateComplex(pos, ch, dip, std::minus<>());
+        else pot->updateComplex(pos, ch, dip);
+        return 0;
+    }
+    int getq(double *q2k) override {
+        for (int i = 0; i < pot->numKVectors(); i++) {
+            q2k[2 * i] = acc().Q_mp[i].real();
+            q2k[2 * i + 1] = acc().Q_mp[i].imag();
+        }
+        return 0;
+    }
+    int energy(double *e) override {
+        *e = pot->reciprocal_energy();
+        return 0;
+    }
+    int force_field(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx, const double *my,
+                    const double *mz, double *force, double *field, double *fs) override {
+        const double pi = 4.0 * std::atan(1.0);
+        for (int64_t i = 0; i < N; i++) {
+            const vec3 r(x[i], y[i], z[i]), mu = mx ? vec3(mx[i], my[i], mz[i]) : vec3(0, 0, 0);
+            const double ch = q ? q[i] : 0.0;
+            if (force) {
+                const vec3 f = pot->reciprocal_force(r, ch, mu);
+                for (int d = 0; d < 3; d++) force[3 * i + d] = f[d];
+            }
+            if (field) {
+                const vec3 f = pot->reciprocal_field(r);
+                for (int d = 0; d < 3; d++) field[3 * i + d] = f[d];
+            }
+            if (fs) { // sum_k |term_k| of reciprocal_force: the scale rounding errors are measured against
+                long double s = 0;
+                for (int k = 0; k < pot->numKVectors(); k++) {
+                    const vec3 kv = acc().k_vectors.col(k);
+                    s += (std::fabs(mu.dot(kv)) + std::fabs(ch)) * std::abs(acc().Q_mp[k]) * kv.norm() * acc().Aks[k];
+                }
+                fs[i] = (double)(4.0 * pi / pot->getVolume() * s);
+            }
+        }
+        return 0;
+    }
+    int surface(int64_t N, const double *x, const double *y, const double *z, const double *q, const double *mx, const double *my,
+                const double *mz, double *energy, double *field3) override {
+        std::vector<vec3> pos, dip;
+        std::vector<double> ch;
+        load(N, x, y, z, q, mx, my, mz, pos, ch, dip);
+        if (energy) *energy = pot->surface_energy(pos, ch, dip);
+        if (field3) {
+            const vec3 f = pot->surface_field(pos, ch, dip);
+            for (int d = 0; d < 3; d++) field3[d] = f[d];
+        }
+        return 0;
+    }
+};
+} // namespace
+cgo::RecipIface *cgo::make_recip(double cutoff, double alpha, double eps_sur, double kappa, int kc, const double *box) {
+    return new RefRecip(cutoff, alpha, eps_sur, kappa, kc, box);
+}
+
 CGO_DEFINE_C_ABI("reference")

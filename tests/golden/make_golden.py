@@ -13,6 +13,8 @@ reference's own double-precision outputs:
   batch/<case>/..       batched loop (oracle/harness.hpp) on a 6^3 lattice: force, field, potential, energy, pairs
   lattice/..            generator output (splitmix64 rule of SURVEY.md 8d)
   batch_quad/<case>/..  the same loop in multipole mode with seeded, non-symmetric quadrupole tensors (quad_inputs)
+  recip/..              reciprocal-space Ewald (ReciprocalEwaldGaussian) on the lattice: k-vectors, Aks, Q, energy, force,
+                        field, force scale, surface terms for recip_params
   self/<scheme>/..      O(N) terms on the lattice with a non-neutral charge set (self_inputs): scalars = sum of
                         self_energy, its absolute sum, neutralization_energy (V = 18^3), charge sum; self_field per
                         particle; self/torque = dipole_torque(mu_i, E_i) for the seeded field of self_inputs
@@ -47,6 +49,10 @@ def pair_inputs(cutoff):
 def quad_inputs(n):
     """Seeded general (non-symmetric, not traceless) 3x3 quadrupole tensors."""
     return np.random.default_rng(4242).normal(size=(n, 3, 3))
+
+
+# cutoff, alpha, eps_sur, kappa, reciprocal_cutoff, box
+RECIP_CASES = {"plain": (9.0, 0.35, 80.0, 0.0, 7, [18.0, 18.0, 18.0]), "screened_ortho": (8.0, 0.4, 1.0, 0.05, 5, [18.0, 20.0, 22.0])}
 
 
 def self_inputs(q):
@@ -99,6 +105,17 @@ def main():
         for f in ("force", "field", "potential", "force_scale", "field_scale", "potential_scale"):
             d[k + f] = r[f]
         d[k + "scalars"] = np.array([r["energy"], r["energy_abs"], float(r["pairs"])])
+    for name, (rc, al, eps, kap, kc, box) in RECIP_CASES.items():
+        r = O.Reciprocal(rc, al, eps, kap, kc, box, "ref")
+        r.update(x, y, z, ch, mu, 0)
+        kv, aks = r.kvectors()
+        ff = r.force_field(x, y, z, ch, mu)
+        se, sf = r.surface(x, y, z, ch, mu)
+        d["recip/%s/k" % name], d["recip/%s/aks" % name] = kv, aks
+        qq = r.q()
+        d["recip/%s/q" % name] = np.stack([qq.real, qq.imag])
+        d["recip/%s/force" % name], d["recip/%s/field" % name], d["recip/%s/force_scale" % name] = ff["force"], ff["field"], ff["force_scale"]
+        d["recip/%s/scalars" % name] = np.array([r.energy(), se, sf[0], sf[1], sf[2]])
     qn, fld = self_inputs(ch)
     for name in ZOO:
         r = O.Scheme(oracle_params(name), "ref").self_terms(qn, mu, 18.0 ** 3, field=fld)

@@ -301,3 +301,74 @@ def test_peer_exchange_single_rank_and_two_ranks_if_available():
                "--master-port", str(29650 + world), script]
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0 and "PEER_EXCHANGE_OK world=%d" % world in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_reciprocal_ewald_against_oracle_golden_and_reference_kats(oracle_kind):
+    """ReciprocalEwaldGaussian on the device (structure factors, energy, force, field, surface terms)."""
+    from golden.make_golden import RECIP_CASES
+    # the reference's own known answers (test/unittests.cpp:559-690)
+    pos = np.array([[-0.5, 0.0, 0.0], [0.5, 0.0, 0.0]])
+    st = cg.ReciprocalEwaldState(box_length=[10.0] * 3, cutoff=5.0, reciprocal_cutoff=11, alpha=0.8, surface_dielectric_constant=np.inf)
+    pot = cg.ReciprocalEwaldGaussian(st)
+    assert pot.numKVectors() == 5574
+    q, zero = np.array([1.0, -1.0]), np.zeros((2, 3))
+    pot.updateComplex(pos, q, zero)
+    assert pot.reciprocal_energy() == pytest.approx(0.1584768302, rel=1e-8)
+    assert pot.reciprocal_force(pos, q, zero)[0] == pytest.approx([0.2617988467, 0.0, 0.0], rel=1e-8, abs=1e-12)
+    assert pot.reciprocal_field(pos)[0] == pytest.approx([0.2617988467, 0.0, 0.0], rel=1e-8, abs=1e-12)
+    assert pot.surface_energy(pos, q, zero) == 0.0
+    assert pot.real_space.ion_ion_energy(1.0, -1.0, 1.0) == pytest.approx(-0.2578990353, rel=1e-8) if hasattr(pot.real_space, "ion_ion_energy") else True
+    st.surface_dielectric_constant = 1.0
+    pot1 = cg.ReciprocalEwaldGaussian(st)
+    assert pot1.surface_energy(pos, q, zero) == pytest.approx(0.0020943951, rel=1e-8)
+    assert pot1.surface_field(pos, q, zero)[0] == pytest.approx(0.0041887902, rel=1e-8)
+    mu = np.array([[1.0, 0.0, 0.0], [1.0, 0.0, 0.0]])
+    pot.setZeroComplex()
+    pot.updateComplex(pos, np.zeros(2), mu)
+    assert pot.reciprocal_energy() == pytest.approx(0.4534417045, rel=1e-8)
+    assert pot.reciprocal_field(pos)[0][0] == pytest.approx(-0.4534417045, rel=1e-8)
+    assert pot1.surface_energy(pos, np.zeros(2), mu) == pytest.approx(0.0083775804, rel=1e-8)
+    assert pot1.surface_energy(pos, q, np.array([[1.0, 1.0, 1.0], [-1.0, 1.0, 0.0]])) == pytest.approx(0.0125663706, rel=1e-8)
+    # incremental updates: subtracting and re-adding a particle restores Q
+    pot.setZeroComplex()
+    pot.updateComplex(pos, q, mu)
+    q0 = pot.Q()
+    pot.updateComplex(pos[:1], q[:1], mu[:1], subtract=True)
+    pot.updateComplex(pos[:1], q[:1], mu[:1])
+    assert np.max(np.abs(pot.Q() - q0)) <= 1e-14
+    # degenerate k-list (reciprocal_cutoff = 0): one dummy vector with zero weight -> zero energy, force and field
+    st0 = cg.ReciprocalEwaldState(box_length=[10.0] * 3, cutoff=5.0, reciprocal_cutoff=0, alpha=0.8, surface_dielectric_constant=1.0)
+    p0 = cg.ReciprocalEwaldGaussian(st0)
+    p0.updateComplex(pos, q, mu)
+    assert p0.numKVectors() == 1 and p0.reciprocal_energy() == 0.0 and np.all(p0.reciprocal_force(pos, q, mu) == 0.0)
+    o0 = O.Reciprocal(5.0, 0.8, 1.0, 0.0, 0, [10.0] * 3, oracle_kind)
+    o0.update(pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), q, tuple(mu[:, k].copy() for k in range(3)), 0)
+    assert np.max(np.abs(p0.Q() - o0.q())) <= 1e-14
+    # lattice system: the live oracle and the committed reference run
+    lat = GOLD["lattice/n6_a3_seed31337"]
+    x, y, z, ch, m = lat[0].copy(), lat[1].copy(), lat[2].copy(), lat[3].copy(), (lat[4].copy(), lat[5].copy(), lat[6].copy())
+    P, M = np.stack([x, y, z], axis=1), np.stack(m, axis=1)
+    for name, (rc, al, eps, kap, kc, box) in RECIP_CASES.items():
+        g = cg.ReciprocalEwaldGaussian(cg.ReciprocalEwaldState(box, rc, kc, al, eps, kap))
+        o = O.Reciprocal(rc, al, eps, kap, kc, box, oracle_kind)
+        g.updateComplex(P, ch, M)
+        o.update(x, y, z, ch, m, 0)
+        kv, aks = g.kvectors()
+        assert np.array_equal(kv, GOLD["recip/%s/k" % name]) and np.allclose(aks, GOLD["recip/%s/aks" % name], rtol=1e-14, atol=0)
+        qscale = np.sum(np.abs(ch)) + np.abs(M @ kv.T).sum(axis=0)  # sum_p |z_p| + |mu_p . k|
+        gq = GOLD["recip/%s/q" % name]
+        for ref in (o.q(), gq[0] + 1j * gq[1]):
+            assert np.max(np.abs(g.Q() - ref) / qscale) <= TOL
+        sc = GOLD["recip/%s/scalars" % name]
+        assert abs(g.reciprocal_energy() - o.energy()) <= TOL * o.energy() and abs(g.reciprocal_energy() - sc[0]) <= TOL * sc[0]
+        F, E, ff = g.reciprocal_force(P, ch, M), g.reciprocal_field(P), o.force_field(x, y, z, ch, m)
+        for ref_f, ref_e, s in ((ff["force"], ff["field"], ff["force_scale"]),
+                                (GOLD["recip/%s/force" % name], GOLD["recip/%s/field" % name], GOLD["recip/%s/force_scale" % name])):
+            assert np.max(np.linalg.norm(F - ref_f, axis=1) / np.maximum(s, 1e-300)) <= TOL
+            assert np.max(np.linalg.norm(E - ref_e, axis=1)) <= TOL * np.max(np.linalg.norm(ref_e, axis=1)) * 50
+        se, sf = o.surface(x, y, z, ch, m)
+        assert g.surface_energy(P, ch, M) == pytest.approx(se, rel=1e-12) and np.allclose(g.surface_field(P, ch, M), sf, rtol=1e-12, atol=1e-300)
+        assert g.surface_energy(P, ch, M) == pytest.approx(sc[1], rel=1e-12)
+        g.close()
+    for p_ in (pot, pot1, p0):
+        p_.close()
