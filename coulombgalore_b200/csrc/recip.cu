@@ -15,8 +15,9 @@
 //   * Q: one thread per k-vector; particles stream through shared memory in tiles together with their per-axis tables
 //     exp(i m theta), m = 0..kc (built once per tile, one sincos per particle and axis); partial sums per particle slab,
 //     then a fixed-order reduction -> bit-reproducible.
-//   * force / field: one thread per particle; the k-loop is regenerated in the reference's order (nx, ny outer; nz inner, walked
+//   * force / field: one thread per particle; the k-loop is regenerated from the reference's order (nx, ny outer; nz inner, walked
 //     from 0 outwards so that +nz and -nz share one recurrence); Q_k and A_k are warp-uniform loads.
+//   * k and -k: Q_{-k} = conj(Q_k) and the force / field terms of k and -k are equal, so both kernels do half of the list.
 // Multi-GPU: every rank updates Q with its own particles, the ranks all-reduce the 2K doubles (cg_recip_q_device), then each
 // rank evaluates its own particles.  No spatial structure is needed.
 #include <cuda_runtime.h>
@@ -73,8 +74,9 @@ __global__ void __launch_bounds__(kQThreads) recip_q_kernel(const __grid_constan
     const int nt = rd.kc + 1;
     double2 *tab = smem;                                                // [kTile][3][nt]
     double *pq = reinterpret_cast<double *>(smem + kTile * 3 * nt);     // [kTile][4]: z, mux, muy, muz
+    // Q_{-k} = conj(Q_k) and -k sits at index K - 1 - idx (the list is in lexicographic order): half the list is computed
     const int kk = blockIdx.x * kQThreads + threadIdx.x;
-    const bool live = kk < rd.K;
+    const bool live = kk < (rd.lattice ? rd.K / 2 : rd.K);
     int nx = 0, ny = 0, nz = 0;
     double kx = 0, ky = 0, kz = 0;
     if (live) {
@@ -141,25 +143,27 @@ __global__ void __launch_bounds__(kQThreads) recip_q_kernel(const __grid_constan
     if (live) partial[(size_t)blockIdx.y * rd.K + kk] = make_double2(qr, qi);
 }
 
-// Q = (sign == 0 ? 0 : Q) +- sum over slabs, in slab order
-__global__ void recip_q_reduce_kernel(int K, int nslabs, const double2 *partial, double2 *Q, int sign) {
+// Q = (sign == 0 ? 0 : Q) +- sum over slabs, in slab order; with `mirror` also Q[K - 1 - k] from the conjugate
+__global__ void recip_q_reduce_kernel(int K, int nslabs, const double2 *partial, double2 *Q, int sign, int mirror) {
     const int kk = blockIdx.x * blockDim.x + threadIdx.x;
-    if (kk >= K) return;
+    if (kk >= (mirror ? K / 2 : K)) return;
     double sr = 0.0, si = 0.0;
     for (int s = 0; s < nslabs; s++) {
         const double2 v = partial[(size_t)s * K + kk];
         sr += v.x;
         si += v.y;
     }
+    const double sg = sign < 0 ? -1.0 : 1.0;
     double2 o = sign == 0 ? make_double2(0.0, 0.0) : Q[kk];
-    if (sign < 0) {
-        o.x -= sr;
-        o.y -= si;
-    } else {
-        o.x += sr;
-        o.y += si;
-    }
+    o.x += sg * sr;
+    o.y += sg * si;
     Q[kk] = o;
+    if (mirror) {
+        double2 m = sign == 0 ? make_double2(0.0, 0.0) : Q[K - 1 - kk];
+        m.x += sg * sr;
+        m.y -= sg * si;
+        Q[K - 1 - kk] = m;
+    }
 }
 
 // energy = 2 pi / V sum_k |Q_k|^2 A_k: one CTA, fixed order
@@ -192,26 +196,28 @@ __global__ void __launch_bounds__(128) recip_force_kernel(const __grid_constant_
     sincos(rd.two_pi_inv_box[0] * x[p], &bx.y, &bx.x);
     sincos(rd.two_pi_inv_box[1] * y[p], &by.y, &by.x);
     sincos(rd.two_pi_inv_box[2] * z[p], &bz.y, &bz.x);
-    sincos(-(double)kc * rd.two_pi_inv_box[0] * x[p], &ex.y, &ex.x);  // exp(i nx theta_x) at nx = -kc
-    sincos(-(double)kc * rd.two_pi_inv_box[1] * y[p], &ey0.y, &ey0.x);
+    sincos(-(double)kc * rd.two_pi_inv_box[1] * y[p], &ey0.y, &ey0.x); // exp(i ny theta_y) at ny = -kc
     double Fx = 0, Fy = 0, Fz = 0, Ex = 0, Ey = 0, Ez = 0;
-    for (int nx = -kc; nx <= kc; nx++, ex = cmul(ex, bx)) {
+    // The terms of k and -k are equal (conjugate phase, conjugate Q, opposite k), so only the half space nx > 0, or nx = 0 and
+    // ny > 0, or nx = ny = 0 and nz > 0 is walked and the sums are doubled.
+    ex = make_double2(1.0, 0.0);
+    for (int nx = 0; nx <= kc; nx++, ex = cmul(ex, bx)) {
         const double kx = rd.two_pi_inv_box[0] * nx;
-        double2 ey = ey0;
-        for (int ny = -kc; ny <= kc; ny++, ey = cmul(ey, by)) {
+        double2 ey = nx == 0 ? make_double2(1.0, 0.0) : ey0;
+        for (int ny = nx == 0 ? 0 : -kc; ny <= kc; ny++, ey = cmul(ey, by)) {
             const int2 r = row[(nx + kc) * side + (ny + kc)];
             if (r.y < 0) continue;
             const double ky = rd.two_pi_inv_box[1] * ny;
             const double2 exy = cmul(ex, ey);
             const double mxy = m0 * kx + m1 * ky;
-            const bool origin_col = nx == 0 && ny == 0; // the column that skips nz = 0
+            const bool origin_col = nx == 0 && ny == 0; // the column that has no nz = 0 and whose nz < 0 half is mirrored
             // k index of (nx, ny, nz): r.x + nz + nzmax, minus one past the skipped origin
             double tf = 0, te = 0, tfz = 0, tez = 0;
             double2 w = make_double2(1.0, 0.0);
             for (int m = 0; m <= r.y; m++, w = cmul(w, bz)) {
 #pragma unroll
                 for (int sgn = 1; sgn >= -1; sgn -= 2) {
-                    if (m == 0 && (sgn < 0 || origin_col)) continue;
+                    if ((m == 0 || origin_col) && (sgn < 0 || (m == 0 && origin_col))) continue;
                     const int nz = sgn * m;
                     const int idx = r.x + nz + r.y - ((origin_col && nz > 0) ? 1 : 0);
                     const double2 e = cmul(exy, make_double2(w.x, sgn * w.y));
@@ -243,6 +249,8 @@ __global__ void __launch_bounds__(128) recip_force_kernel(const __grid_constant_
             }
         }
     }
+    Fx *= 2.0; Fy *= 2.0; Fz *= 2.0;
+    Ex *= 2.0; Ey *= 2.0; Ez *= 2.0;
     if (FORCE) {
         force[3 * p + 0] = rd.prefac * Fx;
         force[3 * p + 1] = rd.prefac * Fy;
@@ -475,7 +483,8 @@ int cg_recip_update_device(cg_recip *r, int64_t n, const double *x, const double
     if ((mux || muy || muz) && !(mux && muy && muz)) return CG_ERR_INVALID;
     cudaSetDevice(r->device);
     const RecipDev rd = dev_params(r);
-    const int kblocks = (r->K + kQThreads - 1) / kQThreads;
+    const int kwork = r->lattice ? r->K / 2 : r->K;
+    const int kblocks = (kwork + kQThreads - 1) / kQThreads;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, r->device);
     // particle slabs: enough CTAs for ~4 per SM, never fewer than one tile of particles per slab
@@ -483,7 +492,7 @@ int cg_recip_update_device(cg_recip *r, int64_t n, const double *x, const double
     RC_CUDA(r, r->d_partial.ensure((size_t)nslabs * r->K));
     const size_t smem = (size_t)kTile * 3 * (r->kc + 1) * sizeof(double2) + (size_t)kTile * 4 * sizeof(double);
     recip_q_kernel<<<dim3(kblocks, nslabs), kQThreads, smem, r->stream>>>(rd, n, x, y, z, q, mux, muy, muz, r->d_partial.p);
-    recip_q_reduce_kernel<<<(r->K + 255) / 256, 256, 0, r->stream>>>(r->K, nslabs, r->d_partial.p, r->d_q.p, sign);
+    recip_q_reduce_kernel<<<(kwork + 255) / 256, 256, 0, r->stream>>>(r->K, nslabs, r->d_partial.p, r->d_q.p, sign, r->lattice);
     RC_CUDA(r, cudaGetLastError());
     return CG_OK;
 }

@@ -13,6 +13,7 @@
 #include "poisson.hpp"
 #include "qpotential.hpp"
 #include "reactionfield.hpp"
+#include "reciprocal.hpp"
 #include "splined.hpp"
 #include "wolf.hpp"
 #include "zahn.hpp"

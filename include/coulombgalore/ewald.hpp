@@ -6,7 +6,7 @@
 namespace CoulombGalore {
 
 // The reciprocal-space classes of the reference's ewald.hpp (ReciprocalEwaldState / ReciprocalEwaldGaussian, :44-94,
-// :214-385) are a k-space sum, not a pair scheme; they are outside this engine's path.
+// :214-385) live in reciprocal.hpp (a k-space sum on the GPU, not a pair scheme).
 class Ewald : public EnergyImplementation<Ewald> {
     detail::ErfcFamilySrf<detail::kEwaldPlain> plain_;
     detail::EwaldScreenedSrf screened_;
