@@ -206,16 +206,11 @@ def main():
         # the exchange step.  halo (default): every rank pulls, over NVLink peer memory, only the particles of its window;
         # peer: it pulls all of them (both are this repo's kernels); nccl: the collective library's all-gather
         xmode = os.environ.get("CG_EXCHANGE", "halo")
+        halo_reason = None
         if xmode == "halo":
-            try:
-                halo = HaloExchange(evs["wolf"], N, box, 4, dev)
-            except Exception as ex_:  # noqa: BLE001 -- no CUDA IPC here: use the collective library
-                halo, xmode, halo_reason = None, "nccl", "%s: %s" % (type(ex_).__name__, ex_)
-            ok = torch.tensor([0.0 if halo is None else 1.0], device=dev)
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-            if ok.item() < 1.0 and halo is not None:
-                halo.close()
-                halo, xmode = None, "nccl"
+            halo, halo_reason = HaloExchange.create(evs["wolf"], N, box, 4, dev)  # None where CUDA IPC is not available
+            if halo is None:
+                xmode = "nccl"
         if halo is None:
             exchange = ShardedStep(N, 4, dev) if xmode == "nccl" else PeerExchange.create(evs["wolf"], N, 4, dev)
         if halo is not None or isinstance(exchange, PeerExchange):
@@ -324,7 +319,7 @@ def main():
             halo.close()
         else:
             exchange_kind = "peer-memory pull kernel (cg_peer_gather)" if isinstance(exchange, PeerExchange) else \
-                "NCCL all-gather (%s)" % (getattr(exchange, "fallback_reason", None) or "CG_EXCHANGE=nccl")
+                "NCCL all-gather (%s)" % (getattr(exchange, "fallback_reason", None) or halo_reason or "CG_EXCHANGE=nccl")
             if isinstance(exchange, PeerExchange):
                 exchange.close()
     if rank != 0:

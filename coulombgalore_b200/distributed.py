@@ -91,11 +91,15 @@ class PeerExchange(ShardedStep):
         self.own_ptr, handles = [], []
         for _ in range(2):
             p, h = C.c_void_p(), C.create_string_buffer(64)
-            check(lib.cg_peer_alloc(self.device.index, nbytes, C.byref(p), h), "cg_peer_alloc")
+            if lib.cg_peer_alloc(self.device.index, nbytes, C.byref(p), h) != 0:
+                handles = None  # still take part in the collective below, so that no rank is left waiting
+                break
             self.own_ptr.append(p)
             handles.append(h.raw)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, handles, group=self.group)
+        if any(e is None for e in everyone):
+            raise RuntimeError("cg_peer_alloc / cudaIpcGetMemHandle failed on rank(s) %s" % [r for r, e in enumerate(everyone) if e is None])
         self.block_ptrs = []  # [buffer][rank] -> device pointer valid in this process
         self._opened = []
         for b in range(2):
@@ -208,11 +212,15 @@ class HaloExchange:
         self.own_ptr, handles = [], []
         for _ in range(2):
             p, h = C.c_void_p(), C.create_string_buffer(64)
-            check(lib.cg_peer_alloc(self.device.index, nbytes, C.byref(p), h), "cg_peer_alloc")
+            if lib.cg_peer_alloc(self.device.index, nbytes, C.byref(p), h) != 0:
+                handles = None  # still take part in the collective below, so that no rank is left waiting
+                break
             self.own_ptr.append(p)
             handles.append(h.raw)
         everyone = [None] * self.world
         dist.all_gather_object(everyone, handles, group=group)
+        if any(e is None for e in everyone):
+            raise RuntimeError("cg_peer_alloc / cudaIpcGetMemHandle failed on rank(s) %s" % [r for r, e in enumerate(everyone) if e is None])
         self.block_ptrs, self._opened = [], []
         for b in range(2):
             row = []
@@ -234,6 +242,22 @@ class HaloExchange:
         self.ids_owned = torch.arange(self.lo, self.lo + self.count, dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.step, self.n_bound = 0, None
+
+    @staticmethod
+    def create(evaluator, n_total, box, n_payload, device, group=None):
+        """HaloExchange where CUDA IPC works on every rank, else None with the reason (all ranks decide alike)."""
+        ex, reason = None, None
+        try:
+            ex = HaloExchange(evaluator, n_total, box, n_payload, device, group=group)
+        except Exception as e:  # noqa: BLE001 -- any failure means: use another exchange
+            reason = "%s: %s" % (type(e).__name__, e)
+        ok = torch.tensor([0.0 if ex is None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() < 1.0:
+            if ex is not None:
+                ex.close()
+            return None, reason or "a peer rank could not map the blocks"
+        return ex, None
 
     def gather(self, owned2d):
         """owned2d: [n_payload, count] float64 on the device (row 2 = z).  -> (list of payload arrays [bound], ids [bound],

@@ -44,7 +44,7 @@ def main():
         # CG_EXCHANGE = halo (default): pull only the particles of the rank's window; peer: pull everything (own kernel);
         # nccl: the collective library's all-gather
         mode_x = os.environ.get("CG_EXCHANGE", "halo") if world > 1 else "nccl"
-        hx = HaloExchange(ev, N, [L] * 3, len(use), dev) if mode_x == "halo" else None
+        hx = HaloExchange.create(ev, N, [L] * 3, len(use), dev)[0] if mode_x == "halo" else None
         ex = ShardedStep(N, len(use), dev) if mode_x != "peer" else PeerExchange.create(ev, N, len(use), dev)
         del arr
         f = torch.empty((N, 3), dtype=torch.float64, device=dev)
