@@ -285,7 +285,7 @@ struct PoissonSrf : SrfDefaults {
 //   lookup grid at lut_off: kSplineGrid 32-bit words, byte k of word c = the interval of table k that contains the
 //   left edge of grid cell c, i.e. a lower bound for every q in [c, c+1)/kSplineGrid; the device then advances at
 //   most `kmax` intervals with exact FP64 comparisons, which reproduces std::lower_bound bit for bit.
-constexpr int kSplineGrid = 64;
+constexpr int kSplineGrid = 256;
 
 struct SplineSrf : SrfDefaults {
     static constexpr int kTable = kTableSpline;
@@ -343,36 +343,51 @@ struct SplineSrf : SrfDefaults {
         tab = dst;
     }
 #ifdef __CUDA_ARCH__
-    // device: grid lookup + at most kmax exact comparisons, coefficients fetched as three 16-byte shared-memory loads
-    __device__ __forceinline__ double table(int k, double q, unsigned int cellword, const double *t) const {
-        const unsigned base = (unsigned)__cvta_generic_to_shared(t);
-        int pos = (int)((cellword >> (8 * k)) & 255u);
-        for (int s = 0; s < kmax; s++) {
-            const int nx = pos + 1;
-            double kn;
-            asm("ld.shared.f64 %0, [%1];" : "=d"(kn) : "r"(base + 8u * (unsigned)(koff[k] + nx)));
-            pos = (nx <= n[k] - 2 && kn < q) ? nx : pos;
-        }
-        double k0, c0, c1, c2, c3, c4, c5;
-        asm("ld.shared.f64 %0, [%1];" : "=d"(k0) : "r"(base + 8u * (unsigned)(koff[k] + pos)));
-        const unsigned ca = base + 8u * (unsigned)(coff[k] + 6 * pos);
-        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(ca));
-        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c2), "=d"(c3) : "r"(ca + 16u));
-        asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(c4), "=d"(c5) : "r"(ca + 32u));
-        const double dz = q - k0;
-        return c0 + dz * (c1 + dz * (c2 + dz * (c3 + dz * (c4 + dz * (c5)))));
-    }
+    // device: grid lookup + at most kmax exact comparisons, coefficients fetched as three 16-byte shared-memory loads.
+    // The four tables are searched and evaluated side by side (independent loads and Horner chains in flight together):
+    // the kernel is latency-bound at its occupancy, not throughput-bound.
     // (fp32 kernels evaluate the tables in fp64 and round the results: the tables are the scheme)
     template <int ND, class T = double> __device__ __forceinline__ void eval(T qin, T *s, const double *t = nullptr) const {
         const double q = (double)qin;
+        const unsigned base = (unsigned)__cvta_generic_to_shared(t);
         int c = __double2int_rd(q * (double)kSplineGrid);
         c = min(max(c, 0), kSplineGrid - 1);
         unsigned int w;
-        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((unsigned)__cvta_generic_to_shared(t) + 8u * (unsigned)lut_off + 4u * (unsigned)c));
-        s[0] = (T)table(0, q, w, t);
-        if (ND >= 1) s[1] = (T)table(1, q, w, t);
-        if (ND >= 2) s[2] = (T)table(2, q, w, t);
-        if (ND >= 3) s[3] = (T)table(3, q, w, t);
+        asm("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + 8u * (unsigned)lut_off + 4u * (unsigned)c));
+        int pos[ND + 1];
+#pragma unroll
+        for (int k = 0; k <= ND; k++) pos[k] = (int)((w >> (8 * k)) & 255u);
+        for (int st = 0; st < kmax; st++) {
+#pragma unroll
+            for (int k = 0; k <= ND; k++) {
+                const int nx = pos[k] + 1;
+                double kn;
+                asm("ld.shared.f64 %0, [%1];" : "=d"(kn) : "r"(base + 8u * (unsigned)(koff[k] + nx)));
+                pos[k] = (nx <= n[k] - 2 && kn < q) ? nx : pos[k];
+            }
+        }
+        double k0[ND + 1], cf[ND + 1][6];
+#pragma unroll
+        for (int k = 0; k <= ND; k++) {
+            asm("ld.shared.f64 %0, [%1];" : "=d"(k0[k]) : "r"(base + 8u * (unsigned)(koff[k] + pos[k])));
+            const unsigned ca = base + 8u * (unsigned)(coff[k] + 6 * pos[k]);
+            asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cf[k][0]), "=d"(cf[k][1]) : "r"(ca));
+            asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cf[k][2]), "=d"(cf[k][3]) : "r"(ca + 16u));
+            asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(cf[k][4]), "=d"(cf[k][5]) : "r"(ca + 32u));
+        }
+        double dz[ND + 1], v[ND + 1];
+#pragma unroll
+        for (int k = 0; k <= ND; k++) {
+            dz[k] = q - k0[k];
+            v[k] = cf[k][5];
+        }
+#pragma unroll
+        for (int j = 4; j >= 0; j--) {
+#pragma unroll
+            for (int k = 0; k <= ND; k++) v[k] = cf[k][j] + dz[k] * v[k]; // same Horner form as the reference, all tables in step
+        }
+#pragma unroll
+        for (int k = 0; k <= ND; k++) s[k] = (T)v[k];
     }
 #else
     inline double table(int k, double q, const double *t) const {
