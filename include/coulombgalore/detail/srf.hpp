@@ -207,8 +207,17 @@ struct EwaldScreenedSrf : SrfDefaults {
         T ecm, Em, ecp, Ep; // erfc(x-), exp(-x-^2), erfc(x+)
         erfc_and_gauss<true>(xm, ecm, Em, tab);
         erfc_and_gauss<false>(xp, ecp, Ep, tab);
+        // P = erfc(x+) exp(2 zeta q).  Since x+^2 - x-^2 = 2 zeta q, exp(2 zeta q) = exp(-x-^2) / exp(-x+^2): on the device the
+        // two Gaussians are already there, a division replaces the exponential (inside the table range, where both are
+        // accurate to a few ulp; beyond it the exponential is evaluated as the reference writes it).
+        T P;
+#ifdef __CUDA_ARCH__
+        if (xp < T(7.5)) P = ecp * (Em / Ep);
+        else P = ecp * exp_any(T(2) * Z * q);
+#else
         (void)Ep;
-        const T P = ecp * exp_any(T(2) * Z * q); // erfc(x+) exp(2 zeta q), as the reference forms it
+        P = ecp * exp_any(T(2) * Z * q);
+#endif
         s[0] = T(0.5) * (P + ecm);
         if (ND >= 1) s[1] = -K1 * Em + Z * P;
         if (ND >= 2) s[2] = T(2) * K1 * (T)eta * (xq - ZE) * Em + T(2) * (T)zeta2 * P;
