@@ -211,18 +211,18 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts
 }
 
 // i-groups: per primary cell row, ceil(count/32) groups
-__global__ void row_group_count_kernel(const __grid_constant__ SortParams sp, const int *cell_start, int *row_ngroups) {
+__global__ void row_group_count_kernel(const __grid_constant__ SortParams sp, const int *cell_start, int *row_ngroups, int gsize) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= sp.row1 - sp.row0) return;
     const int r = sp.row0 + k;
     const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
     const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
     const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
-    row_ngroups[k] = (b - a + 31) / 32;
+    row_ngroups[k] = (b - a + gsize - 1) / gsize;
 }
 
 __global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, const int *cell_start, const int *row_gstart, int2 *groups,
-                                      int ng_cap) {
+                                      int ng_cap, int gsize) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= sp.row1 - sp.row0) return;
     const int r = sp.row0 + k;
@@ -230,7 +230,7 @@ __global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, con
     const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
     const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
     int g = row_gstart[k];
-    for (int s = a; s < b && g < ng_cap; s += 32) groups[g++] = make_int2(s, min(32, b - s)); // beyond ng_cap: overflow is flagged
+    for (int s = a; s < b && g < ng_cap; s += gsize) groups[g++] = make_int2(s, min(gsize, b - s)); // beyond ng_cap: overflow is flagged
 }
 
 // ---- exclusive scan (ints): 4096 elements per block, recursive over block sums ----
@@ -343,11 +343,11 @@ __global__ void combine_kernel(int64_t len, int split, const double *part, doubl
 }
 
 // deterministic: fixed strided partial sums, then a fixed tree
-__global__ void reduce_items_kernel(const int *counts, int split, const double *item_energy, const unsigned long long *item_pairs,
-                                    double *scalars) {
+__global__ void reduce_items_kernel(const int *counts, int count_index, int split, const double *item_energy,
+                                    const unsigned long long *item_pairs, double *scalars) {
     __shared__ double se[1024];
     __shared__ unsigned long long sp[1024];
-    const int items = counts[1] * split;
+    const int items = counts[count_index] * split;
     double e = 0.0;
     unsigned long long c = 0;
     int k = threadIdx.x;
@@ -686,7 +686,10 @@ template <class T> struct DevBuf {
 // what the spatial sort of a handle produced (the arrays themselves live in the handle's DevBufs)
 struct Sorted {
     SortParams sp;
-    int ncell = 0, nrows_prim = 0, cap_sorted = 0, ng_bound = 0, ng_guess = 0;
+    int ncell = 0, nrows_prim = 0, cap_sorted = 0;
+    // two i-group tables: [0] groups of 32 entries (one particle per lane), [1] groups of 64 (ion modes: two per lane)
+    int ng_bound[2] = {0, 0}, ng_guess[2] = {0, 0};
+    bool has_groups[2] = {false, false};
     bool has_mu = false, has_quad = false, fast = false, valid = false;
     double rc = 0.0; // the cut-off the cell grid was built for
 };
@@ -714,13 +717,13 @@ struct cg_handle {
     const double *in[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // device SoA (own or caller's)
     DevBuf<double> own_in[7];
     // sorted system
-    DevBuf<int> cell_count, cell_start, scan_tmp, row_ngroups, row_gstart, orig;
+    DevBuf<int> cell_count, cell_start, scan_tmp, row_ngroups, row_gstart[2], orig;
     DevBuf<unsigned int> keys;
     DevBuf<double4> pos, mu, quad;
     const double *in_quad = nullptr; // device [n][9] (own copy or the caller's); reset by cg_set_system*
     DevBuf<double> own_quad;
     DevBuf<float4> pos32;
-    DevBuf<int2> groups;
+    DevBuf<int2> groups[2];
     DevBuf<double> minmax_partial, self_partial;
     // outputs
     DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
@@ -737,10 +740,12 @@ struct cg_handle {
         bool pbc = false;
         double box[3] = {0, 0, 0};
         int shard_rank = 0, shard_n = 1;
-        int cap_sorted = 0, last_groups = 0;
+        int cap_sorted = 0, last_groups[2] = {0, 0};
     } fast;
     bool last_overflow = false;
     Sorted sorted;
+    int last_gt = 0;
+    bool want_groups[2] = {false, false}; // i-group tables this handle's sort builds (its own modes + what borrowers asked for)
     cudaEvent_t sorted_ev = nullptr, pair_done_ev = nullptr, inputs_ev = nullptr; // inputs_ev: the host path's upload
     cg_handle *share_from = nullptr;     // cg_share_system: evaluate on that handle's sorted system
     std::vector<cg_handle *> borrowers;  // handles whose share_from is this one
@@ -893,7 +898,8 @@ int cg_destroy(cg_handle *h) {
     h->cell_start.release();
     h->scan_tmp.release();
     h->row_ngroups.release();
-    h->row_gstart.release();
+    h->row_gstart[0].release();
+    h->row_gstart[1].release();
     h->orig.release();
     h->keys.release();
     h->pos.release();
@@ -901,7 +907,8 @@ int cg_destroy(cg_handle *h) {
     h->quad.release();
     h->own_quad.release();
     h->pos32.release();
-    h->groups.release();
+    h->groups[0].release();
+    h->groups[1].release();
     h->minmax_partial.release();
     h->self_partial.release();
     h->out_force.release();
@@ -1092,7 +1099,7 @@ static void layout_grid(double rc, bool pbc, const double ext[3], double n_grid,
 }
 
 // ---- binning, spatial sort and i-groups of the handle's own system (steps 0-5); the result is described by h->sorted ----
-static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches_out) {
+static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, bool need64, int *launches_out) {
     cudaStream_t st = h->stream;
     const int n = (int)h->n;
     const double rc = h->desc.cutoff;
@@ -1149,9 +1156,9 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     if (h->counts_pending && cudaEventQuery(h->counts_ev) == cudaSuccess) { // never wait: a stale view only delays the fallback
         h->counts_pending = false;
         h->counters[0] = h->h_counts_async[0];
-        h->counters[2] = h->h_counts_async[1];
         h->last_overflow = h->h_counts_async[2] != 0;
-        h->fast.last_groups = h->h_counts_async[1];
+        h->fast.last_groups[0] = h->h_counts_async[1];
+        h->fast.last_groups[1] = h->h_counts_async[3];
         if (h->last_overflow || h->h_counts_async[0] + 1024 > h->fast.cap_sorted) h->fast.valid = false;
     }
     static const bool fast_enabled = [] {
@@ -1167,7 +1174,9 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     CG_CUDA(h, h->cell_start.ensure((size_t)ncell + 2));
     CG_CUDA(h, h->scan_tmp.ensure(4 * ((size_t)std::max(ncell, nrows_prim) / kScanTile + 8) + 64));
     CG_CUDA(h, h->row_ngroups.ensure((size_t)nrows_prim + 1));
-    CG_CUDA(h, h->row_gstart.ensure((size_t)nrows_prim + 2));
+    const bool need_groups[2] = {need32, need64};
+    for (int t = 0; t < 2; t++)
+        if (need_groups[t]) CG_CUDA(h, h->row_gstart[t].ensure((size_t)nrows_prim + 2));
     CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
     CG_CUDA(h, cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
     const int nb_p = (n + 255) / 256;
@@ -1176,28 +1185,32 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, launches_out));
     scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell, counts + 0, 0, nullptr);
     (*launches_out)++;
-    row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p);
-    (*launches_out)++;
-    CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart.p, nrows_prim, h->scan_tmp.p, st, launches_out));
-    int cap_sorted, ng_bound, ng_guess;
-    if (fast) { // array sizes and the launch shape come from the previous evaluation; no host round trip
-        cap_sorted = h->fast.cap_sorted;
-        ng_guess = h->fast.last_groups;
-        // launch bound: the last count with some room, at most the strict bound (a partial group per primary row)
-        ng_bound = std::min(n / 32 + nrows_prim + 2, ng_guess + ng_guess / 8 + 64);
-    } else {
-        ng_bound = 0x7fffffff;
+    int cap_sorted = 0, ng_bound[2] = {0, 0}, ng_guess[2] = {0, 0};
+    for (int t = 0; t < 2; t++) {
+        if (!need_groups[t]) continue;
+        const int gsize = 32 << t;
+        row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p, gsize);
+        (*launches_out)++;
+        CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart[t].p, nrows_prim, h->scan_tmp.p, st, launches_out));
+        if (fast) { // the launch shape comes from the previous evaluation: the last count with some room, at most the strict
+            ng_guess[t] = h->fast.last_groups[t]; // bound (a partial group per primary row)
+            ng_bound[t] = std::min(n / gsize + nrows_prim + 2, ng_guess[t] + ng_guess[t] / 8 + 64);
+        } else {
+            ng_bound[t] = 0x7fffffff;
+        }
+        scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart[t].p, nrows_prim, counts + (t ? 3 : 1), ng_bound[t], counts + 2);
+        (*launches_out)++;
     }
-    scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart.p, nrows_prim, counts + 1, ng_bound, counts + 2);
-    (*launches_out)++;
-    if (!fast) {
+    if (fast) { // array sizes come from the previous evaluation too; no host round trip
+        cap_sorted = h->fast.cap_sorted;
+    } else {
         CG_CUDA(h, cudaMemcpyAsync(h->h_counts, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CG_CUDA(h, cudaStreamSynchronize(st));
         const int n_sorted = h->h_counts[0];
         cap_sorted = n_sorted + n_sorted / 12 + 4096;
-        ng_bound = ng_guess = h->h_counts[1];
+        ng_bound[0] = ng_guess[0] = h->h_counts[1];
+        ng_bound[1] = ng_guess[1] = h->h_counts[3];
         h->counters[0] = n_sorted;
-        h->counters[2] = h->h_counts[1];
         h->fast.valid = h->pbc;
         h->fast.n = h->n;
         h->fast.pbc = h->pbc;
@@ -1205,7 +1218,8 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
         h->fast.shard_rank = h->shard_rank;
         h->fast.shard_n = h->shard_n;
         h->fast.cap_sorted = cap_sorted;
-        h->fast.last_groups = ng_guess;
+        h->fast.last_groups[0] = ng_guess[0];
+        h->fast.last_groups[1] = ng_guess[1];
     }
 
     // ---- 4-5. scatter, deterministic order, gather ----
@@ -1215,7 +1229,8 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     if (need_quad) CG_CUDA(h, h->quad.ensure(2 * (size_t)cap_sorted));
     CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
-    CG_CUDA(h, h->groups.ensure((size_t)ng_bound + 1));
+    for (int t = 0; t < 2; t++)
+        if (need_groups[t]) CG_CUDA(h, h->groups[t].ensure((size_t)ng_bound[t] + 1));
     CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
     bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, h->cell_start.p, h->keys.p, cap_sorted, counts);
     cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ncell, h->cell_start.p, h->keys.p, cap_sorted);
@@ -1230,8 +1245,13 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     }
     gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p,
                                                          h->orig.p, far_coord);
-    row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart.p, h->groups.p, ng_bound);
-    *launches_out += 4;
+    for (int t = 0; t < 2; t++) {
+        if (!need_groups[t]) continue;
+        row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart[t].p, h->groups[t].p,
+                                                                                     ng_bound[t], 32 << t);
+        (*launches_out)++;
+    }
+    *launches_out += 3;
     CG_CUDA(h, cudaGetLastError());
     // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
     CG_CUDA(h, cudaMemcpyAsync(h->h_counts_async, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1239,8 +1259,11 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, int *launches
     h->counts_pending = true;
     S.rc = rc;
     S.cap_sorted = cap_sorted;
-    S.ng_bound = ng_bound;
-    S.ng_guess = ng_guess;
+    for (int t = 0; t < 2; t++) {
+        S.ng_bound[t] = ng_bound[t];
+        S.ng_guess[t] = ng_guess[t];
+        S.has_groups[t] = need_groups[t];
+    }
     S.has_mu = need_mu;
     S.has_quad = need_quad;
     S.fast = fast;
@@ -1276,6 +1299,8 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
 
     // ---- 0-5. the sorted system: the handle's own, or borrowed from the handle named by cg_share_system ----
     cg_handle *s = h->share_from ? h->share_from : h;
+    // i-group table: ion modes put two particles on a lane (groups of 64 entries), the others one (groups of 32)
+    const int gt = (mode == CG_MODE_ION && CG_IPL == 2) ? 1 : 0;
     if (s == h) {
         const bool need_mu = h->in[4] != nullptr && (mode != CG_MODE_ION || !h->borrowers.empty());
         const bool need_quad = h->in_quad != nullptr && (mode == CG_MODE_MULTIPOLE_QUAD || !h->borrowers.empty());
@@ -1287,7 +1312,9 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
             h->err = "CG_MODE_MULTIPOLE_QUAD without quadrupoles: call cg_set_quadrupoles after cg_set_system";
             return CG_ERR_STATE;
         }
-        const int rcs = sort_system(h, need_mu, need_quad, &launches);
+        // a lender builds both tables once a borrower has asked for the other one
+        h->want_groups[gt] = true;
+        const int rcs = sort_system(h, need_mu, need_quad, h->want_groups[0], h->want_groups[1], &launches);
         if (rcs != CG_OK) return rcs;
     } else {
         if (!s->sorted.valid || s->sorted.rc != D.cutoff) {
@@ -1302,11 +1329,20 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
             h->err = "cg_share_system: the source handle's system has no quadrupoles";
             return CG_ERR_STATE;
         }
+        if (!s->sorted.has_groups[gt]) { // the lender sorted for another mode: have it build this group table as well
+            s->want_groups[gt] = true;
+            int l = 0;
+            const int rcs = sort_system(s, s->sorted.has_mu, s->sorted.has_quad, s->want_groups[0], s->want_groups[1], &l);
+            if (rcs != CG_OK) {
+                h->err = s->err;
+                return rcs;
+            }
+        }
         CG_CUDA(h, cudaStreamWaitEvent(st, s->sorted_ev, 0));
     }
     const Sorted &S = s->sorted;
     const SortParams &sp = S.sp;
-    const int ncell = S.ncell, cap_sorted = S.cap_sorted, ng_bound = S.ng_bound, ng_guess = S.ng_guess;
+    const int ncell = S.ncell, cap_sorted = S.cap_sorted, ng_bound = S.ng_bound[gt], ng_guess = S.ng_guess[gt];
     const bool need_mu = mode != CG_MODE_ION, fast = S.fast;
     int *counts = s->d_counts.p;
     CG_CUDA(h, cudaEventRecord(h->ev[1], st));
@@ -1345,7 +1381,8 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     kp.pos32 = s->pos32.p;
     kp.orig = s->orig.p;
     kp.cell_start = s->cell_start.p;
-    kp.groups = s->groups.p;
+    kp.groups = s->groups[gt].p;
+    kp.count_index = gt ? 3 : 1;
     kp.group_begin = 0;
     kp.group_end = ng_bound;
     kp.counts = counts;
@@ -1458,11 +1495,13 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
             launches++;
         }
     }
-    reduce_items_kernel<<<1, 1024, 0, st>>>(counts, split, h->item_energy.p, h->item_pairs.p, d_scalars);
+    reduce_items_kernel<<<1, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_energy.p, h->item_pairs.p, d_scalars);
     launches++;
     CG_CUDA(h, cudaGetLastError());
     CG_CUDA(h, cudaEventRecord(h->ev[3], st));
     h->counters[1] = ncell;
+    h->counters[2] = ng_guess;
+    h->last_gt = gt;
     h->counters[3] = pair_launches;
     h->counters[4] = launches;
     h->counters[5] = split;
@@ -1527,7 +1566,7 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
         s->fast.valid = false;
         if (s != h) { // borrowed arrays: sort the lender's system again, exactly
             int l = 0;
-            const int rcs = sort_system(s, s->sorted.has_mu, s->sorted.has_quad, &l);
+            const int rcs = sort_system(s, s->sorted.has_mu, s->sorted.has_quad, s->want_groups[0], s->want_groups[1], &l);
             if (rcs != CG_OK) {
                 h->err = s->err;
                 return rcs;
@@ -1688,7 +1727,7 @@ int cg_last_counters(cg_handle *h, int64_t c[8]) {
     if (!h || !c) return CG_ERR_INVALID;
     if (h->counts_pending && cudaEventQuery(h->counts_ev) == cudaSuccess) {
         h->counters[0] = h->h_counts_async[0];
-        h->counters[2] = h->h_counts_async[1];
+        h->counters[2] = h->h_counts_async[h->last_gt ? 3 : 1];
     }
     for (int k = 0; k < 8; k++) c[k] = h->counters[k];
     return CG_OK;

@@ -23,6 +23,11 @@ namespace cgd = CoulombGalore::detail;
 #ifndef CG_SLOTS
 #define CG_SLOTS 40
 #endif
+// i-particles per lane in the ion modes (pair_kernel.cuh: particles_per_lane); decides which i-group table they use.
+// 2 was measured and rejected (see pair_kernel.cuh); the code path stays as a tuning build (-DCG_IPL=2).
+#ifndef CG_IPL
+#define CG_IPL 1
+#endif
 constexpr int kWarpsPerCta = CG_WARPS;
 constexpr int kThreads = kWarpsPerCta * 32;
 constexpr int kSlots = CG_SLOTS; // candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase
@@ -37,7 +42,8 @@ struct KParams {
     const float4 *pos32;  // position relative to the grid origin in fp32, w = |xyz|^2   [n_sorted]
     const int *orig;      // original particle index of a sorted entry               [n_sorted]
     const int *cell_start; // first sorted entry of each cell, x fastest             [ncell + 1]
-    const int2 *groups;   // i-groups: (first sorted entry, count <= 32); a group never crosses a cell row
+    const int2 *groups;   // i-groups: (first sorted entry, count <= 32 * particles per lane); a group never crosses a cell row
+    int count_index;      // which of the device counts is the number of these groups (1: groups of 32, 3: groups of 64)
     int group_begin, group_end; // shard of groups this launch evaluates
     int split;            // j-split factor: work item = (group, s), s in [0, split)
     int nx, ny, nz;       // cells per dimension (ghost layers included; nz = the shard's layer window)
@@ -50,7 +56,7 @@ struct KParams {
     double rc2_safe;      // cutoff_squared / 4 (1 for Plain): the r2 a lane without work feeds to the branch-free arithmetic
     cgd::CoreParams core;
     int n;                // number of (original) particles
-    const int *counts;    // device counts of this evaluation: [0] sorted entries, [1] i-groups, [2] overflow flag
+    const int *counts;    // device counts of this evaluation: [0] sorted entries, [1] i-groups of 32, [2] overflow flag, [3] i-groups of 64
     int cap_sorted;       // capacity of the sorted arrays (the far-away dummy entry sits at min(counts[0], cap_sorted - 1))
     // outputs, indexed by original particle index; with split > 1 they are [split][n] partial buffers
     double *force, *field, *potential;
