@@ -27,8 +27,9 @@ constexpr double kErfcTableStep = 1.0 / 128.0;
 #ifdef __CUDACC__
 // Polynomial coefficients live in constant memory: an FP64 instruction can take a constant-bank operand directly,
 // whereas a 64-bit literal costs two extra uniform moves per use (measured: 12 % of all issued instructions).
-static __device__ __constant__ double cg_specfun_c[8] = {-1.0 / 5040.0, 1.0 / 720.0, -1.0 / 120.0, 1.0 / 24.0,
-                                                         -1.0 / 6.0,    1.0 / 6.0,   0.4,          -0.56418958354775628695}; // last: -1/sqrt(pi)
+static __device__ __constant__ double cg_specfun_c[10] = {-1.0 / 5040.0, 1.0 / 720.0, -1.0 / 120.0, 1.0 / 24.0,
+                                                          -1.0 / 6.0,    1.0 / 6.0,   0.4,          -0.56418958354775628695, // -1/sqrt(pi)
+                                                          0.375,         128.0}; // Halley coefficient, table steps per unit
 #endif
 
 #ifdef __CUDA_ARCH__
@@ -37,7 +38,7 @@ __device__ __forceinline__ double rsqrt_device(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x * y, y, 1.0);
-    return fma(y * e, fma(0.375, e, 0.5), y);
+    return fma(y * e, fma(cg_specfun_c[8], e, 0.5), y);
 }
 
 // ec = erfc(x), E = exp(-x^2) for x >= 0 from the shared-memory table `tab` (interleaved {erfc(x_k), exp(-x_k^2)}).
@@ -45,9 +46,9 @@ __device__ __forceinline__ double rsqrt_device(double x) {
 // around the argument's own grid point, which returns values of that same negligible magnitude.
 __device__ __forceinline__ void erfc_gauss_table(double x, const double *tab, double &ec, double &E) {
     const double magic = 6755399441055744.0; // 2^52 + 2^51: the low word of (x*128 + magic) is round(x*128)
-    const double t = fma(x, kErfcTableInvStep, magic);
-    const int kraw = __double2loint(t);
-    const int k = min(max(kraw, 0), kErfcTableEntries - 1);
+    const double t = fma(x, cg_specfun_c[9], magic);
+    // x >= 0: one unsigned min clamps the index (a negative low word would read as huge and clamp too)
+    const int k = (int)min((unsigned)__double2loint(t), (unsigned)(kErfcTableEntries - 1));
     const double kf = t - magic;
     const double d = fma(kf, -kErfcTableStep, x); // x - x_k, exact
     const double xk = kf * kErfcTableStep;

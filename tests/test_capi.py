@@ -83,3 +83,28 @@ def test_missing_library_fails_loudly():
     code = "import os; os.environ['CG_B200_LIB']='/nonexistent/libcg_b200.so'; import coulombgalore_b200"
     r = subprocess.run(["python", "-c", code], cwd=ROOT, capture_output=True, text=True)
     assert r.returncode != 0 and "is missing" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_client_evaluates_on_the_gpu():
+    out = _run_c_client()
+    assert "pairs = 6" in out
+
+
+def test_c_client_links_and_runs():
+    """A C99 program against the shared library: descriptor constructors, the factory, cg_srf_host; cg_create refuses
+    without a GPU (and on a GPU box the same program uploads three charges and evaluates them)."""
+    assert "coulombgalore_b200" in _run_c_client()
+
+
+def _run_c_client():
+    import tempfile
+    lib_dir = os.path.join(ROOT, "coulombgalore_b200")
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "abi_probe")
+        subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                               os.path.join(ROOT, "tests", "c", "abi_probe.c"), "-o", exe, "-L" + lib_dir, "-l:libcg_b200.so",
+                               "-Wl,-rpath," + lib_dir, "-lm"])
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+        return out.stdout
