@@ -162,3 +162,74 @@ def test_fp32_variant(name, oracle_kind):
         bad = {k: v for k, v in errs.items() if not (v <= 1.0)}
         assert not bad, errs
         assert max(errs.values()) > 1e-6  # and it really is single precision
+
+
+@pytest.mark.parametrize("seed", range(64))
+def test_random_small_systems(seed, oracle_kind):
+    """Randomised configurations: odd particle counts, non-cubic boxes down to one cut-off per side (every particle then
+    meets images of itself and of its neighbours), particles on the box faces, clustered open systems, random scheme, mode
+    and output mask."""
+    rng = np.random.default_rng(1000 + seed)
+    names = sorted(zoo().keys())
+    name = names[int(rng.integers(len(names)))]
+    mk, p = zoo()[name]
+    pot = mk()
+    rc = pot.cutoff
+    pbc = bool(rng.random() < 0.6) and rc < 1e10
+    n = int(rng.integers(1, 400))
+    if pbc:
+        box = [float(rc * rng.uniform(1.0, 3.5)) for _ in range(3)]
+        pos = [rng.uniform(0.0, b, n) for b in box]
+        for k in range(3):  # some particles exactly on the lower face and one ulp below the upper one
+            if n > 4:
+                pos[k][0] = 0.0
+                pos[k][1] = np.nextafter(box[k], 0.0)
+    else:
+        box = [100.0, 100.0, 100.0]
+        rcl = min(rc, 14.0)
+        centres = rng.uniform(-50.0, 50.0, (3, 3))
+        pick = rng.integers(0, 3, n)
+        pos = [centres[pick, k] + rng.normal(scale=0.6 * rcl, size=n) for k in range(3)]
+    # keep pairs apart (the reference diverges at r -> 0): reject near-duplicates
+    P = np.stack(pos, axis=1)
+    keep = np.ones(n, dtype=bool)
+    for i in range(n):
+        if keep[i]:
+            d = P[i + 1:] - P[i]
+            if pbc:
+                d -= np.round(d / np.array(box)) * np.array(box)
+            keep[i + 1:] &= np.einsum("ij,ij->i", d, d) > 0.25
+    x, y, z = (np.ascontiguousarray(a[keep]) for a in pos)
+    n = x.size
+    q = rng.choice([-1.0, 1.0, 0.5, 2.0], n)
+    mu = tuple(rng.normal(size=n) for _ in range(3))
+    mode = int(rng.integers(0, 3))
+    what = int(rng.integers(1, 16))
+    g, r = run_case(pot, O.Scheme(p, oracle_kind), x, y, z, q, mu, box, pbc, mode, what)
+    assert_parity(compare(g, r, what))
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shard_counts_tile_the_system(seed, oracle_kind):
+    """Any number of shards (also more shards than cell rows have work) tiles the evaluation: pair counts and energies add up,
+    every particle's outputs come from exactly one shard."""
+    rng = np.random.default_rng(500 + seed)
+    name = ["wolf", "reactionfield", "poisson43", "qpotential3"][seed % 4]
+    mk, p = zoo()[name]
+    rc = mk().cutoff
+    n = int(rng.integers(50, 3000))
+    box = [float(rc * rng.uniform(1.5, 4.0)) for _ in range(3)]
+    x, y, z = (rng.uniform(0.0, b, n) for b in box)
+    q = rng.choice([-1.0, 1.0], n)
+    mu = tuple(rng.normal(size=n) for _ in range(3))
+    mode = [cg.MODE_ION, cg.MODE_DIPOLE, cg.MODE_MULTIPOLE][seed % 3]
+    w = cg.ENERGY | cg.FORCE
+    full, ref = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, box, True, mode, w)
+    R = int(rng.choice([2, 3, 5, 7, 16]))
+    parts = [run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, box, True, mode, w, shard=(r, R))[0] for r in range(R)]
+    assert sum(pt["pairs"] for pt in parts) == full["pairs"] == ref["pairs"]
+    assert abs(sum(pt["energy"] for pt in parts) - ref["energy"]) <= TOL * max(ref["energy_abs"], 1e-300)
+    fsum = sum(pt["force"] for pt in parts)
+    assert np.max(np.linalg.norm(fsum - ref["force"], axis=1) / np.maximum(ref["force_scale"], 1e-300)) <= TOL
+    owners = sum((np.abs(pt["force"]).sum(axis=1) > 0).astype(int) for pt in parts)
+    assert owners.max() <= 1
