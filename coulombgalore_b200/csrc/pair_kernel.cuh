@@ -67,6 +67,40 @@ template <int MODE> constexpr int pairs_in_flight() {
     return MODE == cgd::kModeIon ? (particles_per_lane<MODE>() > 1 ? 1 : CG_ILP) : CG_ILP_DIP;
 }
 
+// ---- tensor-core prefilter (CG_MMA_PREFILTER, default on; ion and dipole kernels) ----
+// The distance test of 32 i-particles against 32 candidates is a 32 x 32 x 5 product: D[i][c] = |c'|^2 - 2 x'_i . c' - thr'_i
+// (coordinates relative to the group centre), negative <=> candidate inside the margin-widened cut-off.  Eight TF32
+// mma.sync.m16n8k8 per batch replace 32 broadcast shared-memory loads and 128 FFMA/FADD; the 2^-11 operand rounding is covered by
+// a per-group margin (false positives, ~1 % more phase-2 steps, fall to the exact FP64 gate).  Measured: Wolf N = 10^6 1.955 ->
+// 1.865 ms, ReactionField dipoles 0.653 -> 0.625 ms; the multipole kernels are register-bound and keep the FFMA prefilter.
+#ifndef CG_MMA_PREFILTER
+#define CG_MMA_PREFILTER 1
+#endif
+__device__ __forceinline__ unsigned to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const unsigned (&a)[4], unsigned b0, unsigned b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.0f));
+}
+// bit b of a hit mask <-> candidate index within the batch
+template <bool MMA> __device__ __forceinline__ int mask_bit_to_candidate(int b) {
+    if (MMA) return ((b & 6) << 2) | ((b >> 3) << 1) | (b & 1); // b = 8 t + 2 nt + cp  <->  candidate 8 nt + 2 t + cp
+    return b ^ 7;
+}
+template <bool MMA> __device__ __forceinline__ unsigned candidate_to_mask_bit(unsigned c) {
+    if (MMA) return (((c >> 1) & 3u) << 3) | ((c >> 3) << 1) | (c & 1u);
+    return c ^ 7u;
+}
+// which kernels use it: the light ones (ion and dipole modes), where the prefilter is a visible share of the instructions; the
+// multipole kernels are register-bound and lose more to the fragment registers than they gain (measured)
+template <int MODE> constexpr bool mma_prefilter() {
+    return CG_MMA_PREFILTER != 0 && particles_per_lane<MODE>() == 1 && (MODE == cgd::kModeIon || MODE == cgd::kModeDipole);
+}
+
 // T = double: the fp64 path (parity 1e-12).  T = float (CG_FP32): positions, the distance vector and the exact gate stay
 // fp64, the pair arithmetic incl. S(q) runs in fp32, per-chunk fp32 partial sums are folded into fp64 accumulators.
 template <class F, bool YUK, int MODE, int WHAT, class T>
@@ -144,6 +178,37 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     zmin = __int_as_float(__reduce_min_sync(full, __float_as_int(zmin)));
     zmax = __int_as_float(__reduce_max_sync(full, __float_as_int(zmax)));
 
+    constexpr bool kMma = mma_prefilter<MODE>();
+    // A fragments: row = i-particle, k = (-2x', -2y', -2z', 1, -thr', 0, 0, 0), coordinates relative to the group centre
+    const int fg = lane >> 2, ft = lane & 3;
+    const float Ox = 0.5f * (xmin + xmax), Oy = 0.5f * (ymin + ymax), Oz = 0.5f * (zmin + zmax);
+    unsigned afrag[2][4] = {{0u, 0u, 0u, 0u}, {0u, 0u, 0u, 0u}};
+    float Ot = 0.0f;
+    if constexpr (kMma) {
+        const float4 pf0 = p.pos32[iN[0]];
+        const float xr = pf0.x - Ox, yr = pf0.y - Oy, zr = pf0.z - Oz;
+        // operand rounding (2^-11 relative each, cvt.rna): |c'|^2, the three products twice, thr'
+        const float hx = 0.5f * (xmax - xmin), hy = 0.5f * (ymax - ymin), hz = 0.5f * (zmax - zmin);
+        const float X = sqrtf(hx * hx + hy * hy + hz * hz), R = X + p.rc_m + 1e-3f;
+        const float tf_margin = 1.25f * 4.8828125e-4f * (R * R + 4.0f * R * X + (float)p.rc2_m + X * X);
+        const float thrp = act[0] ? (float)(p.rc2_m - ((double)xr * xr + (double)yr * yr + (double)zr * zr)) + tf_margin : -INFINITY;
+        const float comp[4] = {-2.0f * xr, -2.0f * yr, -2.0f * zr, 1.0f};
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+#pragma unroll
+            for (int hh_ = 0; hh_ < 2; hh_++) {
+                const int src = 16 * mt + 8 * hh_ + fg;
+                const float v0 = __shfl_sync(full, comp[0], src), v1 = __shfl_sync(full, comp[1], src);
+                const float v2 = __shfl_sync(full, comp[2], src), v3 = __shfl_sync(full, comp[3], src);
+                const float th = __shfl_sync(full, thrp, src);
+                const float vt = ft == 0 ? v0 : (ft == 1 ? v1 : (ft == 2 ? v2 : v3));
+                afrag[mt][hh_] = to_tf32(vt);                       // a0 / a1: (row g [+8], col t)
+                afrag[mt][2 + hh_] = ft == 0 ? to_tf32(-th) : 0u;   // a2 / a3: (row g [+8], col t + 4)
+            }
+        }
+        Ot = ft == 0 ? Ox : (ft == 1 ? Oy : (ft == 2 ? Oz : 0.0f));
+    }
+    const unsigned bone = ft == 0 ? to_tf32(1.0f) : 0u; // B row 4: the column of ones that picks up -thr'
     const float rcm = p.rc_m;
     const int cy0 = clampi((int)floorf((ymin - rcm) * p.inv_cs_y - p.slack), 0, p.ny - 1);
     const int cy1 = clampi((int)floorf((ymax + rcm) * p.inv_cs_y + p.slack), 0, p.ny - 1);
@@ -210,14 +275,62 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     // software pipeline: the coordinates of the NEXT batch are in flight while the current one is tested
     int nj0 = 0, nn = 0;
     bool nvalid = next_batch(nj0, nn);
+    float bpre[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     float4 cpre = sentinel;
-    if (nvalid && lane < nn) cpre = p.pos32[nj0 + lane];
+    if constexpr (kMma) {
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+            bpre[nt] = (nvalid && 8 * nt + fg < nn && ft < 3) ? reinterpret_cast<const float *>(p.pos32 + nj0)[32 * nt + lane] : 0.0f;
+    } else {
+        if (nvalid && lane < nn) cpre = p.pos32[nj0 + lane];
+    }
 
     while (nvalid) {
         // ================= PHASE 1: prefilter up to kSlots batches of 32 candidates into bit masks =================
         int nb = 0, cnt = 0, qn = 0;
         while (nb < kSlots && nvalid) {
             const int j0 = nj0, n = nn;
+            unsigned m = 0u;
+            if constexpr (kMma) {
+            // B fragments straight from global memory: lane (g, t) holds component t of candidate 8 nt + g; the float4
+            // array read as floats makes that one coalesced 128-byte load per n-tile
+            float braw[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) braw[nt] = bpre[nt];
+            nvalid = next_batch(nj0, nn);
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+                bpre[nt] = (nvalid && 8 * nt + fg < nn && ft < 3) ? reinterpret_cast<const float *>(p.pos32 + nj0)[32 * nt + lane] : 0.0f;
+            unsigned W = 0u;
+            float dres[2][4][4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const float cr = braw[nt] - Ot;              // recentred component (t < 3)
+                float sq = ft < 3 ? cr * cr : 0.0f;
+                sq += __shfl_xor_sync(full, sq, 1);
+                sq += __shfl_xor_sync(full, sq, 2);          // |c'|^2 in all four lanes of the quad
+                const bool live = 8 * nt + fg < n;
+                const unsigned b0 = to_tf32(ft == 3 ? (live ? sq : INFINITY) : cr);
+                mma_tf32_16x8x8(dres[0][nt], afrag[0], b0, bone);
+                mma_tf32_16x8x8(dres[1][nt], afrag[1], b0, bone);
+            }
+            // sign bits -> one word per lane: byte k = 2 mt + h (row 16 mt + 8 h + g), bit 2 nt + cp (candidate 8 nt + 2 t + cp);
+            // four independent funnel-shift chains (one per byte), then one merge
+            unsigned wb[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int nt = 3; nt >= 0; nt--)
+#pragma unroll
+                for (int cp = 1; cp >= 0; cp--)
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) wb[kk] = __funnelshift_l(__float_as_uint(dres[kk >> 1][nt][2 * (kk & 1) + cp]), wb[kk], 1);
+            W = wb[0] | (wb[1] << 8) | (wb[2] << 16) | (wb[3] << 24);
+            // particle `lane` lives in row byte lane / 8 of the four lanes of quad lane % 8
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const unsigned w = __shfl_sync(full, W, 4 * (lane & 7) + t);
+                m |= ((w >> (8 * (lane >> 3))) & 255u) << (8 * t);
+            }
+            } else {
             const float4 c = cpre;
             nvalid = next_batch(nj0, nn);
             cpre = sentinel;
@@ -227,7 +340,6 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             __syncwarp();
             // candidate t0+u lands in bit t0 + 7 - u: the sign bit of (v - thr) is funnel-shifted into the mask
             // (one ALU instruction per test; NaN from the inf sentinel has a clear sign bit, i.e. does not pass)
-            unsigned m = 0;
 #pragma unroll 1
             for (int t0 = 0; t0 < n; t0 += 8) {
                 unsigned m8 = 0;
@@ -242,9 +354,10 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                 }
                 m |= m8 << t0;
             }
+            }
             if constexpr (kIPL == 1) { // the lane's own entry is not a neighbour (with two particles per lane each is the
                 const unsigned rel_self = (unsigned)(i - j0); // other's neighbour: the index check moves to phase 2)
-                if (rel_self < 32u) m &= ~(1u << (rel_self ^ 7u));
+                if (rel_self < 32u) m &= ~(1u << candidate_to_mask_bit<kMma>(rel_self));
             }
             if (m != 0u) hits[(qn++) * 32] = make_uint2(m, (unsigned)j0);
             cnt += __popc(m);
@@ -269,7 +382,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         auto pop = [&](bool &has) -> int {
             has = cnt > 0;
             const int b = 31 - __clz((int)cur); // highest set bit (-1 when empty)
-            const int j = has ? base + (b ^ 7) : dummy;
+            const int j = has ? base + mask_bit_to_candidate<kMma>(b) : dummy;
             cur &= ~(has ? (1u << b) : 0u);
             cnt -= has ? 1 : 0;
             if (cur == 0u && cnt > 0) {
