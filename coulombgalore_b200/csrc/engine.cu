@@ -10,6 +10,11 @@
 //                     deterministic (ascending key), so results are bit-reproducible run to run
 //   5. gather         SoA inputs -> sorted AoS double4 {x,y,z,q}, double4 {mu,0}, float4 (relative, for the prefilter)
 //   6. pair_kernel    (pair_kernel.cuh)  7. combine (j-split only)  8. reduce_items -> U and pair count
+// Steps 1-5 are sort_system(): sizes and launch bounds come from the previous evaluation once a system shape is known (no host
+// round trip; overflow is flagged on the device and repaired by the host entry points), shards bin only their window of cell
+// layers, and handles of other schemes with the same cut-off can borrow the result (cg_share_system).
+// Also here: the O(N) terms (self-energy, neutralisation, torque), the peer-memory exchange kernels of the multi-GPU step
+// (cg_peer_gather, cg_halo_publish / cg_halo_pull) and the probes.  Reciprocal-space Ewald lives in recip.cu.
 #include <cuda_runtime.h>
 
 #include <algorithm>

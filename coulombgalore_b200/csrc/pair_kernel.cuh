@@ -1,5 +1,6 @@
-// pair_kernel.cuh -- the sm_100a pair-interaction kernel (FP64-pipe bound; no tensor cores: the work is
-// elementwise transcendental/polynomial math per pair, not a contraction).
+// pair_kernel.cuh -- the sm_100a pair-interaction kernel.  The pair arithmetic is elementwise transcendental / polynomial FP64
+// math (FP64 pipe); the one dense product of the path, the 32 x 32 distance test of the prefilter, runs on the tensor cores in
+// the ion and dipole kernels.
 //
 // Work decomposition
 //   * one warp per work item = (i-group, j-split slice); an i-group is <= 32 spatially adjacent particles of one
@@ -7,12 +8,13 @@
 //   * the candidate j's are the particles of every cell that intersects the group's bounding box grown by the
 //     cut-off; cells are stored x-fastest so each (y,z) cell row contributes ONE contiguous run of sorted entries.
 //     The run table is built 32 rows at a time, one row per lane, with rounded-corner culling in the y-z plane;
-//   * PHASE 1 (FP32/ALU pipes): candidates stream through shared memory 32 at a time (one coalesced 16 B load per
-//     lane, then 32 broadcast LDS.128).  Each lane tests every candidate against its own particle with three FFMAs,
-//           |c|^2 - 2 c.x_i  <  rc^2 + margin - |x_i|^2      (|c|^2 is precomputed by the sort, margin covers fp32 rounding)
-//     and records the outcome as one bit of a 32-bit mask per batch -- a conservative prefilter, so the FP64 pipe
-//     never sees the ~80 % of candidates that are out of range.  Non-empty masks of up to kSlots batches are parked
-//     in a per-lane list in shared memory (deferred evaluation);
+//   * PHASE 1 (prefilter): candidates are tested 32 at a time against all particles of the group,
+//           |c|^2 - 2 c.x_i  <  rc^2 + margin - |x_i|^2      (margin covers the rounding of the test's arithmetic)
+//     either as eight TF32 mma.sync.m16n8k8 per batch (operands relative to the group centre, B fragments loaded coalesced
+//     from the float4 array, results packed and transposed to one 32-bit mask per particle) or, in the register-bound
+//     multipole kernels, with three FFMAs per test on candidates broadcast from a shared-memory stage.  Either way the test
+//     is conservative, so the FP64 pipe never sees the ~80 % of candidates that are out of range.  Non-empty masks of up to
+//     kSlots batches are parked in a per-lane list in shared memory (deferred evaluation);
 //   * PHASE 2 (FP64 pipe): every lane walks the set bits of its own masks.  All lanes hold work until the lane
 //     with the fewest hits runs dry, so the expensive FP64 pair arithmetic runs with (nearly) all lanes busy instead
 //     of at the ~15-25 % in-cut-off hit rate a branch-per-candidate loop would give.  The evaluation re-tests the

@@ -208,7 +208,8 @@ int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out);
  * ms[0] binning+sort+reorder, ms[1] pair kernel(s), ms[2] reductions/epilogue, ms[3] whole step */
 int cg_last_timings(cg_handle *h, double ms[4]);
 /* counters of the last evaluation: [0] sorted entries incl. periodic images, [1] cells, [2] i-groups,
- * [3] pair-kernel launches, [4] total kernel launches, [5] j-split factor, [6] candidate tests (if counted) */
+ * [3] pair-kernel launches, [4] total kernel launches, [5] j-split factor, [6] 1 if the evaluation took the sync-free path
+ * (sizes from the previous evaluation, no host round trip), [7] work items of the pair kernel */
 int cg_last_counters(cg_handle *h, int64_t c[8]);
 
 /* Exchange step over peer memory, one process per GPU: each rank keeps its owned particles in a block
