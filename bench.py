@@ -121,6 +121,7 @@ def cpu_reference_rate(kind, n_side, target_seconds, nthreads=0):
     if m2 > m:
         pairs, dt = run(m2)
         m = m2
+    cpu_reference_rate.last_seconds = dt
     return pairs / dt, cores, "first %d of %d i-particles, Wolf + Fennell force, %.1f s incl. cell-list build" % (m, N, dt), schemes[0].kind
 
 
@@ -148,16 +149,18 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        per_step = []
+        per_step, step_ms = [], []
         sample = kind = ""
         cores = 0
         for s in range(args.warmup + args.steps):
             rate, cores, sample, kind = cpu_reference_rate(okind, n_side, 4.0)
             if s >= args.warmup:
                 per_step.append(rate)
+                step_ms.append(1e3 * cpu_reference_rate.last_seconds)
         v = statistics.mean(per_step)
         line = {"impl": "reference", "metric": "pair interactions/s (fp64)", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.mean(step_ms),  # one step = one bounded sample
+                "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference" if kind == "reference" else "port",
                                  "sample": sample},
