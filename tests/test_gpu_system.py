@@ -372,3 +372,29 @@ def test_reciprocal_ewald_against_oracle_golden_and_reference_kats(oracle_kind):
         g.close()
     for p_ in (pot, pot1, p0):
         p_.close()
+
+
+def test_full_ewald_sum_of_the_reference_test_case():
+    """All pieces together on the reference's Ewald test system (test/unittests.cpp:559-605: charges +1 / -1 one length unit
+    apart in a 10^3 box, R_c = 5, alpha = 0.8, k_c = 11, conducting boundary): real-space pairs (batched evaluator, periodic),
+    self-energy (O(N) terms), reciprocal and surface energy add up to the reference's total -1.0021255, and the total force on
+    the first charge to 0.9956865."""
+    pos = np.array([[-0.5, 0.0, 0.0], [0.5, 0.0, 0.0]]) + 5.0  # inside the periodic box [0, 10)^3
+    q, mu = np.array([1.0, -1.0]), np.zeros((2, 3))
+    st = cg.ReciprocalEwaldState(box_length=[10.0] * 3, cutoff=5.0, reciprocal_cutoff=11, alpha=0.8, surface_dielectric_constant=np.inf)
+    rec = cg.ReciprocalEwaldGaussian(st)
+    rec.updateComplex(pos, q, mu)
+    ev = cg.BatchedEvaluator(rec.real_space)
+    ev.set_system(pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), q, None, [10.0] * 3, True)
+    real = ev.eval(cg.MODE_ION, cg.ENERGY | cg.FORCE)
+    self_terms = ev.self_terms()
+    assert real["pairs"] == 2                                                     # the direct pair only: images are 9 away
+    assert real["energy"] == pytest.approx(-0.2578990353, rel=1e-8)              # :578
+    assert self_terms["self_energy"] == pytest.approx(-0.9027033337, rel=1e-8)   # :579
+    total = real["energy"] + self_terms["self_energy"] + rec.surface_energy(pos, q, mu) + rec.reciprocal_energy()
+    assert total == pytest.approx(-1.0021255, rel=1e-7)                          # :582
+    # force on the first charge: real + reciprocal (+ zero surface term); the reference quotes the x component
+    f = real["force"][0] + rec.reciprocal_force(pos, q, mu)[0] + rec.surface_force(pos, q, mu, q[0])
+    assert f[0] == pytest.approx(0.9956865, rel=1e-6) and abs(f[1]) < 1e-12 and abs(f[2]) < 1e-12   # :594
+    ev.close()
+    rec.close()
