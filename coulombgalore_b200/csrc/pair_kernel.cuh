@@ -100,7 +100,11 @@ template <bool MMA> __device__ __forceinline__ unsigned candidate_to_mask_bit(un
 // which kernels use it: the light ones (ion and dipole modes), where the prefilter is a visible share of the instructions; the
 // multipole kernels are register-bound and lose more to the fragment registers than they gain (measured)
 template <int MODE> constexpr bool mma_prefilter() {
-    return CG_MMA_PREFILTER != 0 && particles_per_lane<MODE>() == 1 && (MODE == cgd::kModeIon || MODE == cgd::kModeDipole);
+#ifndef CG_MMA_ALL_MODES
+#define CG_MMA_ALL_MODES 0
+#endif
+    return CG_MMA_PREFILTER != 0 && particles_per_lane<MODE>() == 1 &&
+           (CG_MMA_ALL_MODES != 0 || MODE == cgd::kModeIon || MODE == cgd::kModeDipole);
 }
 
 // T = double: the fp64 path (parity 1e-12).  T = float (CG_FP32): positions, the distance vector and the exact gate stay
