@@ -1833,6 +1833,29 @@ int cg_shard_window(cg_handle *h, const double *box, int rank, int nranks, int64
     return CG_OK;
 }
 
+// host-only view of the layout a shard would use (no handle, no GPU): for tests and for callers that plan the exchange
+// out_i: nprim[3], ghost[3], row0, row1, z0, nzl;  out_d: cell size[3], window[2]
+int cg_layout_probe(double cutoff, const double *box, int pbc, int rank, int nranks, int64_t n_global, int out_i[10], double out_d[5]) {
+    if (!(cutoff > 0.0) || !box || !out_i || !out_d || nranks < 1 || rank < 0 || rank >= nranks || n_global < 1) return CG_ERR_INVALID;
+    SortParams sp;
+    std::memset(&sp, 0, sizeof(sp));
+    const double ext[3] = {box[0], box[1], box[2]};
+    layout_grid(cutoff, pbc != 0, ext, (double)n_global, rank, nranks, sp);
+    for (int d = 0; d < 3; d++) {
+        out_i[d] = sp.nprim[d];
+        out_i[3 + d] = sp.ghost[d];
+        out_d[d] = 1.0 / sp.inv_cs[d];
+    }
+    out_i[6] = sp.row0;
+    out_i[7] = sp.row1;
+    out_i[8] = sp.z0;
+    out_i[9] = sp.nzl;
+    const double cs = 1.0 / sp.inv_cs[2];
+    out_d[3] = (sp.z0 - sp.ghost[2]) * cs - 1e-6 * cs;
+    out_d[4] = (sp.z0 + sp.nzl - sp.ghost[2]) * cs + 1e-6 * cs;
+    return CG_OK;
+}
+
 size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count) {
     return 256 + sizeof(double) * (size_t)nranks * (size_t)narrays * (size_t)std::max<int64_t>(count, 1);
 }

@@ -241,6 +241,11 @@ int cg_set_grid_count(cg_handle *h, int64_t n_global);
 int cg_set_count_device(cg_handle *h, const int *n_dev);
 int cg_shard_window(cg_handle *h, const double *box, int rank, int nranks, int64_t n_global, double window[2]);
 size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count);
+/* The cell layout and shard window as plain numbers, computed on the host without a handle or a GPU: out_i = cells per
+ * dimension [3], ghost layers [3], the shard's primary cell rows [row0, row1) (row = z_cell * cells_y + y_cell), its first
+ * cell layer and layer count in the ghost-extended grid; out_d = cell edge [3], z-window [2] (as cg_shard_window). */
+int cg_layout_probe(double cutoff, const double *box, int pbc, int rank, int nranks, int64_t n_global, int out_i[10],
+                    double out_d[5]);
 int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned,
                     const double *zlo, const double *zhi, double period, void *block);
 int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays,

@@ -108,3 +108,36 @@ def _run_c_client():
         out = subprocess.run([exe], capture_output=True, text=True)
         assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
         return out.stdout
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 8])
+def test_shard_layout_tiles_the_box_and_windows_hold_every_neighbour(nranks):
+    """Host-only layout logic of the multi-GPU step (cg_layout_probe): the shards' blocks of cell rows partition the grid, and
+    every particle within one cut-off (periodic) of a particle of shard t lies inside t's z-window -- what the halo exchange
+    relies on when it sends a rank only the particles of its window."""
+    rng = np.random.default_rng(7 + nranks)
+    lib = _capi.lib
+    for trial in range(6):
+        rc = float(rng.uniform(6.0, 14.0))
+        box = np.array([rc * rng.uniform(1.0, 9.0) for _ in range(3)])
+        n_global = int(rng.integers(100, 2_000_000))
+        lay = []
+        for t in range(nranks):
+            oi, od = (C.c_int * 10)(), (C.c_double * 5)()
+            assert lib.cg_layout_probe(rc, box.ctypes.data_as(_capi._dp), 1, t, nranks, n_global, oi, od) == 0
+            lay.append((list(oi), list(od)))
+        (nx, ny, nz), ghost = lay[0][0][0:3], lay[0][0][3:6]
+        cs = lay[0][1][0:3]
+        assert all(l[0][0:6] == lay[0][0][0:6] for l in lay)  # every rank lays out the same grid
+        assert all(abs(cs[d] * [nx, ny, nz][d] - box[d]) < 1e-9 * box[d] for d in range(3))
+        assert all(ghost[d] * cs[d] >= rc - 1e-9 for d in range(3))  # ghost layers cover one cut-off
+        # rows partition [0, ny * nz)
+        assert lay[0][0][6] == 0 and lay[-1][0][7] == ny * nz and all(lay[t][0][7] == lay[t + 1][0][6] for t in range(nranks - 1))
+        # neighbours: random particle i of shard t, random j within rc of it (minimum image) -> z_j (or an image) is in window t
+        for _ in range(300):
+            zi, yi = rng.uniform(0.0, box[2]), rng.uniform(0.0, box[1])
+            row = min(int(zi / cs[2]), nz - 1) * ny + min(int(yi / cs[1]), ny - 1)
+            t = next(k for k in range(nranks) if lay[k][0][6] <= row < lay[k][0][7])
+            zj = (zi + rng.uniform(-rc, rc)) % box[2]
+            lo, hi = lay[t][1][3], lay[t][1][4]
+            assert any(lo <= zj + k * box[2] < hi for k in (-1, 0, 1)), (trial, t, zi, zj, lo, hi)
