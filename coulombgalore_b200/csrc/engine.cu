@@ -185,12 +185,12 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts
                               double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     int n_sorted = counts[0];
-    if (n_sorted > cap - 1) { // no room (the dummy entry needs one slot too): flag it, stay inside the arrays
+    if (n_sorted > cap - kDummies) { // no room (the dummy entries need slots too): flag it, stay inside the arrays
         if (k == 0) counts[2] = 1;
-        n_sorted = cap - 1;
+        n_sorted = cap - kDummies;
     }
-    if (k > n_sorted) return;
-    if (k == n_sorted) { // dummy entry far outside the system: chargeless, momentless, beyond every cut-off
+    if (k >= n_sorted + kDummies) return;
+    if (k >= n_sorted) { // dummy entries far outside the system: chargeless, momentless, beyond every cut-off
         pos[k] = make_double4(far, far, far, 0.0);
         if (mu) mu[k] = make_double4(0.0, 0.0, 0.0, 0.0);
         if (quad) quad[2 * k] = quad[2 * k + 1] = make_double4(0.0, 0.0, 0.0, 0.0);
@@ -733,6 +733,7 @@ struct cg_handle {
     // outputs
     DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
     DevBuf<unsigned long long> item_pairs;
+    DevBuf<int> work_counter;    // next work item of the persistent pair kernel
     int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
     int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
     DevBuf<int> d_counts, halo_counts;
@@ -925,6 +926,7 @@ int cg_destroy(cg_handle *h) {
     h->item_energy.release();
     h->scalars.release();
     h->item_pairs.release();
+    h->work_counter.release();
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_counts_async) cudaFreeHost(h->h_counts_async);
     if (h->counts_ev) cudaEventDestroy(h->counts_ev);
@@ -1305,7 +1307,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     // ---- 0-5. the sorted system: the handle's own, or borrowed from the handle named by cg_share_system ----
     cg_handle *s = h->share_from ? h->share_from : h;
     // i-group table: ion modes put two particles on a lane (groups of 64 entries), the others one (groups of 32)
-    const int gt = (mode == CG_MODE_ION && CG_IPL == 2) ? 1 : 0;
+    const int gt = 0;
     if (s == h) {
         const bool need_mu = h->in[4] != nullptr && (mode != CG_MODE_ION || !h->borrowers.empty());
         const bool need_quad = h->in_quad != nullptr && (mode == CG_MODE_MULTIPOLE_QUAD || !h->borrowers.empty());
@@ -1360,10 +1362,9 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         const char *e = std::getenv("CG_SPLIT");
         return e ? std::atoi(e) : 0;
     }();
-    // j-split: only when the groups cannot fill the machine once (2 CTAs of 8 warps per SM); then as many slices as
-    // fit into that one wave (measured: 144 groups -> 16, 1024 -> 2, 2048 and more -> 1 are the fastest choices)
+    // j-split: only when the groups cannot give every resident warp of the machine an item; then as many slices as it takes
     int split = 1;
-    const int wave = device_sms * 2 * kWarpsPerCta;
+    const int wave = device_sms * 16; // resident warps of the machine (pair_kernel.cuh: 16 per SM in every launch shape)
     if (ng > 0 && ng < wave) split = std::max(1, std::min(64, wave / ng));
     if (split_env > 0) split = std::min(64, split_env);
     const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split
@@ -1425,7 +1426,16 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.slack = (float)(1e-4 + 1e-6 * nmax);
     }
     kp.rc2 = D.cutoff_squared;
-    kp.rc2_safe = D.cutoff_squared < 1e30 ? 0.25 * D.cutoff_squared : 1.0;
+    {
+        // what fails the exact gate by more than this is a dummy entry: its r2 is clamped before the branch-free arithmetic
+        const double cap = D.cutoff_squared < 1e300 ? 4.0 * D.cutoff_squared : 1.7e308;
+        long long bits;
+        std::memcpy(&bits, &cap, sizeof(bits));
+        kp.r2cap_hi = (int)(bits >> 32);
+    }
+    CG_CUDA(h, h->work_counter.ensure(1));
+    CG_CUDA(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(int), st));
+    kp.work_counter = h->work_counter.p;
     kp.core.inverse_cutoff = D.inverse_cutoff;
     kp.core.cutoff_squared = D.cutoff_squared;
     kp.core.kappa = D.inverse_debye_length;
@@ -1472,8 +1482,26 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         dev_table = h->d_erfc_table.p;
         table_doubles = 2 * cgd::kErfcTableEntries;
     }
+#ifdef CG_KPROF
+    static const bool kprof = std::getenv("CG_KPROF") != nullptr;
+    static unsigned long long *d_prof = nullptr;
+    if (kprof) {
+        if (!d_prof) cudaMalloc((void **)&d_prof, 16 * sizeof(unsigned long long));
+        cudaMemsetAsync(d_prof, 0, 16 * sizeof(unsigned long long), st);
+        kp.prof = d_prof;
+    }
+#endif
     if (items > 0) {
-        CG_CUDA(h, (h->precision == CG_FP32 ? fe->pair32[ci] : fe->pair[ci])(kp, D, dev_table, table_doubles, items, st));
+        CG_CUDA(h, (h->precision == CG_FP32 ? fe->pair32[ci] : fe->pair[ci])(kp, D, dev_table, table_doubles, items, device_sms, st));
+#ifdef CG_KPROF
+        if (kprof) {
+            unsigned long long c[16];
+            cudaStreamSynchronize(st);
+            cudaMemcpy(c, d_prof, sizeof(c), cudaMemcpyDeviceToHost);
+            std::fprintf(stderr, "kprof warps: set-up/epilogue %.4g prefilter %.4g pair loop %.4g total %.4g Mcyc; batches %llu rounds %llu chunks %llu\n",
+                         c[0] / 1e6, c[1] / 1e6, c[2] / 1e6, c[7] / 1e6, c[3], c[4], c[5]);
+        }
+#endif
         pair_launches++;
         launches++;
     }

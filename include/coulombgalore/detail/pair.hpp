@@ -13,6 +13,7 @@
 #pragma once
 #include "hd.hpp"
 #include "specfun.hpp"
+#include "srf.hpp"
 
 namespace CoulombGalore {
 namespace detail {
@@ -36,10 +37,17 @@ template <class T> struct RadialT {
 };
 typedef RadialT<double> Radial;
 
+// S..S^(ND) through the functor; the erfc family takes the table argument as it comes (pointer or ErfcCtx)
+template <int ND, class T, class F, class TAB> CG_HD void eval_srf(const F &f, T q, T *s, const TAB &tab) {
+    if constexpr (F::kTable == kTableErfc) f.template eval<ND, T, TAB>(q, s, tab);
+    else f.template eval<ND, T>(q, s, tab);
+}
+
 // ANGCOR_ONLY: the caller needs nothing but angcor (ion field / force without screening) and the functor has a closed form.
 // T: arithmetic type of the pair math (double; float for the CG_FP32 kernels)
-template <class F, bool YUK, int ND, bool ANGCOR_ONLY = false, class T = double>
-CG_HD RadialT<T> radial_terms(const F &f, const CoreParams &cp, T r2, const double *tab) {
+// TAB: what the functor's table argument is (a pointer, nullptr, or the kernels' ErfcCtx)
+template <class F, bool YUK, int ND, bool ANGCOR_ONLY = false, class T = double, class TAB = const double *>
+CG_HD RadialT<T> radial_terms(const F &f, const CoreParams &cp, T r2, const TAB &tab) {
     RadialT<T> R;
     R.rinv = rsqrt_pos(r2);
     R.r1 = r2 * R.rinv;
@@ -47,12 +55,12 @@ CG_HD RadialT<T> radial_terms(const F &f, const CoreParams &cp, T r2, const doub
     if constexpr (ANGCOR_ONLY) {
         R.s0 = T(0);
         R.ek = T(1);
-        R.angcor = f.template angcor<T>(R.q, tab);
+        R.angcor = f.template angcor<T, TAB>(R.q, tab);
         R.unicor = R.totcor = R.r3corr = T(0);
         return R;
     } else {
         T s[4] = {T(0), T(0), T(0), T(0)};
-        f.template eval<ND, T>(R.q, s, tab);
+        eval_srf<ND, T>(f, R.q, s, tab);
         R.s0 = s[0];
         const T third = T(1.0 / 3.0);
         const T qs1 = R.q * s[1];
@@ -96,13 +104,13 @@ template <class T> CG_HD Vec3T<T> quad_times(const QuadT<T> &s, const Vec3T<T> &
 // Conventions: SURVEY.md 8b / oracle/harness.hpp.
 // `pass` = the pair is inside the cut-off.  The kernels evaluate branch-free (the radial arithmetic must then stay
 // finite for rejected / absent pairs): every contribution carries a scalar factor that is zeroed by a select.
-template <class F, bool YUK, int MODE, int WHAT, class T = double>
-CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const double *tab, const Vec3T<T> &d, T r2, T zi, T zj,
+template <class F, bool YUK, int MODE, int WHAT, class T = double, class TAB = const double *>
+CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const TAB &tab, const Vec3T<T> &d, T r2, T zi, T zj,
                            const Vec3T<T> &mui, const Vec3T<T> &muj, AccumT<T> &acc, bool pass = true,
                            const QuadT<T> *quadi = nullptr, const QuadT<T> *quadj = nullptr) {
     constexpr int ND = derivatives_needed(MODE, WHAT);
     constexpr bool kAngcorOnly = F::kHasAngcor && !YUK && MODE == kModeIon && (WHAT & (kWhatEnergy | kWhatPotential)) == 0;
-    const RadialT<T> R = radial_terms<F, YUK, ND, kAngcorOnly, T>(f, cp, r2, tab);
+    const RadialT<T> R = radial_terms<F, YUK, ND, kAngcorOnly, T, TAB>(f, cp, r2, tab);
     const T rinv2 = R.rinv * R.rinv;
     const T rinv3 = rinv2 * R.rinv;
     const T ek3 = pass ? R.ek * rinv3 : T(0); // exp(-kr) / r^3

@@ -32,33 +32,42 @@ static __device__ __constant__ double cg_specfun_c[10] = {-1.0 / 5040.0, 1.0 / 7
                                                           0.375,         128.0}; // Halley coefficient, table steps per unit
 #endif
 
+// What the device erfc needs besides its argument: the shared-memory address of the table and the ten coefficients of
+// cg_specfun_c.  The pair kernel builds one ErfcCtx per thread with the coefficients held in registers: left to itself the
+// compiler re-loads them from the constant bank in every iteration of the pair loop, and a constant load that misses the
+// small per-SM constant cache costs as much as a global load.
+struct ErfcCtx {
+    unsigned tab;
+    double c[10];
+};
+
 #ifdef __CUDA_ARCH__
 // 1/sqrt(x), x > 0 normal: MUFU.RSQ64H seed (2^-22) + one third-order (Halley) step -> full double precision
 __device__ __forceinline__ double rsqrt_device(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     const double e = fma(-x * y, y, 1.0);
-    return fma(y * e, fma(cg_specfun_c[8], e, 0.5), y);
+    return fma(y * e, fma(0.375, e, 0.5), y); // 0.375, 0.5: immediates (the low word of the literal is zero)
 }
 
-// ec = erfc(x), E = exp(-x^2) for x >= 0 from the shared-memory table `tab` (interleaved {erfc(x_k), exp(-x_k^2)}).
+// ec = erfc(x), E = exp(-x^2) for x >= 0 from the shared-memory table at address `tab` (interleaved {erfc(x_k), exp(-x_k^2)}).
 // Branch-free: beyond the table (x >= 8, where erfc < 1.2e-29 and exp(-x^2) < 1.7e-28) the last entry is expanded
 // around the argument's own grid point, which returns values of that same negligible magnitude.
-__device__ __forceinline__ void erfc_gauss_table(double x, const double *tab, double &ec, double &E) {
+__device__ __forceinline__ void erfc_gauss_table(double x, unsigned tab, const double (&c)[10], double &ec, double &E) {
     const double magic = 6755399441055744.0; // 2^52 + 2^51: the low word of (x*128 + magic) is round(x*128)
-    const double t = fma(x, cg_specfun_c[9], magic);
+    const double t = fma(x, kErfcTableInvStep, magic);
     // x >= 0: one unsigned min clamps the index (a negative low word would read as huge and clamp too)
     const int k = (int)min((unsigned)__double2loint(t), (unsigned)(kErfcTableEntries - 1));
     const double kf = t - magic;
     const double d = fma(kf, -kErfcTableStep, x); // x - x_k, exact
     const double xk = kf * kErfcTableStep;
     double2 T; // the table lives in shared memory: address it as such (a generic load would cost an aperture check)
-    asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(T.x), "=d"(T.y) : "r"((unsigned)__cvta_generic_to_shared(tab) + 16u * (unsigned)k));
+    asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(T.x), "=d"(T.y) : "r"(tab + 16u * (unsigned)k));
     const double w = d * (x + xk);
-    double e = fma(w, cg_specfun_c[0], cg_specfun_c[1]);
-    e = fma(e, w, cg_specfun_c[2]);
-    e = fma(e, w, cg_specfun_c[3]);
-    e = fma(e, w, cg_specfun_c[4]);
+    double e = fma(w, c[0], c[1]);
+    e = fma(e, w, c[2]);
+    e = fma(e, w, c[3]);
+    e = fma(e, w, c[4]);
     e = fma(e, w, 0.5);
     e = fma(e, w, -1.0);
     e = fma(e, w, 1.0); // exp(-w)
@@ -67,10 +76,14 @@ __device__ __forceinline__ void erfc_gauss_table(double x, const double *tab, do
     const double a0 = 1.0 + e;
     const double a1 = fma(x, e, -xk);
     const double a2h = fma(fma(xk, xk, -0.5), a0, w * e);
-    const double u = fma(d * cg_specfun_c[5], a2h, a1);
-    const double I2 = d * fma(d * cg_specfun_c[6], u, a0);
+    const double u = fma(d * c[5], a2h, a1);
+    const double I2 = d * fma(d * c[6], u, a0);
     E = T.y * e;
-    ec = fma(cg_specfun_c[7] * T.y, I2, T.x);
+    ec = fma(c[7] * T.y, I2, T.x);
+}
+__device__ __forceinline__ void erfc_gauss_table(double x, const ErfcCtx &cx, double &ec, double &E) { erfc_gauss_table(x, cx.tab, cx.c, ec, E); }
+__device__ __forceinline__ void erfc_gauss_table(double x, const double *tab, double &ec, double &E) {
+    erfc_gauss_table(x, (unsigned)__cvta_generic_to_shared(tab), cg_specfun_c, ec, E);
 }
 #endif
 
@@ -103,9 +116,9 @@ CG_HD double exp_any(double y) {
 #endif
 }
 
-// ec = erfc(x), E = exp(-x^2); `tab` is the device erfc table (ignored on the host).  SIGNED: x may be negative
-// (screened Ewald at small q): erfc(-x) = 2 - erfc(x).
-template <bool SIGNED = false> CG_HD void erfc_and_gauss(double x, double &ec, double &E, const double *tab) {
+// ec = erfc(x), E = exp(-x^2); `tab` is the device erfc table -- a pointer into shared memory or an ErfcCtx -- and is
+// ignored on the host.  SIGNED: x may be negative (screened Ewald at small q): erfc(-x) = 2 - erfc(x).
+template <bool SIGNED = false, class TAB = const double *> CG_HD void erfc_and_gauss(double x, double &ec, double &E, const TAB &tab) {
 #ifdef __CUDA_ARCH__
     if (SIGNED) {
         erfc_gauss_table(fabs(x), tab, ec, E); // the kernels always stage the table
@@ -135,7 +148,7 @@ CG_HD float exp_any(float y) {
     return std::exp(y);
 #endif
 }
-template <bool SIGNED = false> CG_HD void erfc_and_gauss(float x, float &ec, float &E, const double *) {
+template <bool SIGNED = false, class TAB = const double *> CG_HD void erfc_and_gauss(float x, float &ec, float &E, const TAB &) {
 #ifdef __CUDA_ARCH__
     E = expf(-x * x);
     ec = erfcf(x);

@@ -134,7 +134,7 @@ template <int KIND> struct ErfcFamilySrf : SrfDefaults {
     CG_HD explicit ErfcFamilySrf(const cg_scheme_desc &d)
         : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), c(d.erfc_eta), e(d.exp_eta2),
           c2(d.erfc_eta + d.eta * kTwoOverSqrtPi * d.exp_eta2), invF0(KIND == kEwaldT ? 1.0 / d.F0 : 1.0) {}
-    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double *tab = nullptr) const {
+    template <int ND, class T = double, class TAB = const double *> CG_HD void eval(T q, T *s, const TAB &tab = TAB()) const {
         const T x = (T)eta * q;
         T E, ec;
         erfc_and_gauss(x, ec, E, tab); // ec = erfc(x), E = exp(-x^2)
@@ -178,7 +178,7 @@ template <int KIND> struct ErfcFamilySrf : SrfDefaults {
     }
     // S - q S' with the q-linear and q-polynomial terms of S and q S' cancelled analytically: what ion fields and
     // forces need (core.hpp:352-365 with kappa = 0).  erfc(x) + (2/sqrt(pi)) x exp(-x^2) is common to all kinds.
-    template <class T = double> CG_HD T angcor(T q, const double *tab) const {
+    template <class T = double, class TAB = const double *> CG_HD T angcor(T q, const TAB &tab) const {
         const T x = (T)eta * q;
         T E, ec;
         erfc_and_gauss(x, ec, E, tab);
@@ -201,7 +201,7 @@ struct EwaldScreenedSrf : SrfDefaults {
         : eta(d.eta), eta2(d.eta * d.eta), k1(d.eta * kTwoOverSqrtPi), zeta(d.zeta), zeta2(d.zeta * d.zeta),
           zeta3(d.zeta * d.zeta * d.zeta), half_z_over_eta(d.zeta / (2.0 * d.eta)), z_over_eta(d.zeta / d.eta),
           z2_over_eta2((d.zeta * d.zeta) / (d.eta * d.eta)) {}
-    template <int ND, class T = double> CG_HD void eval(T q, T *s, const double *tab = nullptr) const {
+    template <int ND, class T = double, class TAB = const double *> CG_HD void eval(T q, T *s, const TAB &tab = TAB()) const {
         const T xq = (T)eta * q, H = (T)half_z_over_eta, ZE = (T)z_over_eta, Z = (T)zeta, K1 = (T)k1;
         const T xm = xq - H, xp = xq + H;
         T ecm, Em, ecp, Ep; // erfc(x-), exp(-x-^2), erfc(x+)

@@ -140,6 +140,14 @@ int cgo_recip_force_field(void *handle, int64_t N, const double *x, const double
 int cgo_recip_surface(void *handle, int64_t N, const double *x, const double *y, const double *z, const double *q,
                       const double *mux, const double *muy, const double *muz, double *energy, double *field3);
 
+/* EwaldTruncated::surface_energy(positions, charges, dipoles, volume) (reference ewald_truncated.hpp:91-104) of a scheme
+ * constructed as EwaldTruncated(cutoff, alpha, eps_sur); q / mu pointers may be NULL (all zero). */
+int cgo_ewaldt_surface(double cutoff, double alpha, double eps_sur, int64_t N, const double *x, const double *y, const double *z,
+                       const double *q, const double *mux, const double *muy, const double *muz, double volume, double *energy);
+
+/* out[0..3] = qPochhammerSymbol, ...Derivative, ...SecondDerivative, ...ThirdDerivative (q, l, P) (qpotential.hpp:50-192) */
+int cgo_qpochhammer(double q, int32_t l, int32_t P, double *out4);
+
 #ifdef __cplusplus
 }
 #endif

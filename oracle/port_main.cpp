@@ -153,3 +153,35 @@ cgo::RecipIface *cgo::make_recip(double cutoff, double alpha, double eps_sur, do
 }
 
 CGO_DEFINE_C_ABI("port")
+
+extern "C" {
+// ewald_truncated.hpp:91-104: the charge-weighted position sum and the dipole sum are accumulated separately (particle
+// order), squared as P.P + 2 P.D + D.D; the prefactor uses the constructor argument as given (the constructor's
+// `surface_dielectric_constant < 1 -> infinity` repair at :56-58 assigns the parameter, not the member)
+int cgo_ewaldt_surface(double cutoff, double alpha, double eps_sur, int64_t N, const double *x, const double *y, const double *z,
+                       const double *q, const double *mx, const double *my, const double *mz, double volume, double *energy) {
+    (void)cutoff;
+    (void)alpha;
+    const double pi = 4.0 * std::atan(1.0);
+    double P[3] = {0, 0, 0}, D[3] = {0, 0, 0};
+    for (int64_t p = 0; p < N; p++) {
+        const double ch = q ? q[p] : 0.0;
+        P[0] += x[p] * ch;
+        P[1] += y[p] * ch;
+        P[2] += z[p] * ch;
+        if (mx) {
+            D[0] += mx[p];
+            D[1] += my[p];
+            D[2] += mz[p];
+        }
+    }
+    const double pp = P[0] * P[0] + P[1] * P[1] + P[2] * P[2], pd = P[0] * D[0] + P[1] * D[1] + P[2] * D[2],
+                 dd = D[0] * D[0] + D[1] * D[1] + D[2] * D[2];
+    *energy = 2.0 * pi / (2.0 * eps_sur + 1.0) / volume * (pp + 2.0 * pd + dd);
+    return 0;
+}
+int cgo_qpochhammer(double q, int32_t l, int32_t P, double *out4) {
+    cgport::qpochhammer(q, P, out4, l);
+    return 0;
+}
+}

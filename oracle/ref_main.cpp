@@ -172,3 +172,26 @@ cgo::RecipIface *cgo::make_recip(double cutoff, double alpha, double eps_sur, do
 }
 
 CGO_DEFINE_C_ABI("reference")
+
+extern "C" {
+int cgo_ewaldt_surface(double cutoff, double alpha, double eps_sur, int64_t N, const double *x, const double *y, const double *z,
+                       const double *q, const double *mx, const double *my, const double *mz, double volume, double *energy) {
+    try {
+        const EwaldTruncated pot(cutoff, alpha, eps_sur);
+        std::vector<vec3> pos, dip;
+        std::vector<double> ch;
+        RefRecip::load(N, x, y, z, q, mx, my, mz, pos, ch, dip);
+        *energy = pot.surface_energy(pos, ch, dip, volume);
+        return 0;
+    } catch (...) {
+        return -1;
+    }
+}
+int cgo_qpochhammer(double q, int32_t l, int32_t P, double *out4) {
+    out4[0] = qPochhammerSymbol(q, l, P);
+    out4[1] = qPochhammerSymbolDerivative(q, l, P);
+    out4[2] = qPochhammerSymbolSecondDerivative(q, l, P);
+    out4[3] = qPochhammerSymbolThirdDerivative(q, l, P);
+    return 0;
+}
+}

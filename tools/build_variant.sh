@@ -5,3 +5,4 @@ ROOT=$(cd "$(dirname "$0")/.." && pwd)
 name=$1; shift
 make -s -C "$ROOT/coulombgalore_b200/csrc" -j8 BUILD="$ROOT/coulombgalore_b200/csrc/build_$name" LIB="$ROOT/gpurun_tmp_$name.so" EXTRA_NVFLAGS="$*" 2>&1 | grep -E "error" || true
 ls -la "$ROOT/gpurun_tmp_$name.so" | awk '{print $5, $9}'
+rm -rf "$ROOT/coulombgalore_b200/csrc/build_$name"  # objects only; the snapshot sent to the GPU box is size-limited
