@@ -135,6 +135,17 @@ class BatchedEvaluator:
         check(lib.cg_eval_device(self.h, mode, what, _devptr(force), _devptr(field), _devptr(potential), _devptr(scalars)),
               "cg_eval_device", self.h)
 
+    def eval_device_checked(self, mode, what, force=None, field=None, potential=None, scalars=None):
+        """eval_device, then a host read of the two scalars (waits for the stream); an evaluation the sync-free sizing made
+        invalid (pair count -1, see cg_eval_device in cg_b200.h) is repeated once with exact sizes.  -> (energy, pairs)"""
+        host = (C.c_double * 2)()
+        for _ in range(2):
+            self.eval_device(mode, what, force, field, potential, scalars)
+            check(lib.cg_read_scalars(self.h, _devptr(scalars), host), "cg_read_scalars", self.h)
+            if not host[1] < 0.0:
+                return host[0], int(host[1] + 0.5)
+        raise RuntimeError("cg_eval_device: evaluation invalid twice in a row")
+
     # ---- O(N) terms (reference core.hpp:794, 809-842) ----
     def self_terms(self, self_field=False):
         """-> dict(self_energy, neutralization_energy, charge_sum[, self_field (n,3)]) of the current system."""
@@ -146,6 +157,25 @@ class BatchedEvaluator:
 
     def self_terms_device(self, out3, self_field=None):
         check(lib.cg_self_terms_device(self.h, _devptr(out3), _devptr(self_field)), "cg_self_terms_device", self.h)
+
+    def dipole_moments(self):
+        """-> (sum_i z_i r_i, sum_i mu_i) of the current system, two 3-vectors summed on the device in a fixed order."""
+        out = (C.c_double * 6)()
+        check(lib.cg_dipole_moments(self.h, out), "cg_dipole_moments", self.h)
+        return np.array(out[0:3]), np.array(out[3:6])
+
+    def dipole_moments_device(self, out6):
+        check(lib.cg_dipole_moments_device(self.h, _devptr(out6)), "cg_dipole_moments_device", self.h)
+
+    def surface_energy(self, volume):
+        """EwaldTruncated::surface_energy(positions, charges, dipoles, volume) of the current system (reference
+        ewald_truncated.hpp:91-104); the scheme must be an EwaldTruncated."""
+        eps = getattr(self.scheme, "surface_dielectric_constant", None)
+        if eps is None:
+            raise TypeError("surface_energy: the evaluator's scheme has no surface dielectric constant (EwaldTruncated)")
+        P, D = self.dipole_moments()
+        sq = float(P @ P) + 2.0 * float(P @ D) + float(D @ D)
+        return 2.0 * (4.0 * np.arctan(1.0)) / (2.0 * eps + 1.0) / volume * sq
 
     def dipole_torque(self, field):
         field = np.ascontiguousarray(field, dtype=np.float64)

@@ -144,6 +144,9 @@ template <bool SCATTER>
 __global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int cap,
                            int *counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    // more valid particles on the device than the arrays this evaluation was given (halo exchange: the received count
+    // outgrew the caller's bound): the results would silently miss particles, so the evaluation is marked invalid
+    if (p == 0 && sp.n_dev && *sp.n_dev > sp.n) counts[2] = 1;
     if (p >= (sp.n_dev ? min(*sp.n_dev, sp.n) : sp.n)) return;
     int sx[3], cx[3], sy[3], cy[3], sz[3], cz[3];
     const int mx = images_1d(sp, 0, sp.x[p] - sp.lo[0], sx, cx);
@@ -518,6 +521,44 @@ __global__ void torque_kernel(int n, const double *mx, const double *my, const d
     torque[3 * (size_t)i + 0] = ay * bz - az * by; // mu x E
     torque[3 * (size_t)i + 1] = az * bx - ax * bz;
     torque[3 * (size_t)i + 2] = ax * by - ay * bx;
+}
+
+// ---- total moments of the configuration: out[0..2] = sum_i z_i r_i, out[3..5] = sum_i mu_i, accumulated separately (what
+// EwaldTruncated::surface_energy squares, reference ewald_truncated.hpp:91-104); per-block partial sums, then one thread adds
+// them in block order: fixed summation order, bit-reproducible ----
+__global__ void moments_partial_kernel(int n, const double *x, const double *y, const double *z, const double *q, const double *mx,
+                                       const double *my, const double *mz, double *partial) {
+    __shared__ double sh[6][kSelfThreads / 32];
+    double a[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int i = blockIdx.x * kSelfThreads + threadIdx.x; i < n; i += gridDim.x * kSelfThreads) {
+        const double c = q ? q[i] : 0.0;
+        a[0] += x[i] * c;
+        a[1] += y[i] * c;
+        a[2] += z[i] * c;
+        if (mx) {
+            a[3] += mx[i];
+            a[4] += my[i];
+            a[5] += mz[i];
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < 6; d++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) a[d] += __shfl_down_sync(0xffffffffu, a[d], off);
+        if ((threadIdx.x & 31) == 0) sh[d][threadIdx.x >> 5] = a[d];
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double t = 0.0;
+        for (int w = 0; w < kSelfThreads / 32; w++) t += sh[threadIdx.x][w];
+        partial[6 * blockIdx.x + threadIdx.x] = t;
+    }
+}
+__global__ void moments_final_kernel(int nb, const double *partial, double *out6) {
+    if (blockIdx.x != 0 || threadIdx.x >= 6) return;
+    double t = 0.0;
+    for (int k = 0; k < nb; k++) t += partial[6 * k + threadIdx.x];
+    out6[threadIdx.x] = t;
 }
 
 // ---- exchange step over peer memory: every rank pulls the other ranks' owned SoA blocks over NVLink ----
@@ -1172,8 +1213,10 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
         const char *e = std::getenv("CG_SYNC_FREE");
         return !(e && e[0] == '0');
     }();
-    const bool fast = fast_enabled && h->fast.valid && h->pbc && h->fast.pbc && h->fast.n == h->n && h->fast.shard_rank == h->shard_rank &&
-                      h->fast.shard_n == h->shard_n && h->fast.box[0] == h->box[0] && h->fast.box[1] == h->box[1] && h->fast.box[2] == h->box[2];
+    bool fast = fast_enabled && h->fast.valid && h->pbc && h->fast.pbc && h->fast.n == h->n && h->fast.shard_rank == h->shard_rank &&
+                h->fast.shard_n == h->shard_n && h->fast.box[0] == h->box[0] && h->fast.box[1] == h->box[1] && h->fast.box[2] == h->box[2];
+    // a group table that was never built before (a borrower asked for it) has no previous count to size it from
+    if ((need32 && h->fast.last_groups[0] == 0) || (need64 && h->fast.last_groups[1] == 0)) fast = false;
 
     // ---- 1-3. histogram, scan, groups ----
     int *counts = h->d_counts.p;
@@ -1548,6 +1591,16 @@ int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *fiel
     return eval_device_impl(h, mode, what, force, field, potential, scalars);
 }
 
+int cg_read_scalars(cg_handle *h, const double *scalars_dev, double host2[2]) {
+    if (!h || !scalars_dev || !host2) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CG_CUDA(h, cudaMemcpyAsync(h->h_scalars, scalars_dev, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CG_CUDA(h, cudaStreamSynchronize(h->stream));
+    host2[0] = h->h_scalars[0];
+    host2[1] = h->h_scalars[1];
+    return CG_OK;
+}
+
 int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field, double *potential) {
     if (!h) return CG_ERR_INVALID;
     cudaSetDevice(h->device);
@@ -1694,6 +1747,39 @@ int cg_self_terms(cg_handle *h, double out[3], double *self_field) {
     CG_CUDA(h, cudaMemcpyAsync(h->h_scalars + 4, h->scalars.p + 4, 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CG_CUDA(h, cudaStreamSynchronize(h->stream));
     for (int k = 0; k < 3; k++) out[k] = h->h_scalars[4 + k];
+    return CG_OK;
+}
+
+int cg_dipole_moments_device(cg_handle *h, double *out6) {
+    if (!h || !out6) return CG_ERR_INVALID;
+    cg_handle *sys = h->share_from ? h->share_from : h;
+    if (!sys->have_system) {
+        h->err = "cg_dipole_moments before cg_set_system";
+        return CG_ERR_STATE;
+    }
+    cudaSetDevice(h->device);
+    cudaStream_t st = h->stream;
+    const int n = (int)sys->n;
+    const int nb = std::max(1, std::min(1024, (n + kSelfThreads - 1) / kSelfThreads));
+    CG_CUDA(h, h->self_partial.ensure(6 * (size_t)nb));
+    if (sys != h) CG_CUDA(h, cudaStreamWaitEvent(st, sys->inputs_ev, 0)); // the lender's upload
+    moments_partial_kernel<<<nb, kSelfThreads, 0, st>>>(n, sys->in[0], sys->in[1], sys->in[2], sys->in[3], sys->in[4], sys->in[5], sys->in[6],
+                                                       h->self_partial.p);
+    moments_final_kernel<<<1, 32, 0, st>>>(nb, h->self_partial.p, out6);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+int cg_dipole_moments(cg_handle *h, double out[6]) {
+    if (!h || !out) return CG_ERR_INVALID;
+    cudaSetDevice(h->device);
+    CG_CUDA(h, h->scalars.ensure(16));
+    const int rc = cg_dipole_moments_device(h, h->scalars.p + 8);
+    if (rc != CG_OK) return rc;
+    double *pin = h->h_scalars; // 8 pinned doubles
+    CG_CUDA(h, cudaMemcpyAsync(pin, h->scalars.p + 8, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CG_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (int k = 0; k < 6; k++) out[k] = pin[k];
     return CG_OK;
 }
 

@@ -33,11 +33,18 @@ class ShardedStep:
                 f.copy_(o)
             return self.full
         if self.even and self.coalesce:
-            # one NCCL group (a single fused launch) for all SoA arrays instead of one collective per array
-            with self._coalescing_manager(group=self.group, device=self.full[0].device, async_ops=False):
-                for f, o in zip(self.full, owned):
-                    dist.all_gather_into_tensor(f, o, group=self.group)
-            return self.full
+            # one NCCL group (a single fused launch) for all SoA arrays instead of one collective per array.  The manager is a
+            # private torch API: a signature that differs from the one probed here switches the coalescing off for good.
+            try:
+                cm = self._coalescing_manager(group=self.group, device=self.full[0].device, async_ops=False)
+            except TypeError:
+                self.coalesce = False
+                cm = None
+            if cm is not None:
+                with cm:
+                    for f, o in zip(self.full, owned):
+                        dist.all_gather_into_tensor(f, o, group=self.group)
+                return self.full
         for f, o in zip(self.full, owned):
             if self.even:
                 dist.all_gather_into_tensor(f, o, group=self.group)
@@ -140,6 +147,9 @@ class PeerExchange(ShardedStep):
         return ex
 
     def gather(self, owned):
+        # The two-block protocol orders publish -> all-reduce -> pull by STREAM order: the evaluator's kernels (cg_peer_gather)
+        # must run on the stream the copies and the collective are enqueued on, i.e. torch's current stream.
+        self.ev.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
         b = self.step & 1
         self.step += 1
         blk = self.owned_blocks[b]
@@ -242,6 +252,9 @@ class HaloExchange:
         self.ids_owned = torch.arange(self.lo, self.lo + self.count, dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.step, self.n_bound = 0, None
+        self._n_host = torch.zeros(2, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else torch.zeros(2, dtype=torch.int32)
+        self._n_event = torch.cuda.Event() if self.device.type == "cuda" else None
+        self._n_pending, self.last_count = False, 0
 
     @staticmethod
     def create(evaluator, n_total, box, n_payload, device, group=None):
@@ -263,6 +276,10 @@ class HaloExchange:
         """owned2d: [n_payload, count] float64 on the device (row 2 = z).  -> (list of payload arrays [bound], ids [bound],
         n_out int32[2] on the device: particles received, overflow flag).  `bound` >= the received count."""
         C = self.C
+        # publish -> all-reduce -> pull are ordered by STREAM order (see PeerExchange.gather): bind the evaluator to torch's
+        # current stream, whatever stream it was created with
+        self.ev.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._track_bound()
         b = self.step & 1
         self.step += 1
         src = (C.c_void_p * self.narrays)(*([owned2d[a].data_ptr() for a in range(self.n_payload)] + [self.ids_owned.data_ptr()]))
@@ -277,8 +294,24 @@ class HaloExchange:
             if int(got[1]) != 0:
                 raise RuntimeError("HaloExchange: capacity %d too small" % self.capacity)
             self.n_bound = min(self.capacity, int(got[0]) + int(got[0]) // 8 + 1024)
+        else:  # the count of this step travels to pinned memory behind the pull; a later gather() reads it without waiting
+            self._n_host.copy_(self.n_out, non_blocking=True)
+            self._n_event.record(torch.cuda.current_stream(self.device))
+            self._n_pending = True
         nb = self.n_bound
         return [self.recv[a, :nb] for a in range(self.n_payload)], self.recv[self.n_payload, :nb], self.n_out
+
+    def _track_bound(self):
+        """Grow the bound handed to the engine before the received count reaches it.  A step that does exceed it is not
+        silent: the engine raises its overflow flag (energy NaN, pair count -1) when the device count is larger than the
+        arrays it was given."""
+        if self.n_bound is None or not self._n_pending or not self._n_event.query():
+            return
+        self._n_pending = False
+        got = int(self._n_host[0])
+        self.last_count = got
+        if got + got // 32 + 256 > self.n_bound:
+            self.n_bound = min(self.capacity, got + got // 8 + 1024)
 
     def set_system(self, ev, arrays, has_q=True, has_mu=False, pbc=True):
         """Hand the received subset to the evaluator: arrays = x, y, z[, q][, mux, muy, muz]."""

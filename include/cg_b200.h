@@ -183,9 +183,17 @@ int cg_eval(cg_handle *h, int mode, int what, double *force, double *field, doub
 int cg_eval_begin(cg_handle *h, int mode, int what, double *force, double *field, double *potential);
 int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs);
 /* Same with DEVICE output buffers; scalars[0] = U, scalars[1] = pair count (as double), on the device.
- * Asynchronous on the handle's stream. */
+ * Asynchronous on the handle's stream.  From the second evaluation of a system shape (same n, box, shard) on, array sizes and
+ * launch bounds come from the previous evaluation and no host round trip takes place.  Should the new configuration not fit
+ * them -- or should a device-side particle count (cg_set_count_device) exceed the arrays given to cg_set_system_device --
+ * the evaluation is INVALID and says so: scalars[0] = NaN, scalars[1] = -1, per-particle outputs partial.  A caller of this
+ * entry point checks scalars[1] < 0 and evaluates again (the next call sizes exactly); cg_eval / cg_eval_end do that
+ * themselves. */
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,
                    double *scalars);
+
+/* two scalars written by cg_eval_device (a DEVICE pointer) -> host; waits for the handle's stream */
+int cg_read_scalars(cg_handle *h, const double *scalars_dev, double host2[2]);
 
 /* Quadrupole tensors of the current system for CG_MODE_MULTIPOLE_QUAD: quad[n][9], row-major 3x3 per particle, not
  * necessarily symmetric or traceless (reference mat33 arguments).  Call after every cg_set_system* (which clears them);
@@ -198,6 +206,11 @@ int cg_set_quadrupoles_device(cg_handle *h, const double *quad);
  * The _device forms take device pointers and are asynchronous on the handle's stream. */
 int cg_self_terms(cg_handle *h, double out[3], double *self_field);
 int cg_self_terms_device(cg_handle *h, double *out3, double *self_field);
+/* Total moments of the current system, the two sums EwaldTruncated::surface_energy is built from (reference
+ * ewald_truncated.hpp:91-104): out[0..2] = sum_i z_i r_i, out[3..5] = sum_i mu_i, accumulated separately in a fixed order.
+ * The surface term is 2 pi / (2 eps_sur + 1) / V * (P.P + 2 P.D + D.D); the header class EwaldTruncated evaluates it. */
+int cg_dipole_moments(cg_handle *h, double out[6]);
+int cg_dipole_moments_device(cg_handle *h, double *out6);
 /* torque[3n] = mu_i x field_i (reference core.hpp:794); field as written by cg_eval* with CG_FIELD */
 int cg_dipole_torque(cg_handle *h, const double *field, double *torque);
 int cg_dipole_torque_device(cg_handle *h, const double *field, double *torque);

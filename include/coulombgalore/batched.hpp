@@ -53,7 +53,6 @@ class BatchedEvaluator {
     void eval(int mode, int what, double *force, double *field, double *potential, double *energy, int64_t *pairs) {
         check(cg_eval(h_, mode, what, force, field, potential, energy, pairs), "cg_eval");
     }
-    /** device outputs; scalars[0] = U, scalars[1] = pair count; asynchronous on the handle's stream */
     // the same in two halves (several evaluators overlap their copies and kernels; buffers stay valid until eval_end)
     void eval_begin(int mode, int what, double *force, double *field, double *potential) {
         check(cg_eval_begin(h_, mode, what, force, field, potential), "cg_eval_begin");
@@ -62,8 +61,21 @@ class BatchedEvaluator {
     // O(N) terms: out[0] = sum self_energy, out[1] = neutralization_energy, out[2] = sum z; self_field[3n] may be null
     void self_terms(double out[3], double *self_field) { check(cg_self_terms(h_, out, self_field), "cg_self_terms"); }
     void dipole_torque(const double *field, double *torque) { check(cg_dipole_torque(h_, field, torque), "cg_dipole_torque"); }
+    /** device outputs; scalars[0] = U, scalars[1] = pair count; asynchronous on the handle's stream.  From the second
+     *  evaluation of a system shape on, sizes come from the previous evaluation (no host round trip); a configuration that
+     *  does not fit them yields scalars = {NaN, -1} and partial outputs -- check scalars[1] < 0 and call again, or use
+     *  eval_device_checked */
     void eval_device(int mode, int what, double *force, double *field, double *potential, double *scalars) {
         check(cg_eval_device(h_, mode, what, force, field, potential, scalars), "cg_eval_device");
+    }
+    /** eval_device + a read of the two scalars (waits for the stream) + one exactly-sized re-evaluation if the first was invalid */
+    void eval_device_checked(int mode, int what, double *force, double *field, double *potential, double *scalars, double host_scalars[2]) {
+        for (int attempt = 0; attempt < 2; attempt++) {
+            eval_device(mode, what, force, field, potential, scalars);
+            check(cg_read_scalars(h_, scalars, host_scalars), "cg_read_scalars");
+            if (!(host_scalars[1] < 0.0)) return;
+        }
+        throw std::runtime_error("cg_eval_device: evaluation invalid twice in a row");
     }
 };
 

@@ -182,6 +182,7 @@ template <class T, bool debyehuckel = true> class EnergyImplementation : public 
             if (ND >= 3) s[3] = self->short_range_function_third_derivative(q);
         }
         static constexpr bool kHasAngcor = false;
+        static constexpr int kTable = detail::kTableNone;
     };
     Functor functor() const { return Functor{static_cast<const T *>(this)}; }
     detail::CoreParams core() const { return detail::CoreParams{desc_.inverse_cutoff, desc_.cutoff_squared, desc_.inverse_debye_length}; }

@@ -12,8 +12,9 @@
 //   * erfc(x) = erfc(x_k) - 2/sqrt(pi) exp(-x_k^2) I,  I = int_0^d exp(-2 x_k t - t^2) dt, d = x - x_k, by the
 //     two-point Hermite (osculatory) rule  I = d/2 (f0+f1) + d^2/10 (f0'-f1') + d^3/120 (f0''+f1'') + d^7 f^(6)/100800,
 //     whose end-point values all follow from the exp(-w) just computed: f1 = e, f' = -(2 x_k + 2 t) f, ...
-// Measured against mpmath (tests/test_specfun.py): <= 2 ulp for x < 4, <= 4e-15 relative for x < 6, i.e. three to
-// four orders inside the 1e-12 parity budget.  For x >= 8 both functions are only known to be < 2e-28 in magnitude.
+// Measured against mpmath (tests/test_specfun.py, on the GPU): <= 4 ulp for x < 4, <= 1e-14 relative for x < 6, <= 1e-13 up to
+// x = 7.99, i.e. at least an order inside the 1e-12 parity budget where the values matter at all (erfc(6) = 2e-17).  From
+// x = 8 - 1/256 on both functions are only known to be < 2e-28 in magnitude.
 #pragma once
 #include "hd.hpp"
 

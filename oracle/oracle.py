@@ -259,3 +259,24 @@ def generate(n, a, seed, kind="best"):
     arrs = [np.zeros(N) for _ in range(7)]
     lib.cgo_generate(n, a, seed, *[_ptr(v) for v in arrs])
     return arrs[0], arrs[1], arrs[2], arrs[3], (arrs[4], arrs[5], arrs[6])
+
+
+def ewaldt_surface_energy(cutoff, alpha, eps_sur, x, y, z, q, mu, volume, kind="best"):
+    """EwaldTruncated(cutoff, alpha, eps_sur).surface_energy(positions, charges, dipoles, volume) (reference ewald_truncated.hpp:91-104)."""
+    lib = load(kind)
+    lib.cgo_ewaldt_surface.argtypes = [C.c_double] * 3 + [C.c_int64] + [_dp] * 7 + [C.c_double, _dp]
+    mx, my, mz = (None, None, None) if mu is None else mu
+    e = np.zeros(1)
+    rc = lib.cgo_ewaldt_surface(cutoff, alpha, eps_sur, x.size, _ptr(x), _ptr(y), _ptr(z), _ptr(q), _ptr(mx), _ptr(my), _ptr(mz), volume, _ptr(e))
+    if rc != 0:
+        raise RuntimeError("cgo_ewaldt_surface failed rc=%d" % rc)
+    return float(e[0])
+
+
+def qpochhammer(q, l, P, kind="best"):
+    """(qPochhammerSymbol, ...Derivative, ...SecondDerivative, ...ThirdDerivative)(q, l, P) (reference qpotential.hpp:50-192)."""
+    lib = load(kind)
+    lib.cgo_qpochhammer.argtypes = [C.c_double, C.c_int32, C.c_int32, _dp]
+    o = np.zeros(4)
+    lib.cgo_qpochhammer(q, l, P, _ptr(o))
+    return o

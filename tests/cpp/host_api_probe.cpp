@@ -157,6 +157,13 @@ int probe_pair(void *h, double zA, double zB, const double *a, const double *b, 
     put(o + 32, s.multipole_multipole_force(zA, zB, muA, muB, quadA, quadB, r));
     return 0;
 }
+// the q-Pochhammer free functions of the reference (qpotential.hpp:50, 66, 97, 138)
+void probe_qpochhammer(double q, int l, int P, double *o) {
+    o[0] = qPochhammerSymbol(q, l, P);
+    o[1] = qPochhammerSymbolDerivative(q, l, P);
+    o[2] = qPochhammerSymbolSecondDerivative(q, l, P);
+    o[3] = qPochhammerSymbolThirdDerivative(q, l, P);
+}
 // statically typed use, as in the reference's README: no virtual dispatch
 double probe_static_wolf_energy(double cutoff, double alpha, double zA, double zB, double r) {
     Wolf pot(cutoff, alpha);

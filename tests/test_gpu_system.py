@@ -398,3 +398,41 @@ def test_full_ewald_sum_of_the_reference_test_case():
     assert f[0] == pytest.approx(0.9956865, rel=1e-6) and abs(f[1]) < 1e-12 and abs(f[2]) < 1e-12   # :594
     ev.close()
     rec.close()
+
+
+def test_ewald_truncated_surface_energy(oracle_kind, tmp_path):
+    """SURVEY.md 8f rank 3: EwaldTruncated::surface_energy (reference ewald_truncated.hpp:91-104) -- the two moment sums reduced
+    on the device (cg_dipole_moments), through the Python evaluator and through the header-only C++ class, against the oracle."""
+    import ctypes as C
+    import subprocess
+    x, y, z, q, mu = O.generate(9, 3.0, 808, oracle_kind)
+    q = q + 0.25  # a charged, polar system: both sums and their cross term matter
+    V = 27.0 ** 3
+    _dp = C.POINTER(C.c_double)
+    lib_dir = os.path.join(ROOT, "coulombgalore_b200")
+    so = str(tmp_path / "surface_probe.so")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-ffp-contract=off", "-fPIC", "-shared",
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "surface_probe.cpp"), "-o", so,
+                           "-L" + lib_dir, "-l:libcg_b200.so", "-Wl,-rpath," + lib_dir])
+    probe = C.CDLL(so)
+    probe.probe_ewaldt_surface.argtypes = [C.c_double] * 3 + [C.c_int64] + [_dp] * 7 + [C.c_double, _dp]
+    for eps in (1.0, 35.0, float("inf"), 0.5):  # 0.5: the reference keeps a sub-unity argument in the member it reads here
+        ref = O.ewaldt_surface_energy(10.0, 0.3, eps, x, y, z, q, mu, V, oracle_kind)
+        ev = cg.BatchedEvaluator(cg.EwaldTruncated(10.0, 0.3, eps))
+        ev.set_system(x, y, z, q, mu, [27.0] * 3, True)
+        P, D = ev.dipole_moments()
+        # the sums themselves: 1e-13 of the sum of magnitudes (the device adds in a different, fixed order)
+        assert np.all(np.abs(P - np.array([np.sum(c * q) for c in (x, y, z)])) <= 1e-13 * np.array([np.sum(np.abs(c * q)) for c in (x, y, z)]))
+        assert np.all(np.abs(D - np.array([np.sum(m) for m in mu])) <= 1e-13 * np.array([np.sum(np.abs(m)) for m in mu]))
+        got = ev.surface_energy(V)
+        e = np.zeros(1)
+        assert probe.probe_ewaldt_surface(10.0, 0.3, eps, x.size, *[a.ctypes.data_as(_dp) for a in (x, y, z, q, mu[0], mu[1], mu[2])], V,
+                                          e.ctypes.data_as(_dp)) == 0
+        # |sum|^2 of sums that cancel: compare on the scale of the squared sums of magnitudes
+        scale = 2.0 * np.pi / abs(2.0 * eps + 1.0) / V * sum((np.sum(np.abs(c * q)) + np.sum(np.abs(m))) ** 2 for c, m in zip((x, y, z), mu)) \
+            if np.isfinite(eps) else 0.0
+        for val in (got, float(e[0])):
+            assert abs(val - ref) <= 1e-13 * scale, (eps, val, ref)
+        if not np.isfinite(eps):
+            assert got == 0.0 and e[0] == 0.0 and ref == 0.0
+        ev.close()

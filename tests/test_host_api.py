@@ -147,6 +147,34 @@ def test_splined_wrapper(probe, name, oracle_kind):
     assert np.max(np.abs(sh - analytic)) <= 2.1e-3
 
 
+def test_qpochhammer_free_functions(probe, oracle_kind):
+    """qPochhammerSymbol and its three derivative functions (reference qpotential.hpp:50-192): the reference's own known
+    answers (test/unittests.cpp:66-85, default doctest tolerance) and the live oracle on a (q, l, P) grid."""
+    probe.probe_qpochhammer.argtypes = [C.c_double, C.c_int, C.c_int, _dp]
+    probe.probe_qpochhammer.restype = None
+
+    def f(q, l, P):
+        o = np.zeros(4)
+        probe.probe_qpochhammer(q, l, P, _f(o))
+        return o
+    kat = [  # (q, l, P, derivative order, value)  unittests.cpp:68-84
+        (0.5, 0, 0, 0, 1.0), (0.0, 0, 1, 0, 1.0), (1.0, 0, 1, 0, 0.0), (1.0, 1, 2, 0, 0.0), (0.75, 0, 2, 0, 0.109375),
+        (2.0 / 3.0, 2, 5, 0, 0.4211104676), (0.125, 1, 1, 0, 0.984375), (0.75, 0, 2, 1, -0.8125), (2.0 / 3.0, 2, 5, 1, -2.538458169),
+        (0.125, 1, 1, 1, -0.25), (0.75, 0, 2, 2, 2.5), (2.0 / 3.0, 2, 5, 2, -1.444601767), (0.125, 1, 1, 2, -2.0), (0.75, 0, 2, 3, 6.0),
+        (2.0 / 3.0, 2, 5, 3, 92.48631425), (0.125, 1, 1, 3, 0.0), (0.4, 3, 7, 3, -32.80472205)]
+    eps = 100 * np.finfo(np.float32).eps  # doctest::Approx default
+    for q, l, P, k, v in kat:
+        got = f(q, l, P)[k]
+        assert abs(got - v) < eps * (1.0 + max(abs(got), abs(v))), (q, l, P, k, got, v)
+    for l in (0, 1, 2, 5):
+        for P in (1, 2, 3, 6, 12):
+            for q in (0.05, 0.3, 0.5, 0.77, 0.93):
+                ref, got = O.qpochhammer(q, l, P, oracle_kind), f(q, l, P)
+                # the reference forms the derivatives from log-derivative sums; 1e-12 of the largest term of each sum
+                scale = np.maximum(np.abs(ref), np.abs(O.qpochhammer(q, l, P, oracle_kind)).max())
+                assert np.all(np.abs(got - ref) <= 1e-12 * scale * (1 + P * (P + l)) ** 2), (q, l, P, got, ref)
+
+
 def test_constructor_errors_and_static_use(probe):
     for C_, D in ((0, 3), (3, -2), (3, 0)):
         with pytest.raises(ValueError):
