@@ -208,3 +208,18 @@ class BatchedEvaluator:
         t, ms = C.c_double(0), C.c_double(0)
         check(lib.cg_fp64_peak_probe(self.h, C.byref(t), C.byref(ms)), "cg_fp64_peak_probe", self.h)
         return t.value, ms.value
+
+
+def eval_multi_device(evaluators, mode, what, force=None, field=None, potential=None, scalars=None):
+    """Several schemes in one pass over the pairs (cg_eval_multi_device): `evaluators` evaluate the same system (the first
+    owns it, the others borrowed it with share_system); force / field / potential / scalars are lists of device tensors, one
+    per evaluator (or None).  Raises CgError(CG_ERR_UNSUPPORTED) where the fused pass does not apply."""
+    n = len(evaluators)
+
+    def arr(lst):
+        if lst is None:
+            return None
+        return (C.c_void_p * n)(*[_devptr(t) for t in lst])
+    hs = (C.c_void_p * n)(*[ev.h.value for ev in evaluators])
+    check(lib.cg_eval_multi_device(hs, n, mode, what, arr(force), arr(field), arr(potential), arr(scalars)), "cg_eval_multi_device",
+          evaluators[0].h)

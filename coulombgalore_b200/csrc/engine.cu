@@ -50,6 +50,7 @@ const FunctorEntry *entry_ewald_screened();
 const FunctorEntry *entry_ewaldt();
 const FunctorEntry *entry_spline();
 const FunctorEntry *entry_spline_yukawa();
+const FunctorEntry *entry_erfc_multi2();
 
 const FunctorEntry *functor_entry(int id) {
     switch (id) {
@@ -70,6 +71,7 @@ const FunctorEntry *functor_entry(int id) {
     case kFnEwaldT: return entry_ewaldt();
     case kFnSpline: return entry_spline();
     case kFnSplineYukawa: return entry_spline_yukawa();
+    case kFnErfcMulti2: return entry_erfc_multi2();
     default: return nullptr;
     }
 }
@@ -139,53 +141,54 @@ __device__ __forceinline__ int images_1d(const SortParams &sp, int d, double v, 
     return m;
 }
 
-// counts[0] = sorted entries, counts[1] = i-groups, counts[2] = overflow flag (an array was smaller than needed)
+// counts[0] = sorted entries, counts[1] = i-groups, counts[2] = overflow flag (an array was smaller than needed, or a particle
+// lies outside the cached bounding box of an open system)
+// SCATTER = false: histogram (cell_count[cell]++).  SCATTER = true: every (particle, image) takes the slot
+// cell_start[cell] + --cell_count[cell]: the histogram counts back down to zero, no second clearing pass; the order inside a
+// cell is arbitrary here and made deterministic by the gather (ascending key).
 template <bool SCATTER>
-__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int cap,
-                           int *counts) {
+__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int *cell_of,
+                           int cap, int *counts) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     // more valid particles on the device than the arrays this evaluation was given (halo exchange: the received count
     // outgrew the caller's bound): the results would silently miss particles, so the evaluation is marked invalid
     if (p == 0 && sp.n_dev && *sp.n_dev > sp.n) counts[2] = 1;
     if (p >= (sp.n_dev ? min(*sp.n_dev, sp.n) : sp.n)) return;
+    const double rx = sp.x[p] - sp.lo[0], ry = sp.y[p] - sp.lo[1], rz = sp.z[p] - sp.lo[2];
+    if (!SCATTER && !sp.pbc) { // open system laid out from the cached bounding box of an earlier evaluation: still inside?
+        if (!(rx >= 0.0 && rx <= sp.box[0] && ry >= 0.0 && ry <= sp.box[1] && rz >= 0.0 && rz <= sp.box[2])) counts[2] = 1;
+    }
     int sx[3], cx[3], sy[3], cy[3], sz[3], cz[3];
-    const int mx = images_1d(sp, 0, sp.x[p] - sp.lo[0], sx, cx);
-    const int my = images_1d(sp, 1, sp.y[p] - sp.lo[1], sy, cy);
-    const int mz = images_1d(sp, 2, sp.z[p] - sp.lo[2], sz, cz);
+    const int mx = images_1d(sp, 0, rx, sx, cx);
+    const int my = images_1d(sp, 1, ry, sy, cy);
+    const int mz = images_1d(sp, 2, rz, sz, cz);
     for (int c = 0; c < mz; c++)
         for (int b = 0; b < my; b++)
             for (int a = 0; a < mx; a++) {
                 const int czl = cz[c] - sp.z0;
                 if (czl < 0 || czl >= sp.nzl) continue; // outside this shard's layers
                 const int cell = (czl * sp.ntot[1] + cy[b]) * sp.ntot[0] + cx[a];
-                const int slot = atomicAdd(&cell_count[cell], 1);
-                if (SCATTER) {
+                if (!SCATTER) {
+                    atomicAdd(&cell_count[cell], 1);
+                } else {
+                    const int slot = atomicSub(&cell_count[cell], 1) - 1;
                     const unsigned int code = (unsigned int)((sx[a] + 1) + 3 * (sy[b] + 1) + 9 * (sz[c] + 1));
                     const int at = cell_start[cell] + slot;
-                    if (at < cap) keys[at] = (unsigned int)p * 27u + code;
-                    else counts[2] = 1;
+                    if (at < cap) {
+                        keys[at] = (unsigned int)p * 27u + code;
+                        cell_of[at] = cell;
+                    } else {
+                        counts[2] = 1;
+                    }
                 }
             }
 }
 
-// make the order inside every cell deterministic: ascending key (cells hold a handful of entries)
-__global__ void cell_sort_kernel(int ncell, const int *cell_start, unsigned int *keys, int cap) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncell) return;
-    const int a = min(cell_start[c], cap), b = min(cell_start[c + 1], cap);
-    for (int i = a + 1; i < b; i++) {
-        const unsigned int k = keys[i];
-        int j = i - 1;
-        while (j >= a && keys[j] > k) {
-            keys[j + 1] = keys[j];
-            j--;
-        }
-        keys[j + 1] = k;
-    }
-}
-
-__global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, double4 *pos,
-                              double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
+// SoA inputs -> sorted AoS arrays.  Thread k takes the key the scatter left at position k of its cell and moves it to its RANK
+// among the keys of that cell (cells hold a handful of entries): ascending key inside every cell, i.e. a deterministic order
+// and bit-reproducible results run to run, without a separate sorting pass.
+__global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, const int *cell_of,
+                              const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     int n_sorted = counts[0];
     if (n_sorted > cap - kDummies) { // no room (the dummy entries need slots too): flag it, stay inside the arrays
@@ -200,56 +203,56 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts
         return;
     }
     const unsigned int key = keys[k];
+    const int cell = cell_of[k];
+    const int a = cell_start[cell], b = min(cell_start[cell + 1], cap);
+    int dst = a;
+    for (int t = a; t < b; t++) dst += keys[t] < key ? 1 : 0; // keys are unique: (particle, image)
     const int p = (int)(key / 27u);
     const int code = (int)(key - (unsigned int)p * 27u);
     const int sx = code % 3 - 1, sy = (code / 3) % 3 - 1, sz = code / 9 - 1;
     // stored coordinate = r_j + shift (the image), formed exactly as oracle/harness.hpp forms it
     const double X = sp.x[p] + (double)sx * sp.box[0], Y = sp.y[p] + (double)sy * sp.box[1], Z = sp.z[p] + (double)sz * sp.box[2];
-    pos[k] = make_double4(X, Y, Z, sp.q ? sp.q[p] : 0.0);
-    if (mu) mu[k] = sp.mx ? make_double4(sp.mx[p], sp.my[p], sp.mz[p], 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
+    pos[dst] = make_double4(X, Y, Z, sp.q ? sp.q[p] : 0.0);
+    if (mu) mu[dst] = sp.mx ? make_double4(sp.mx[p], sp.my[p], sp.mz[p], 0.0) : make_double4(0.0, 0.0, 0.0, 0.0);
     if (quad) { // the pair formulas need S = Q + Q^T and trace(Q) only (detail/pair.hpp: QuadT)
         const double *Q = sp.quad + 9 * (size_t)p;
-        quad[2 * k] = make_double4(2.0 * Q[0], 2.0 * Q[4], 2.0 * Q[8], Q[0] + Q[4] + Q[8]);
-        quad[2 * k + 1] = make_double4(Q[1] + Q[3], Q[2] + Q[6], Q[5] + Q[7], 0.0);
+        quad[2 * dst] = make_double4(2.0 * Q[0], 2.0 * Q[4], 2.0 * Q[8], Q[0] + Q[4] + Q[8]);
+        quad[2 * dst + 1] = make_double4(Q[1] + Q[3], Q[2] + Q[6], Q[5] + Q[7], 0.0);
     }
     const float fx = (float)(X - (sp.lo[0] - sp.gw[0])), fy = (float)(Y - (sp.lo[1] - sp.gw[1])), fz = (float)(Z - (sp.lo[2] - sp.gw[2]));
     // w = |c|^2 of the ROUNDED coordinates (formed in fp64, rounded once): the prefilter expands |c - x_i|^2 around it
-    pos32[k] = make_float4(fx, fy, fz, (float)((double)fx * fx + (double)fy * fy + (double)fz * fz));
-    orig[k] = p;
+    pos32[dst] = make_float4(fx, fy, fz, (float)((double)fx * fx + (double)fy * fy + (double)fz * fz));
+    orig[dst] = p;
 }
 
-// i-groups: per primary cell row, ceil(count/32) groups
-__global__ void row_group_count_kernel(const __grid_constant__ SortParams sp, const int *cell_start, int *row_ngroups, int gsize) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= sp.row1 - sp.row0) return;
+// i-groups of one primary cell row k: its sorted entries [a, b)
+__device__ __forceinline__ void row_span(const SortParams &sp, const int *cell_start, int k, int &a, int &b) {
     const int r = sp.row0 + k;
     const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
     const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
-    const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
-    row_ngroups[k] = (b - a + gsize - 1) / gsize;
+    a = cell_start[rowbase + sp.ghost[0]];
+    b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
 }
 
 __global__ void row_group_emit_kernel(const __grid_constant__ SortParams sp, const int *cell_start, const int *row_gstart, int2 *groups,
                                       int ng_cap, int gsize) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= sp.row1 - sp.row0) return;
-    const int r = sp.row0 + k;
-    const int ry = r % sp.nprim[1], rz = r / sp.nprim[1];
-    const int rowbase = ((rz + sp.ghost[2] - sp.z0) * sp.ntot[1] + (ry + sp.ghost[1])) * sp.ntot[0];
-    const int a = cell_start[rowbase + sp.ghost[0]], b = cell_start[rowbase + sp.ghost[0] + sp.nprim[0]];
+    int a, b;
+    row_span(sp, cell_start, k, a, b);
     int g = row_gstart[k];
     for (int s = a; s < b && g < ng_cap; s += gsize) groups[g++] = make_int2(s, min(gsize, b - s)); // beyond ng_cap: overflow is flagged
 }
 
-// ---- exclusive scan (ints): 4096 elements per block, recursive over block sums ----
-constexpr int kScanThreads = 512, kScanItems = 8, kScanTile = kScanThreads * kScanItems;
+// ---- exclusive scan (ints) over many CTAs, for large grids: 4096 elements per block, recursive over block sums ----
+constexpr int kWideThreads = 512, kWideItems = 8, kWideTile = kWideThreads * kWideItems;
 
 __global__ void scan_tile_kernel(const int *in, int *out, int n, int *tile_sums) {
-    __shared__ int warp_sums[kScanThreads / 32];
-    const int base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
-    int v[kScanItems], sum = 0;
+    __shared__ int warp_sums[kWideThreads / 32];
+    const int base = blockIdx.x * kWideTile + threadIdx.x * kWideItems;
+    int v[kWideItems], sum = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
+    for (int k = 0; k < kWideItems; k++) {
         v[k] = (base + k < n) ? in[base + k] : 0;
         sum += v[k];
     }
@@ -263,53 +266,147 @@ __global__ void scan_tile_kernel(const int *in, int *out, int n, int *tile_sums)
     if (lane == 31) warp_sums[warp] = incl;
     __syncthreads();
     if (warp == 0) {
-        int w = (lane < kScanThreads / 32) ? warp_sums[lane] : 0;
+        int w = (lane < kWideThreads / 32) ? warp_sums[lane] : 0;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
             const int t = __shfl_up_sync(0xffffffffu, w, off);
             if (lane >= off) w += t;
         }
-        if (lane < kScanThreads / 32) warp_sums[lane] = w; // inclusive over warps
+        if (lane < kWideThreads / 32) warp_sums[lane] = w; // inclusive over warps
     }
     __syncthreads();
     int excl = incl - sum + (warp > 0 ? warp_sums[warp - 1] : 0);
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
+    for (int k = 0; k < kWideItems; k++) {
         if (base + k < n) out[base + k] = excl;
         excl += v[k];
     }
-    if (threadIdx.x == kScanThreads - 1 && tile_sums) tile_sums[blockIdx.x] = excl;
+    if (threadIdx.x == kWideThreads - 1 && tile_sums) tile_sums[blockIdx.x] = excl;
 }
 
 __global__ void scan_add_kernel(int *out, int n, const int *tile_offsets) {
     const int off = tile_offsets[blockIdx.x];
-    for (int k = threadIdx.x; k < kScanTile; k += kScanThreads)
-        if (blockIdx.x * kScanTile + k < n) out[blockIdx.x * kScanTile + k] += off;
+    for (int k = threadIdx.x; k < kWideTile; k += kWideThreads)
+        if (blockIdx.x * kWideTile + k < n) out[blockIdx.x * kWideTile + k] += off;
 }
 
-// out[0..n) = exclusive scan of in[0..n).  `tmp` needs >= 4*(n/kScanTile+8) ints.
+// out[0..n) = exclusive scan of in[0..n).  `tmp` needs >= 4*(n/kWideTile+8) ints.
 static cudaError_t exclusive_scan(const int *in, int *out, int n, int *tmp, cudaStream_t st, int *launches) {
     // out[n] (the total) is written afterwards by scan_total_kernel
-    const int tiles = (n + kScanTile) / kScanTile;
-    scan_tile_kernel<<<tiles, kScanThreads, 0, st>>>(in, out, n, tmp);
+    const int tiles = (n + kWideTile) / kWideTile;
+    scan_tile_kernel<<<tiles, kWideThreads, 0, st>>>(in, out, n, tmp);
     (*launches)++;
     if (tiles > 1) {
         int *tile_off = tmp + tiles;
         cudaError_t e = exclusive_scan(tmp, tile_off, tiles, tile_off + tiles + 1, st, launches);
         if (e != cudaSuccess) return e;
-        scan_add_kernel<<<tiles, kScanThreads, 0, st>>>(out, n, tile_off);
+        scan_add_kernel<<<tiles, kWideThreads, 0, st>>>(out, n, tile_off);
         (*launches)++;
     }
     return cudaGetLastError();
 }
 
-// out[n] = out[n-1] + in[n-1]; the total also goes to *total, and *overflow is raised when it exceeds `limit`
-__global__ void scan_total_kernel(const int *in, int *out, int n, int *total, int limit, int *overflow) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const int t = n > 0 ? out[n - 1] + in[n - 1] : 0;
-        out[n] = t;
-        if (total) *total = t;
-        if (overflow && t > limit) *overflow = 1;
+
+// ---- the scans of the sort phase, one kernel, one CTA ----
+// Exclusive scan of the cell histogram -> cell_start (total -> counts[0]), then per primary cell row the number of i-groups
+// (ceil(entries / gsize), a group never crosses a row), its exclusive scan -> row_gstart (total -> counts[1], overflow flag when
+// it exceeds ng_bound) and, when `groups` is given, the group table itself.  The data of one step are a few hundred KB that sit in
+// L2; what a multi-kernel scan costs at these sizes is launches (seven of them before), so one CTA walks the arrays in tiles of
+// kScanTile elements with coalesced 16-byte loads and carries the running total.
+constexpr int kScanThreads = 1024, kScanItems = 4, kScanTile = kScanThreads * kScanItems;
+
+// exclusive scan of v[0..kScanItems) across the CTA; returns the CTA total (all threads)
+__device__ __forceinline__ int block_scan_tile(int (&v)[kScanItems], int *warp_sums) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) sum += v[k];
+    int incl = sum;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    __syncthreads(); // the previous tile's warp_sums have been read
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    int w = warp_sums[lane]; // 32 warps
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, off);
+        if (lane >= off) w += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, w, 31);
+    int excl = incl - sum + __shfl_sync(0xffffffffu, w - warp_sums[lane], warp);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+        const int x = v[k];
+        v[k] = excl;
+        excl += x;
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_groups_kernel(const __grid_constant__ SortParams sp, const int *cell_count, int *cell_start,
+                                                                    int ncell, int cells_done, int *row_gstart, int2 *groups, int ng_bound,
+                                                                    int gsize, int *counts) {
+    __shared__ int warp_sums[32];
+    // ---- cells (cells_done: a many-CTA scan has already filled cell_start[0 .. ncell), only the total is missing) ----
+    int carry = 0;
+    if (cells_done) carry = ncell > 0 ? cell_start[ncell - 1] + cell_count[ncell - 1] : 0;
+    for (int base = 0; base < (cells_done ? 0 : ncell); base += kScanTile) {
+        const int i0 = base + threadIdx.x * kScanItems;
+        int v[kScanItems];
+        if (i0 + kScanItems <= ncell) {
+            const int4 q = *reinterpret_cast<const int4 *>(cell_count + i0);
+            v[0] = q.x, v[1] = q.y, v[2] = q.z, v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k++) v[k] = i0 + k < ncell ? cell_count[i0 + k] : 0;
+        }
+        const int total = block_scan_tile(v, warp_sums);
+        if (i0 + kScanItems <= ncell) {
+            *reinterpret_cast<int4 *>(cell_start + i0) = make_int4(v[0] + carry, v[1] + carry, v[2] + carry, v[3] + carry);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k++)
+                if (i0 + k < ncell) cell_start[i0 + k] = v[k] + carry;
+        }
+        carry += total;
+    }
+    if (threadIdx.x == 0) {
+        cell_start[ncell] = carry;
+        counts[0] = carry;
+    }
+    __threadfence_block();
+    __syncthreads(); // cell_start is complete for this CTA's own reads below
+    // ---- rows -> groups ----
+    const int nrows = sp.row1 - sp.row0;
+    int gcarry = 0;
+    for (int base = 0; base < nrows; base += kScanTile) {
+        const int i0 = base + threadIdx.x * kScanItems;
+        int v[kScanItems], a[kScanItems], b[kScanItems];
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            a[k] = b[k] = 0;
+            if (i0 + k < nrows) row_span(sp, cell_start, i0 + k, a[k], b[k]);
+            v[k] = (b[k] - a[k] + gsize - 1) / gsize;
+        }
+        const int total = block_scan_tile(v, warp_sums);
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) {
+            if (i0 + k >= nrows) continue;
+            int g = v[k] + gcarry;
+            row_gstart[i0 + k] = g;
+            if (groups)
+                for (int s = a[k]; s < b[k] && g < ng_bound; s += gsize) groups[g++] = make_int2(s, min(gsize, b[k] - s));
+        }
+        gcarry += total;
+    }
+    if (threadIdx.x == 0) {
+        row_gstart[nrows] = gcarry;
+        counts[1] = gcarry;
+        if (gcarry > ng_bound) counts[2] = 1;
     }
 }
 
@@ -352,7 +449,7 @@ __global__ void combine_kernel(int64_t len, int split, const double *part, doubl
 
 // deterministic: fixed strided partial sums, then a fixed tree
 __global__ void reduce_items_kernel(const int *counts, int count_index, int split, const double *item_energy,
-                                    const unsigned long long *item_pairs, double *scalars) {
+                                    const unsigned long long *item_pairs, double *scalars, int *work_counter) {
     __shared__ double se[1024];
     __shared__ unsigned long long sp[1024];
     const int items = counts[count_index] * split;
@@ -383,6 +480,7 @@ __global__ void reduce_items_kernel(const int *counts, int count_index, int spli
         __syncthreads();
     }
     if (threadIdx.x == 0) {
+        *work_counter = 0;        // the pair kernel of this evaluation is done with it: ready for the next launch
         scalars[0] = 0.5 * se[0]; // U = 1/2 sum_i sum_j u_ij
         scalars[1] = (double)sp[0];
         if (counts[2]) { // an array overflowed in the sync-free path: the results are invalid, make that unmistakable
@@ -589,8 +687,14 @@ __global__ void peer_gather_kernel(const __grid_constant__ PeerGather g) {
 
 // ---- halo exchange: the owner sorts its particles into one segment per destination rank (those inside the destination's
 // z-window, periodic images included), the destination pulls only its segments.  Block layout (one per rank, peer-mapped):
-//   [0, 256) bytes : int counts[kMaxPeers]      particles of this owner destined to rank t
-//   then           : double seg[nranks][narrays][cap]   (cap = the owner's particle count)
+//   [0, 64)    : int counts[kMaxPeers]      particles of this owner destined to rank t
+//   [64, 128)  : int acks[kMaxPeers]        acks[t] = s + 1 once rank t has finished pulling step s from this block
+//   [128, 132) : int published              = s + 1 once the segments and counts of step s are complete
+//   [132, 136) : int ctas_done              scratch of the publishing kernels
+//   [256, ...) : double seg[nranks][narrays][cap]   (cap = the owner's particle count)
+// Device-side ordering (cg_halo_publish / cg_halo_pull with step >= 0): the owner may only rewrite block b = s & 1 at step s
+// once every rank has acknowledged step s - 2 (acks, written over NVLink by the pullers at the start of their next
+// publish), and a puller may only read it once `published` says s + 1.  Release / acquire at system scope; no collective.
 constexpr int kHaloThreads = 256;
 struct HaloPlan {
     int nranks, narrays, n;          // n = owned particles
@@ -600,7 +704,27 @@ struct HaloPlan {
     double zlo[kMaxPeers], zhi[kMaxPeers], period; // window of rank t: zlo <= z + k period < zhi for some k in {-1, 0, 1}
     unsigned char *block;
     int *block_counts;               // [nblocks][nranks] scratch, then exclusive block offsets
+    int step, rank;                  // step >= 0: device-side flags (see the block layout); -1: the caller orders the ranks
+    unsigned char *ack_block[kMaxPeers]; // step >= 1: the peers' blocks of step - 1 (peer-mapped), where this rank acknowledges its pull
 };
+constexpr int kHaloAckOff = 64, kHaloPubOff = 128, kHaloDoneOff = 132;
+constexpr long long kHaloSpinLimit = 4000000000LL; // clock cycles (~2 s): a peer that never arrives must not hang the GPU
+
+__device__ __forceinline__ int ld_acquire_sys(const int *p) {
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// spin until *p >= want; false on time-out
+__device__ __forceinline__ bool wait_at_least(const int *p, int want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(p) < want) {
+        if (clock64() - t0 > kHaloSpinLimit) return false;
+        __nanosleep(200);
+    }
+    return true;
+}
 __device__ __forceinline__ unsigned halo_mask(const HaloPlan &hp, double z) {
     unsigned m = 0;
     for (int t = 0; t < hp.nranks; t++) {
@@ -615,6 +739,9 @@ __device__ __forceinline__ unsigned halo_mask(const HaloPlan &hp, double z) {
 __global__ void halo_count_kernel(const __grid_constant__ HaloPlan hp) {
     __shared__ int cnt[kMaxPeers];
     if (threadIdx.x < kMaxPeers) cnt[threadIdx.x] = 0;
+    // stream order has put this kernel behind the pull of step - 1: tell every owner that its block of that step is free
+    if (hp.step >= 1 && blockIdx.x == 0 && (int)threadIdx.x < hp.nranks)
+        st_release_sys(reinterpret_cast<int *>(hp.ack_block[threadIdx.x] + kHaloAckOff) + hp.rank, hp.step);
     __syncthreads();
     const int p = blockIdx.x * kHaloThreads + threadIdx.x;
     const unsigned m = p < hp.n ? halo_mask(hp, hp.src[hp.zindex][p]) : 0u;
@@ -626,9 +753,13 @@ __global__ void halo_count_kernel(const __grid_constant__ HaloPlan hp) {
     if (threadIdx.x < hp.nranks) hp.block_counts[blockIdx.x * hp.nranks + threadIdx.x] = cnt[threadIdx.x];
 }
 // pass 2 (one CTA per destination): exclusive scan over the blocks; the total goes to the header of the peer block
-__global__ void __launch_bounds__(1024) halo_scan_kernel(const __grid_constant__ HaloPlan hp, int nblocks) {
+__global__ void __launch_bounds__(1024) halo_scan_kernel(const __grid_constant__ HaloPlan hp, int nblocks, int *err) {
     __shared__ int warp_sum[32];
     const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (hp.step >= 2) { // everyone must have finished pulling step - 2 out of this block before its header is rewritten
+        if (tid < hp.nranks && !wait_at_least(reinterpret_cast<const int *>(hp.block + kHaloAckOff) + tid, hp.step - 1)) *err = 2;
+        __syncthreads();
+    }
     const int chunk = (nblocks + 1023) / 1024;
     const int b0 = min(tid * chunk, nblocks), b1 = min(b0 + chunk, nblocks);
     int sum = 0;
@@ -677,6 +808,19 @@ __global__ void halo_scatter_kernel(const __grid_constant__ HaloPlan hp) {
         double *seg = seg0 + (long long)t * hp.narrays * hp.cap;
         for (int a = 0; a < hp.narrays; a++) seg[(long long)a * hp.cap + pos] = hp.src[a][p];
     }
+    if (hp.step >= 0) { // the last CTA to finish publishes the block
+        __shared__ int last;
+        __threadfence();
+        __syncthreads();
+        int *done = reinterpret_cast<int *>(hp.block + kHaloDoneOff);
+        if (threadIdx.x == 0) last = atomicAdd(done, 1) == (int)gridDim.x - 1;
+        __syncthreads();
+        if (last && threadIdx.x == 0) {
+            *done = 0;
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<int *>(hp.block + kHaloPubOff), hp.step + 1);
+        }
+    }
 }
 
 struct HaloPull {
@@ -685,11 +829,23 @@ struct HaloPull {
     long long cap[kMaxPeers]; // per source rank: its segment capacity (= its particle count)
     double *dst[kMaxPeerArrays];
     long long dst_cap;
-    int *n_out; // [0] particles received, [1] overflow flag
+    int *n_out; // [0] particles received, [1] 1 = dst_cap too small, 2 = a peer did not publish in time
+    int step;   // >= 0: wait for the owners' `published` flags; -1: the caller has ordered the ranks
 };
 // grid: (chunks, narrays, nranks).  Every CTA reads the nranks counts from the peer headers (a few NVLink words).
 __global__ void halo_pull_kernel(const __grid_constant__ HaloPull g) {
     const int a = blockIdx.y, r = blockIdx.z;
+    if (g.step >= 0) { // the counts of ALL owners are read below: wait for every block (a few NVLink words per CTA)
+        __shared__ int bad;
+        if (threadIdx.x == 0) bad = 0;
+        __syncthreads();
+        if ((int)threadIdx.x < g.nranks && !wait_at_least(reinterpret_cast<const int *>(g.block[threadIdx.x] + kHaloPubOff), g.step + 1)) bad = 1;
+        __syncthreads();
+        if (bad) {
+            if (threadIdx.x == 0) g.n_out[1] = 2;
+            return;
+        }
+    }
     long long off = 0;
     int mine = 0;
     for (int s = 0; s < g.nranks; s++) {
@@ -699,7 +855,7 @@ __global__ void halo_pull_kernel(const __grid_constant__ HaloPull g) {
     }
     if (a == 0 && r == g.nranks - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
         g.n_out[0] = (int)min(off + mine, g.dst_cap);
-        g.n_out[1] = off + mine > g.dst_cap ? 1 : 0;
+        if (off + mine > g.dst_cap) g.n_out[1] = 1;
     }
     long long n = mine;
     if (off + n > g.dst_cap) n = max(0LL, g.dst_cap - off);
@@ -765,6 +921,7 @@ struct cg_handle {
     // sorted system
     DevBuf<int> cell_count, cell_start, scan_tmp, row_ngroups, row_gstart[2], orig;
     DevBuf<unsigned int> keys;
+    DevBuf<int> cell_of; // cell of every scattered key
     DevBuf<double4> pos, mu, quad;
     const double *in_quad = nullptr; // device [n][9] (own copy or the caller's); reset by cg_set_system*
     DevBuf<double> own_quad;
@@ -788,6 +945,7 @@ struct cg_handle {
         double box[3] = {0, 0, 0};
         int shard_rank = 0, shard_n = 1;
         int cap_sorted = 0, last_groups[2] = {0, 0};
+        double lo[3] = {0, 0, 0}, ext[3] = {0, 0, 0}; // open systems: the padded bounding box the grid was laid out from
     } fast;
     bool last_overflow = false;
     Sorted sorted;
@@ -806,6 +964,7 @@ struct cg_handle {
     double *h_scalars = nullptr; // pinned
     double ms[4] = {0, 0, 0, 0};
     int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cg_handle *multi_of = nullptr; // last evaluated as a further scheme of that handle's multi-scheme launch (timings: see there)
 };
 
 static thread_local std::string g_create_error;
@@ -949,6 +1108,7 @@ int cg_destroy(cg_handle *h) {
     h->row_gstart[1].release();
     h->orig.release();
     h->keys.release();
+    h->cell_of.release();
     h->pos.release();
     h->mu.release();
     h->quad.release();
@@ -1170,12 +1330,26 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
     sp.quad = h->in_quad;
     sp.n_dev = h->n_dev;
     sp.pbc = h->pbc ? 1 : 0;
+    static const bool fast_enabled = [] {
+        const char *e = std::getenv("CG_SYNC_FREE");
+        return !(e && e[0] == '0');
+    }();
     double ext[3];
+    bool open_cached = false;
     if (h->pbc) {
         for (int d = 0; d < 3; d++) {
             sp.lo[d] = 0.0;
             ext[d] = h->box[d];
         }
+    } else if (fast_enabled && h->fast.valid && !h->fast.pbc && h->fast.n == h->n && h->fast.shard_rank == h->shard_rank &&
+               h->fast.shard_n == h->shard_n) {
+        // open system, same shape as the previous evaluation: lay the grid out from its (padded) bounding box instead of
+        // asking the device for the new one; bin_kernel flags a particle that has left it and the evaluation is redone
+        for (int d = 0; d < 3; d++) {
+            sp.lo[d] = h->fast.lo[d];
+            ext[d] = h->fast.ext[d];
+        }
+        open_cached = true;
     } else {
         const int nb = 64;
         CG_CUDA(h, h->minmax_partial.ensure(6 * nb));
@@ -1189,9 +1363,12 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
                 lo = std::min(lo, h->h_minmax[b * 6 + d]);
                 hi = std::max(hi, h->h_minmax[b * 6 + 3 + d]);
             }
-            sp.lo[d] = lo;
-            ext[d] = std::max(hi - lo, 1e-9 * std::max(1.0, std::fabs(hi)));
-            ext[d] *= (1.0 + 1e-12);
+            // 2 % room on either side: the next evaluations of a slowly changing configuration reuse this box
+            const double w = std::max(hi - lo, 1e-9 * std::max(1.0, std::fabs(hi)));
+            sp.lo[d] = lo - 0.02 * w;
+            ext[d] = 1.04 * w * (1.0 + 1e-12);
+            h->fast.lo[d] = sp.lo[d];
+            h->fast.ext[d] = ext[d];
         }
     }
     layout_grid(rc, h->pbc, ext, h->grid_count > 0 ? (double)h->grid_count : (double)n, h->shard_rank, h->shard_n, sp);
@@ -1209,59 +1386,55 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
         h->fast.last_groups[1] = h->h_counts_async[3];
         if (h->last_overflow || h->h_counts_async[0] + 1024 > h->fast.cap_sorted) h->fast.valid = false;
     }
-    static const bool fast_enabled = [] {
-        const char *e = std::getenv("CG_SYNC_FREE");
-        return !(e && e[0] == '0');
-    }();
-    bool fast = fast_enabled && h->fast.valid && h->pbc && h->fast.pbc && h->fast.n == h->n && h->fast.shard_rank == h->shard_rank &&
-                h->fast.shard_n == h->shard_n && h->fast.box[0] == h->box[0] && h->fast.box[1] == h->box[1] && h->fast.box[2] == h->box[2];
+    bool fast = fast_enabled && h->fast.valid && h->fast.pbc == h->pbc && h->fast.n == h->n && h->fast.shard_rank == h->shard_rank &&
+                h->fast.shard_n == h->shard_n &&
+                (h->pbc ? (h->fast.box[0] == h->box[0] && h->fast.box[1] == h->box[1] && h->fast.box[2] == h->box[2]) : open_cached);
     // a group table that was never built before (a borrower asked for it) has no previous count to size it from
     if ((need32 && h->fast.last_groups[0] == 0) || (need64 && h->fast.last_groups[1] == 0)) fast = false;
 
-    // ---- 1-3. histogram, scan, groups ----
-    int *counts = h->d_counts.p;
-    CG_CUDA(h, h->cell_count.ensure((size_t)ncell + 1));
-    CG_CUDA(h, h->cell_start.ensure((size_t)ncell + 2));
-    CG_CUDA(h, h->scan_tmp.ensure(4 * ((size_t)std::max(ncell, nrows_prim) / kScanTile + 8) + 64));
-    CG_CUDA(h, h->row_ngroups.ensure((size_t)nrows_prim + 1));
-    const bool need_groups[2] = {need32, need64};
-    for (int t = 0; t < 2; t++)
-        if (need_groups[t]) CG_CUDA(h, h->row_gstart[t].ensure((size_t)nrows_prim + 2));
-    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
-    CG_CUDA(h, cudaMemsetAsync(counts, 0, 4 * sizeof(int), st));
+    // ---- 1-3. histogram, scans, groups ----
+    // device counts and the cell histogram share one array (one clearing pass): [0, 8) the counts, then ncell + 1 cells
+    CG_CUDA(h, h->cell_count.ensure((size_t)ncell + 16));
+    int *counts = h->cell_count.p;
+    int *hist = h->cell_count.p + 8;
+    CG_CUDA(h, h->cell_start.ensure((size_t)ncell + 8));
+    CG_CUDA(h, h->row_gstart[0].ensure((size_t)nrows_prim + 8));
+    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 9) * sizeof(int), st));
     const int nb_p = (n + 255) / 256;
-    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, nullptr, nullptr, 0, counts);
-    (*launches_out)++;
-    CG_CUDA(h, exclusive_scan(h->cell_count.p, h->cell_start.p, ncell, h->scan_tmp.p, st, launches_out));
-    scan_total_kernel<<<1, 32, 0, st>>>(h->cell_count.p, h->cell_start.p, ncell, counts + 0, 0, nullptr);
+    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, hist, nullptr, nullptr, nullptr, 0, counts);
     (*launches_out)++;
     int cap_sorted = 0, ng_bound[2] = {0, 0}, ng_guess[2] = {0, 0};
-    for (int t = 0; t < 2; t++) {
-        if (!need_groups[t]) continue;
-        const int gsize = 32 << t;
-        row_group_count_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_ngroups.p, gsize);
-        (*launches_out)++;
-        CG_CUDA(h, exclusive_scan(h->row_ngroups.p, h->row_gstart[t].p, nrows_prim, h->scan_tmp.p, st, launches_out));
-        if (fast) { // the launch shape comes from the previous evaluation: the last count with some room, at most the strict
-            ng_guess[t] = h->fast.last_groups[t]; // bound (a partial group per primary row)
-            ng_bound[t] = std::min(n / gsize + nrows_prim + 2, ng_guess[t] + ng_guess[t] / 8 + 64);
-        } else {
-            ng_bound[t] = 0x7fffffff;
-        }
-        scan_total_kernel<<<1, 32, 0, st>>>(h->row_ngroups.p, h->row_gstart[t].p, nrows_prim, counts + (t ? 3 : 1), ng_bound[t], counts + 2);
-        (*launches_out)++;
+    const bool need_groups[2] = {true, false};
+    (void)need32;
+    (void)need64;
+    const int gsize = 32;
+    // small grids (a shard of a 10^6-particle system, a few thousand particles): the one-CTA kernel scans the cells too; large
+    // grids: a many-CTA scan first (measured at 157 464 cells: 12 us against 40 us for the single CTA)
+    const int cells_done = ncell > 32768 ? 1 : 0;
+    if (cells_done) {
+        CG_CUDA(h, h->scan_tmp.ensure(4 * ((size_t)ncell / kWideTile + 8) + 64));
+        CG_CUDA(h, exclusive_scan(hist, h->cell_start.p, ncell, h->scan_tmp.p, st, launches_out));
     }
-    if (fast) { // array sizes come from the previous evaluation too; no host round trip
+    if (fast) {
+        // array sizes and the launch shape come from the previous evaluation: the last counts with some room, at most the
+        // strict bound (a partial group per primary row); no host round trip
         cap_sorted = h->fast.cap_sorted;
+        ng_guess[0] = h->fast.last_groups[0];
+        ng_bound[0] = std::min(n / gsize + nrows_prim + 2, ng_guess[0] + ng_guess[0] / 8 + 64);
+        CG_CUDA(h, h->groups[0].ensure((size_t)ng_bound[0] + 1));
+        scan_groups_kernel<<<1, kScanThreads, 0, st>>>(sp, hist, h->cell_start.p, ncell, cells_done, h->row_gstart[0].p, h->groups[0].p, ng_bound[0], gsize,
+                                                       counts);
+        (*launches_out)++;
     } else {
+        scan_groups_kernel<<<1, kScanThreads, 0, st>>>(sp, hist, h->cell_start.p, ncell, cells_done, h->row_gstart[0].p, nullptr, 0x7fffffff, gsize, counts);
+        (*launches_out)++;
         CG_CUDA(h, cudaMemcpyAsync(h->h_counts, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CG_CUDA(h, cudaStreamSynchronize(st));
         const int n_sorted = h->h_counts[0];
         cap_sorted = n_sorted + n_sorted / 12 + 4096;
         ng_bound[0] = ng_guess[0] = h->h_counts[1];
-        ng_bound[1] = ng_guess[1] = h->h_counts[3];
         h->counters[0] = n_sorted;
-        h->fast.valid = h->pbc;
+        h->fast.valid = h->h_counts[2] == 0;
         h->fast.n = h->n;
         h->fast.pbc = h->pbc;
         for (int d = 0; d < 3; d++) h->fast.box[d] = h->box[d];
@@ -1269,21 +1442,21 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
         h->fast.shard_n = h->shard_n;
         h->fast.cap_sorted = cap_sorted;
         h->fast.last_groups[0] = ng_guess[0];
-        h->fast.last_groups[1] = ng_guess[1];
+        CG_CUDA(h, h->groups[0].ensure((size_t)ng_bound[0] + 1));
+        row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart[0].p, h->groups[0].p,
+                                                                                     ng_bound[0], gsize);
+        (*launches_out)++;
     }
 
-    // ---- 4-5. scatter, deterministic order, gather ----
+    // ---- 4-5. scatter, gather into ascending-key order ----
     CG_CUDA(h, h->keys.ensure((size_t)cap_sorted));
+    CG_CUDA(h, h->cell_of.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->pos.ensure((size_t)cap_sorted));
     if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)cap_sorted));
     if (need_quad) CG_CUDA(h, h->quad.ensure(2 * (size_t)cap_sorted));
     CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
-    for (int t = 0; t < 2; t++)
-        if (need_groups[t]) CG_CUDA(h, h->groups[t].ensure((size_t)ng_bound[t] + 1));
-    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 1) * sizeof(int), st));
-    bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, h->cell_count.p, h->cell_start.p, h->keys.p, cap_sorted, counts);
-    cell_sort_kernel<<<(ncell + 127) / 128, 128, 0, st>>>(ncell, h->cell_start.p, h->keys.p, cap_sorted);
+    bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, hist, h->cell_start.p, h->keys.p, h->cell_of.p, cap_sorted, counts);
     double far_coord;
     {
         double span = 0.0, lo = 0.0;
@@ -1293,15 +1466,9 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
         }
         far_coord = lo - 4.0 * span - 4.0 * std::min(rc, 1e9) - 1.0;
     }
-    gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->pos.p, need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p,
-                                                         h->orig.p, far_coord);
-    for (int t = 0; t < 2; t++) {
-        if (!need_groups[t]) continue;
-        row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart[t].p, h->groups[t].p,
-                                                                                     ng_bound[t], 32 << t);
-        (*launches_out)++;
-    }
-    *launches_out += 3;
+    gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->cell_of.p, h->cell_start.p, h->pos.p,
+                                                         need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p, h->orig.p, far_coord);
+    *launches_out += 2;
     CG_CUDA(h, cudaGetLastError());
     // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
     CG_CUDA(h, cudaMemcpyAsync(h->h_counts_async, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1322,8 +1489,16 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
     return CG_OK;
 }
 
+// further schemes evaluated in the same pass (cg_eval_multi_device): their handles and outputs, scheme 0 being `h` itself
+struct MultiArgs {
+    int n;
+    cg_handle *const *hs;
+    double *const *force, *const *field, *const *pot, *const *scalars;
+};
+
 // the evaluation proper; outputs are device pointers (may be null)
-static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars) {
+static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars,
+                            const MultiArgs *ma = nullptr) {
     cg_handle *sys = h->share_from ? h->share_from : h;
     if (!sys->have_system) {
         h->err = "cg_eval before cg_set_system";
@@ -1394,7 +1569,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     const SortParams &sp = S.sp;
     const int ncell = S.ncell, cap_sorted = S.cap_sorted, ng_bound = S.ng_bound[gt], ng_guess = S.ng_guess[gt];
     const bool need_mu = mode != CG_MODE_ION, fast = S.fast;
-    int *counts = s->d_counts.p;
+    int *counts = s->cell_count.p; // [0, 8): the device counts of the lender's sort
     CG_CUDA(h, cudaEventRecord(h->ev[1], st));
 
     // ---- 6. pair kernel ----
@@ -1476,8 +1651,10 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         std::memcpy(&bits, &cap, sizeof(bits));
         kp.r2cap_hi = (int)(bits >> 32);
     }
-    CG_CUDA(h, h->work_counter.ensure(1));
-    CG_CUDA(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(int), st));
+    if (!h->work_counter.p) { // zeroed once; every evaluation's reduce_items_kernel leaves it at zero for the next
+        CG_CUDA(h, h->work_counter.ensure(1));
+        CG_CUDA(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(int), st));
+    }
     kp.work_counter = h->work_counter.p;
     kp.core.inverse_cutoff = D.inverse_cutoff;
     kp.core.cutoff_squared = D.cutoff_squared;
@@ -1514,8 +1691,26 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.potential = o_pot;
     }
     (void)cwhat;
-    const FunctorEntry *fe = functor_entry(h->functor);
+    const FunctorEntry *fe = functor_entry(ma ? (int)kFnErfcMulti2 : h->functor);
     if (!fe) return CG_ERR_INVALID;
+    cg_scheme_desc Dm = D; // the descriptor the functor is built from
+    if (ma) {
+        if (split > 1) {
+            h->err = "cg_eval_multi_device: the system is too small (j-split evaluation); evaluate the schemes one by one";
+            return CG_ERR_UNSUPPORTED;
+        }
+        Dm.reserved0 = 0;
+        CG_CUDA(h, h->item_energy.ensure((size_t)std::max(items, 1) * (size_t)ma->n));
+        kp.item_energy = h->item_energy.p;
+        for (int k = 0; k < ma->n; k++) {
+            Dm.reserved0 |= (ma->hs[k]->desc.functor & 255) << (8 * k);
+            if (k == 0) continue;
+            kp.force_k[k - 1] = (what & CG_FORCE) ? ma->force[k] : nullptr;
+            kp.field_k[k - 1] = (what & CG_FIELD) ? ma->field[k] : nullptr;
+            kp.potential_k[k - 1] = (what & CG_POTENTIAL) ? ma->pot[k] : nullptr;
+            kp.item_energy_k[k - 1] = h->item_energy.p + (size_t)k * (size_t)std::max(items, 1);
+        }
+    }
     const double *dev_table = nullptr;
     int table_doubles = 0;
     if (fe->table_kind == cgd::kTableSpline) {
@@ -1535,7 +1730,9 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     }
 #endif
     if (items > 0) {
-        CG_CUDA(h, (h->precision == CG_FP32 ? fe->pair32[ci] : fe->pair[ci])(kp, D, dev_table, table_doubles, items, device_sms, st));
+        const pair_launch_fn launch = h->precision == CG_FP32 ? fe->pair32[ci] : fe->pair[ci];
+        if (!launch) return CG_ERR_UNSUPPORTED;
+        CG_CUDA(h, launch(kp, Dm, dev_table, table_doubles, items, device_sms, st));
 #ifdef CG_KPROF
         if (kprof) {
             unsigned long long c[16];
@@ -1571,8 +1768,15 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
             launches++;
         }
     }
-    reduce_items_kernel<<<1, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_energy.p, h->item_pairs.p, d_scalars);
+    reduce_items_kernel<<<1, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_energy.p, h->item_pairs.p, d_scalars, h->work_counter.p);
     launches++;
+    if (ma)
+        for (int k = 1; k < ma->n; k++) {
+            double *sck = ma->scalars[k];
+            if (!sck) continue;
+            reduce_items_kernel<<<1, 1024, 0, st>>>(counts, 1, split, kp.item_energy_k[k - 1], h->item_pairs.p, sck, h->work_counter.p);
+            launches++;
+        }
     CG_CUDA(h, cudaGetLastError());
     CG_CUDA(h, cudaEventRecord(h->ev[3], st));
     h->counters[1] = ncell;
@@ -1589,6 +1793,46 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential, double *scalars) {
     if (!h) return CG_ERR_INVALID;
     return eval_device_impl(h, mode, what, force, field, potential, scalars);
+}
+
+int cg_eval_multi_device(cg_handle *const *hs, int n, int mode, int what, double *const *force, double *const *field,
+                         double *const *potential, double *const *scalars) {
+    if (!hs || n < 1 || !hs[0]) return CG_ERR_INVALID;
+    cg_handle *h = hs[0];
+    if (n == 1)
+        return eval_device_impl(h, mode, what, force ? force[0] : nullptr, field ? field[0] : nullptr, potential ? potential[0] : nullptr,
+                                scalars ? scalars[0] : nullptr);
+    if (n != 2 || mode != CG_MODE_ION) {
+        h->err = "cg_eval_multi_device: two schemes, CG_MODE_ION";
+        return CG_ERR_UNSUPPORTED;
+    }
+    cg_handle *sys = h->share_from ? h->share_from : h;
+    for (int k = 0; k < n; k++) {
+        cg_handle *g = hs[k];
+        if (!g) return CG_ERR_INVALID;
+        const bool erfc_family = g->functor == kFnWolf || g->functor == kFnFennell || g->functor == kFnZeroDipole || g->functor == kFnZahn ||
+                                 g->functor == kFnEwald || g->functor == kFnEwaldT;
+        if (!erfc_family || g->desc.inverse_debye_length != 0.0 || g->desc.eta != h->desc.eta || g->desc.cutoff != h->desc.cutoff ||
+            g->precision != h->precision || g->device != h->device) {
+            h->err = "cg_eval_multi_device: the schemes must be unscreened erfc-family schemes (Wolf, Fennell, ZeroDipole, Zahn, Ewald, "
+                     "EwaldTruncated) with one alpha and one cut-off";
+            return CG_ERR_UNSUPPORTED;
+        }
+        if ((g->share_from ? g->share_from : g) != sys) {
+            h->err = "cg_eval_multi_device: all handles must evaluate the same system (cg_share_system)";
+            return CG_ERR_STATE;
+        }
+    }
+    static double *const none[4] = {nullptr, nullptr, nullptr, nullptr};
+    MultiArgs ma = {n, hs, force ? force : none, field ? field : none, potential ? potential : none, scalars ? scalars : none};
+    const int rc = eval_device_impl(h, mode, what, ma.force[0], ma.field[0], ma.pot[0], ma.scalars[0], &ma);
+    if (rc == CG_OK)
+        for (int k = 1; k < n; k++) { // the further schemes shared this launch: same timings and counters
+            for (int t = 0; t < 4; t++) hs[k]->ms[t] = 0.0;
+            for (int t = 0; t < 8; t++) hs[k]->counters[t] = h->counters[t];
+            hs[k]->multi_of = h;
+        }
+    return rc;
 }
 
 int cg_read_scalars(cg_handle *h, const double *scalars_dev, double host2[2]) {
@@ -1828,6 +2072,7 @@ int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out) {
 
 int cg_last_timings(cg_handle *h, double ms[4]) {
     if (!h || !ms) return CG_ERR_INVALID;
+    if (h->multi_of) h = h->multi_of; // evaluated inside that handle's launch
     cudaSetDevice(h->device);
     CG_CUDA(h, cudaEventSynchronize(h->ev[3]));
     float a = 0, b = 0, c = 0, d = 0;
@@ -1861,6 +2106,7 @@ int cg_peer_alloc(int device, size_t bytes, void **ptr, void *handle64) {
         g_create_error = std::string("cg_peer_alloc: ") + cudaGetErrorString(cudaGetLastError());
         return CG_ERR_ALLOC;
     }
+    cudaMemset(*ptr, 0, std::min<size_t>(bytes, 256)); // the header of a halo block: counts, acknowledgements, published word
     cudaIpcMemHandle_t hd;
     const cudaError_t e = cudaIpcGetMemHandle(&hd, *ptr);
     if (e != cudaSuccess) {
@@ -1976,8 +2222,14 @@ size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count) {
 
 int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned, const double *zlo,
                     const double *zhi, double period, void *block) {
+    return cg_halo_publish_step(h, nranks, narrays, zindex, count, owned, zlo, zhi, period, block, -1, 0, nullptr, nullptr);
+}
+
+int cg_halo_publish_step(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned, const double *zlo,
+                         const double *zhi, double period, void *block, int64_t step, int rank, void *const *prev_blocks, int *err_dev) {
     if (!h || !owned || !zlo || !zhi || !block || nranks < 1 || nranks > kMaxPeers || narrays < 1 || narrays > kMaxPeerArrays ||
-        zindex < 0 || zindex >= narrays || count < 0 || count > 0x7fffffff)
+        zindex < 0 || zindex >= narrays || count < 0 || count > 0x7fffffff || step > 0x7ffffff0 || rank < 0 || rank >= nranks ||
+        (step >= 1 && !prev_blocks) || (step >= 0 && !err_dev))
         return CG_ERR_INVALID;
     cudaSetDevice(h->device);
     HaloPlan hp;
@@ -1997,12 +2249,19 @@ int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t c
         hp.zhi[t] = zhi[t];
     }
     hp.block = static_cast<unsigned char *>(block);
+    hp.step = (int)step;
+    hp.rank = rank;
+    if (step >= 1)
+        for (int t = 0; t < nranks; t++) {
+            if (!prev_blocks[t]) return CG_ERR_INVALID;
+            hp.ack_block[t] = static_cast<unsigned char *>(prev_blocks[t]);
+        }
     const int nblocks = std::max(1, (int)((count + kHaloThreads - 1) / kHaloThreads));
     CG_CUDA(h, h->halo_counts.ensure((size_t)nblocks * nranks));
     hp.block_counts = h->halo_counts.p;
     cudaStream_t st = h->stream;
     halo_count_kernel<<<nblocks, kHaloThreads, 0, st>>>(hp);
-    halo_scan_kernel<<<nranks, 1024, 0, st>>>(hp, nblocks);
+    halo_scan_kernel<<<nranks, 1024, 0, st>>>(hp, nblocks, err_dev);
     halo_scatter_kernel<<<nblocks, kHaloThreads, 0, st>>>(hp);
     CG_CUDA(h, cudaGetLastError());
     return CG_OK;
@@ -2010,6 +2269,12 @@ int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t c
 
 int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays, double *const *dst,
                  int64_t dst_cap, int *n_out) {
+    return cg_halo_pull_step(h, nranks, rank, blocks, counts, narrays, dst, dst_cap, n_out, -1);
+}
+
+int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays, double *const *dst,
+                      int64_t dst_cap, int *n_out, int64_t step) {
+    if (step > 0x7ffffff0) return CG_ERR_INVALID;
     if (!h || !blocks || !counts || !dst || !n_out || nranks < 1 || nranks > kMaxPeers || rank < 0 || rank >= nranks || narrays < 1 ||
         narrays > kMaxPeerArrays || dst_cap < 1)
         return CG_ERR_INVALID;
@@ -2032,6 +2297,7 @@ int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, 
     }
     g.dst_cap = dst_cap;
     g.n_out = n_out;
+    g.step = (int)step;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int per = (int)std::max<long long>(1, std::min<long long>((cmax + 255) / 256, std::max(1, 8 * sms / (nranks * narrays))));

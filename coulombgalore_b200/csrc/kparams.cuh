@@ -51,6 +51,8 @@ struct KParams {
     int cap_sorted;       // capacity of the sorted arrays (the dummy entries start at min(counts[0], cap_sorted - kDummies))
     // outputs, indexed by original particle index; with split > 1 they are [split][n] partial buffers
     double *force, *field, *potential;
+    // schemes 1.. of a multi-scheme functor (cg_eval_multi_device): their own outputs and item energies
+    double *force_k[3], *field_k[3], *potential_k[3], *item_energy_k[3];
     double *item_energy;              // [items] sum_j u_ij over the item's pairs (not yet halved)
     unsigned long long *item_pairs;   // [items]
 };
@@ -104,6 +106,7 @@ enum FunctorId {
     kFnEwaldT,
     kFnSpline,
     kFnSplineYukawa,
+    kFnErfcMulti2, // two schemes of the erfc family with one eta, ion modes (cg_eval_multi_device)
     kNumFunctors
 };
 const FunctorEntry *functor_entry(int id);

@@ -182,6 +182,7 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     constexpr int kIlp = pairs_in_flight<MODE>();
     constexpr int kSets = gather_sets<MODE>();
     constexpr int kGather = gather_policy<MODE>();
+    constexpr int kNS = F::kSchemes;
     typedef cgd::Vec3T<T> V3;
     constexpr bool kF32 = !std::is_same<T, double>::value;
     const int fg = lane >> 2, ft = lane & 3;
@@ -273,8 +274,8 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                 if ((4 * primes[k] > nrows || k == 13) && primes[k] < nrows && nrows % primes[k] != 0) rstride = primes[k];
         }
 
-        cgd::AccumT<T> acc; // what the pair arithmetic accumulates into
-        cgd::Accum acc64;   // fp32 path only: running fp64 totals
+        cgd::AccumT<T> acc[kNS]; // what the pair arithmetic accumulates into (one set per scheme of a multi-scheme functor)
+        cgd::Accum acc64[kNS];   // fp32 path only: running fp64 totals
         unsigned int npairs = 0;
 
         // ---- iterator over the candidate batches (warp-uniform; jb/je hold one cell row's run per lane) ----
@@ -443,12 +444,14 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                         const V3 d = {(T)dx, (T)dy, (T)dz};
                         V3 muj = {T(0), T(0), T(0)};
                         if constexpr (MODE != cgd::kModeIon) muj = {(T)mm[s][u].x, (T)mm[s][u].y, (T)mm[s][u].z};
-                        if constexpr (MODE == cgd::kModeMultipoleQuad) {
+                        if constexpr (kNS > 1) {
+                            cgd::pair_accumulate_multi<F, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, acc, pass);
+                        } else if constexpr (MODE == cgd::kModeMultipoleQuad) {
                             const double4 qa = ldg256<kGather>(p.quad + 2 * jj[s][u]), qb = ldg256<kGather>(p.quad + 2 * jj[s][u] + 1);
                             const cgd::QuadT<T> quadj = {(T)qa.x, (T)qa.y, (T)qa.z, (T)qa.w, (T)qb.x, (T)qb.y, (T)qb.z};
-                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc, pass, &quadi, &quadj);
+                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc[0], pass, &quadi, &quadj);
                         } else {
-                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc, pass);
+                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc[0], pass);
                         }
                     }
                 };
@@ -465,15 +468,18 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                 }
             }
             if constexpr (kF32) { // fold this chunk's fp32 partial sums into the fp64 totals
-                acc64.U += (double)acc.U;
-                acc64.Fx += (double)acc.Fx;
-                acc64.Fy += (double)acc.Fy;
-                acc64.Fz += (double)acc.Fz;
-                acc64.Ex += (double)acc.Ex;
-                acc64.Ey += (double)acc.Ey;
-                acc64.Ez += (double)acc.Ez;
-                acc64.phi += (double)acc.phi;
-                acc = cgd::AccumT<T>();
+#pragma unroll
+                for (int k = 0; k < kNS; k++) {
+                    acc64[k].U += (double)acc[k].U;
+                    acc64[k].Fx += (double)acc[k].Fx;
+                    acc64[k].Fy += (double)acc[k].Fy;
+                    acc64[k].Fz += (double)acc[k].Fz;
+                    acc64[k].Ex += (double)acc[k].Ex;
+                    acc64[k].Ey += (double)acc[k].Ey;
+                    acc64[k].Ez += (double)acc[k].Ez;
+                    acc64[k].phi += (double)acc[k].phi;
+                    acc[k] = cgd::AccumT<T>();
+                }
             }
             __syncwarp();
             KPROF_ADD(2); // [2] pair loop
@@ -484,47 +490,51 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         }
 
         // ---- epilogue: per-particle outputs straight from registers, one reduction per item for the scalars ----
-        if constexpr (!kF32) {
-            acc64.U = (double)acc.U;
-            acc64.Fx = (double)acc.Fx;
-            acc64.Fy = (double)acc.Fy;
-            acc64.Fz = (double)acc.Fz;
-            acc64.Ex = (double)acc.Ex;
-            acc64.Ey = (double)acc.Ey;
-            acc64.Ez = (double)acc.Ez;
-            acc64.phi = (double)acc.phi;
-        }
-        double u = 0.0;
-        if (act) {
-            const size_t o = (size_t)slice * (size_t)p.n + (size_t)p.orig[i];
-            if constexpr ((WHAT & cgd::kWhatForce) != 0) {
-                if (p.force) {
-                    p.force[3 * o + 0] = acc64.Fx;
-                    p.force[3 * o + 1] = acc64.Fy;
-                    p.force[3 * o + 2] = acc64.Fz;
-                }
-            }
-            if constexpr ((WHAT & cgd::kWhatField) != 0) {
-                if (p.field) {
-                    p.field[3 * o + 0] = acc64.Ex;
-                    p.field[3 * o + 1] = acc64.Ey;
-                    p.field[3 * o + 2] = acc64.Ez;
-                }
-            }
-            if constexpr ((WHAT & cgd::kWhatPotential) != 0) {
-                if (p.potential) p.potential[o] = acc64.phi;
-            }
-            if ((WHAT & cgd::kWhatEnergy) != 0) u = acc64.U;
-        }
         unsigned int np = npairs; // inactive lanes only ever pop dummies
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            u += __shfl_down_sync(full, u, off);
-            np += __shfl_down_sync(full, np, off);
-        }
-        if (lane == 0) {
-            p.item_energy[item] = u;
-            p.item_pairs[item] = np;
+        for (int off = 16; off > 0; off >>= 1) np += __shfl_down_sync(full, np, off);
+        if (lane == 0) p.item_pairs[item] = np;
+#pragma unroll
+        for (int k = 0; k < kNS; k++) {
+            if constexpr (!kF32) {
+                acc64[k].U = (double)acc[k].U;
+                acc64[k].Fx = (double)acc[k].Fx;
+                acc64[k].Fy = (double)acc[k].Fy;
+                acc64[k].Fz = (double)acc[k].Fz;
+                acc64[k].Ex = (double)acc[k].Ex;
+                acc64[k].Ey = (double)acc[k].Ey;
+                acc64[k].Ez = (double)acc[k].Ez;
+                acc64[k].phi = (double)acc[k].phi;
+            }
+            // scheme 0 writes the launch's main outputs, the further schemes of a multi-scheme functor their own
+            double *o_force = k == 0 ? p.force : p.force_k[k > 0 ? k - 1 : 0], *o_field = k == 0 ? p.field : p.field_k[k > 0 ? k - 1 : 0];
+            double *o_pot = k == 0 ? p.potential : p.potential_k[k > 0 ? k - 1 : 0];
+            double *o_energy = k == 0 ? p.item_energy : p.item_energy_k[k > 0 ? k - 1 : 0];
+            double u = 0.0;
+            if (act) {
+                const size_t o = (size_t)slice * (size_t)p.n + (size_t)p.orig[i];
+                if constexpr ((WHAT & cgd::kWhatForce) != 0) {
+                    if (o_force) {
+                        o_force[3 * o + 0] = acc64[k].Fx;
+                        o_force[3 * o + 1] = acc64[k].Fy;
+                        o_force[3 * o + 2] = acc64[k].Fz;
+                    }
+                }
+                if constexpr ((WHAT & cgd::kWhatField) != 0) {
+                    if (o_field) {
+                        o_field[3 * o + 0] = acc64[k].Ex;
+                        o_field[3 * o + 1] = acc64[k].Ey;
+                        o_field[3 * o + 2] = acc64[k].Ez;
+                    }
+                }
+                if constexpr ((WHAT & cgd::kWhatPotential) != 0) {
+                    if (o_pot) o_pot[o] = acc64[k].phi;
+                }
+                if ((WHAT & cgd::kWhatEnergy) != 0) u = acc64[k].U;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) u += __shfl_down_sync(full, u, off);
+            if (lane == 0) o_energy[item] = u;
         }
     }
     KPROF_FLUSH();
@@ -596,6 +606,19 @@ cudaError_t launch_srf(const cg_scheme_desc &desc, const double *dev_table, int 
      launch_pair<FUNCTOR, YUK, combo(4).mode, combo(4).what, T>, launch_pair<FUNCTOR, YUK, combo(5).mode, combo(5).what, T>,   \
      launch_pair<FUNCTOR, YUK, combo(6).mode, combo(6).what, T>, launch_pair<FUNCTOR, YUK, combo(7).mode, combo(7).what, T>,   \
      launch_pair<FUNCTOR, YUK, combo(8).mode, combo(8).what, double>, launch_pair<FUNCTOR, YUK, combo(9).mode, combo(9).what, double>}
+// ion modes only (combos 0, 1, 2, 7); the other slots stay empty
+#define CGB_PAIR_ROW_ION(FUNCTOR, T)                                                                                       \
+    {launch_pair<FUNCTOR, false, combo(0).mode, combo(0).what, T>, launch_pair<FUNCTOR, false, combo(1).mode, combo(1).what, T>, \
+     launch_pair<FUNCTOR, false, combo(2).mode, combo(2).what, T>, nullptr, nullptr, nullptr, nullptr,                     \
+     launch_pair<FUNCTOR, false, combo(7).mode, combo(7).what, T>, nullptr, nullptr}
+#define CGB_DEFINE_FUNCTOR_ENTRY_ION(NAME, FUNCTOR)                                                                        \
+    namespace cgb {                                                                                                       \
+    const FunctorEntry *NAME() {                                                                                          \
+        static const FunctorEntry e = {CGB_PAIR_ROW_ION(FUNCTOR, double), CGB_PAIR_ROW_ION(FUNCTOR, float), launch_srf<FUNCTOR>, \
+                                       FUNCTOR::kTable};                                                                 \
+        return &e;                                                                                                        \
+    }                                                                                                                     \
+    }
 #define CGB_DEFINE_FUNCTOR_ENTRY(NAME, FUNCTOR, YUK)                                                                  \
     namespace cgb {                                                                                                   \
     const FunctorEntry *NAME() {                                                                                      \

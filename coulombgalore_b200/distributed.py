@@ -190,9 +190,11 @@ class HaloExchange:
 
     Rank t evaluates a block of cell rows and touches only the particles in the cell layers within one cut-off of it
     (`cg_shard_window`).  Per step every rank sorts its owned particles into one segment per destination inside its
-    peer-mapped block (`cg_halo_publish`), one small all-reduce orders the ranks (same two-block protocol as
-    PeerExchange) and every rank pulls just its segments over NVLink (`cg_halo_pull`).  The evaluator then works on the
-    received subset; `ids` maps subset entries back to global particle indices.
+    peer-mapped block (`cg_halo_publish_step`) and pulls just its segments from all blocks over NVLink
+    (`cg_halo_pull_step`).  The ranks are ordered on the device -- a `published` word per block that the pull kernels spin
+    on, acknowledgement words that free a block for rewriting two steps later -- so a step contains no collective at all
+    (CG_HALO_SYNC=nccl: one small all-reduce per step instead).  The evaluator then works on the received subset; `ids` maps
+    subset entries back to global particle indices.
 
         ex = HaloExchange(ev, n_total, box, n_payload)         # payload arrays: x, y, z first, then q / mu as needed
         arrays, ids, n_dev = ex.gather(owned2d)                # owned2d: [n_payload, count] of this rank
@@ -252,6 +254,9 @@ class HaloExchange:
         self.ids_owned = torch.arange(self.lo, self.lo + self.count, dtype=torch.float64, device=self.device)
         self.flag = torch.zeros(1, dtype=torch.float32, device=self.device)
         self.step, self.n_bound = 0, None
+        # CG_HALO_SYNC=nccl: order the ranks with one small all-reduce per step instead of the device-side flags
+        import os
+        self.device_flags = os.environ.get("CG_HALO_SYNC", "flags") != "nccl"
         self._n_host = torch.zeros(2, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else torch.zeros(2, dtype=torch.int32)
         self._n_event = torch.cuda.Event() if self.device.type == "cuda" else None
         self._n_pending, self.last_count = False, 0
@@ -284,11 +289,20 @@ class HaloExchange:
         self.step += 1
         src = (C.c_void_p * self.narrays)(*([owned2d[a].data_ptr() for a in range(self.n_payload)] + [self.ids_owned.data_ptr()]))
         self._keep = owned2d
-        self.check(self.lib.cg_halo_publish(self.ev.h, self.world, self.narrays, 2, self.count, src, self.zlo, self.zhi, self.box[2],
-                                            self.own_ptr[b]), "cg_halo_publish", self.ev.h)
-        dist.all_reduce(self.flag, group=self.group)  # every owner has published block b; nobody still reads the other block
-        self.check(self.lib.cg_halo_pull(self.ev.h, self.world, self.rank, self.block_ptrs[b], self.counts_c, self.narrays, self.recv_c,
-                                         self.capacity, self.n_out.data_ptr()), "cg_halo_pull", self.ev.h)
+        if self.device_flags:
+            # the ranks are ordered on the device: `published` / acknowledgement words in the block headers (cg_b200.h)
+            s = self.step - 1
+            prev = self.block_ptrs[(s - 1) & 1] if s >= 1 else None
+            self.check(self.lib.cg_halo_publish_step(self.ev.h, self.world, self.narrays, 2, self.count, src, self.zlo, self.zhi, self.box[2],
+                                                     self.own_ptr[b], s, self.rank, prev, self.n_out.data_ptr() + 4), "cg_halo_publish_step", self.ev.h)
+            self.check(self.lib.cg_halo_pull_step(self.ev.h, self.world, self.rank, self.block_ptrs[b], self.counts_c, self.narrays, self.recv_c,
+                                                  self.capacity, self.n_out.data_ptr(), s), "cg_halo_pull_step", self.ev.h)
+        else:
+            self.check(self.lib.cg_halo_publish(self.ev.h, self.world, self.narrays, 2, self.count, src, self.zlo, self.zhi, self.box[2],
+                                                self.own_ptr[b]), "cg_halo_publish", self.ev.h)
+            dist.all_reduce(self.flag, group=self.group)  # every owner has published block b; nobody still reads the other block
+            self.check(self.lib.cg_halo_pull(self.ev.h, self.world, self.rank, self.block_ptrs[b], self.counts_c, self.narrays, self.recv_c,
+                                             self.capacity, self.n_out.data_ptr()), "cg_halo_pull", self.ev.h)
         if self.n_bound is None:  # first step: one host read to size the engine's launches (later steps reuse it)
             got = self.n_out.cpu()
             if int(got[1]) != 0:
@@ -325,6 +339,8 @@ class HaloExchange:
     def check_overflow(self):
         """Host read of the overflow flag and the received count (synchronises)."""
         got = self.n_out.cpu()
+        if int(got[1]) == 2:
+            raise RuntimeError("HaloExchange: a peer rank did not publish / acknowledge its block in time")
         if int(got[1]) != 0 or (self.n_bound is not None and int(got[0]) > self.n_bound):
             raise RuntimeError("HaloExchange: received %d particles, bound %s, capacity %d" % (int(got[0]), self.n_bound, self.capacity))
         return int(got[0])

@@ -192,6 +192,17 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs);
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,
                    double *scalars);
 
+/* Several schemes in ONE pass over the pairs.  hs[0..n) evaluate the same system (hs[0] owns it or borrows it, the others
+ * borrow the same one through cg_share_system) with the same mode and outputs; force / field / potential / scalars are arrays
+ * of n DEVICE pointers (NULL arrays or entries allowed), one per scheme.  The binning, the prefilter, the walk over the hit
+ * lists, the gathers, the distance and 1/r are done once per pair; schemes of the erfc family that share alpha also share
+ * erfc(eta q) and exp(-eta^2 q^2) and differ by a cubic polynomial each (detail/srf.hpp: ErfcMultiSrf).  Supported: n = 2,
+ * CG_MODE_ION, unscreened Wolf / Fennell / ZeroDipole / Zahn / Ewald / EwaldTruncated with one alpha and one cut-off, systems
+ * large enough not to need the j-split; CG_ERR_UNSUPPORTED otherwise (evaluate one by one then).  n = 1 is cg_eval_device.
+ * The results agree with the one-by-one evaluation to rounding (1e-15 relative), the pair counts exactly.  Timings and
+ * counters of the launch are reported for every handle. */
+int cg_eval_multi_device(cg_handle *const *hs, int n, int mode, int what, double *const *force, double *const *field,
+                         double *const *potential, double *const *scalars);
 /* two scalars written by cg_eval_device (a DEVICE pointer) -> host; waits for the handle's stream */
 int cg_read_scalars(cg_handle *h, const double *scalars_dev, double host2[2]);
 
@@ -263,6 +274,19 @@ int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t c
                     const double *zlo, const double *zhi, double period, void *block);
 int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays,
                  double *const *dst, int64_t dst_cap, int *n_out);
+/* The same two calls with the ranks ordered ON THE DEVICE instead of by a collective of the caller: `step` = 0, 1, 2, ...
+ * counts the exchange steps (the same on every rank), block = the rank's block number step % 2.  The owner's last publishing
+ * CTA sets a `published` word in the block header (st.release.sys), cg_halo_pull_step spins on the owners' words
+ * (ld.acquire.sys over NVLink) before it reads; the pullers acknowledge at the start of their next publish -- prev_blocks =
+ * all ranks' blocks of step - 1, peer-mapped, needed from step 1 on -- and an owner waits for the acknowledgements of step - 2
+ * before it rewrites that block.  A peer that does not show up within ~2 s sets *err_dev = 2 / n_out[1] = 2 instead of
+ * hanging the GPU.  One process per GPU only: kernels of two ranks that wait on each other must run at the same time.
+ * New blocks must be zero-filled in their first 256 bytes. */
+int cg_halo_publish_step(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned,
+                         const double *zlo, const double *zhi, double period, void *block, int64_t step, int rank,
+                         void *const *prev_blocks, int *err_dev);
+int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays,
+                      double *const *dst, int64_t dst_cap, int *n_out, int64_t step);
 
 /* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,

@@ -244,5 +244,49 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const TAB &tab, con
     }
 }
 
+// One in-cutoff ordered pair (i <- j) for the NS schemes of an ErfcMultiSrf, ion mode (ion_potential core.hpp:268-280, ion_field
+// :352-365, ion_ion_energy :501, ion_ion_force :630, all with kappa = 0): the geometry, 1/r, erfc and the Gaussian once,
+// then per scheme its polynomial part and its own accumulators.
+template <class F, int WHAT, class T, class TAB>
+CG_HD void pair_accumulate_multi(const F &f, const CoreParams &cp, const TAB &tab, const Vec3T<T> &d, T r2, T zi, T zj,
+                                 AccumT<T> (&acc)[F::kSchemes], bool pass) {
+    const T rinv = rsqrt_pos(r2);
+    const T r1 = r2 * rinv;
+    const T q = r1 * (T)cp.inverse_cutoff;
+    const T x = (T)f.eta * q;
+    T E, ec;
+    erfc_and_gauss(x, ec, E, tab);
+    const T rinv3 = rinv * rinv * rinv;
+    const T zr1 = pass ? zj * rinv : T(0);  // z_j / r
+    const T zr3 = pass ? zj * rinv3 : T(0); // z_j / r^3
+    const T g = ec + (q * (T)f.k1) * E;     // erfc(x) + 2 x exp(-x^2) / sqrt(pi)
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+    for (int k = 0; k < F::kSchemes; k++) {
+        if (WHAT & (kWhatPotential | kWhatEnergy)) {
+            const T s0 = (T)f.m[k] * (ec + (T)f.a0[k] + q * ((T)f.a1[k] + q * ((T)f.a2[k] + q * (T)f.a3[k])));
+            const T p = zr1 * s0;
+            if (WHAT & kWhatPotential) acc[k].phi += p;
+            if (WHAT & kWhatEnergy) acc[k].U += zi * p;
+        }
+        if (WHAT & (kWhatField | kWhatForce)) {
+            const T ang = (T)f.m[k] * (g + (T)f.b0[k] + (q * q) * ((T)f.b2[k] + q * (T)f.b3[k]));
+            const T c = zr3 * ang;
+            if (WHAT & kWhatField) {
+                acc[k].Ex += c * d.x;
+                acc[k].Ey += c * d.y;
+                acc[k].Ez += c * d.z;
+            }
+            if (WHAT & kWhatForce) {
+                const T cf = zi * c;
+                acc[k].Fx += cf * d.x;
+                acc[k].Fy += cf * d.y;
+                acc[k].Fz += cf * d.z;
+            }
+        }
+    }
+}
+
 } // namespace detail
 } // namespace CoulombGalore

@@ -26,6 +26,8 @@ enum { kTableNone = 0, kTableSpline = 1, kTableErfc = 2 };
 struct SrfDefaults {
     // true: the functor offers angcor(q, tab) = S - q S' in closed form (cheaper than S and S' separately)
     static constexpr bool kHasAngcor = false;
+    // schemes evaluated per pair (ErfcMultiSrf: several, each with its own accumulators)
+    static constexpr int kSchemes = 1;
 };
 
 // 2/sqrt(pi); the reference forms it as 2/(2*sqrt(atan(1))) (e.g. wolf.hpp:36), equal to within one ulp
@@ -188,6 +190,52 @@ template <int KIND> struct ErfcFamilySrf : SrfDefaults {
         if (KIND == kZeroDipole) return g - (q * q) * (q * (T)c2);
         if (KIND == kZahn) return g + (q * q) * (T)c2;
         return (g - (T)(c + k1 * e)) * (T)invF0; // kEwaldT
+    }
+};
+
+// Several schemes of the erfc family on ONE pair (batched path only; the reference evaluates one scheme per call): schemes that
+// share eta = alpha R_c and the cut-off differ only in a cubic polynomial added to erfc(eta q), so the expensive part --
+// erfc(x) and exp(-x^2) -- is evaluated once per pair and every scheme costs a short Horner on top:
+//     S_k      = m_k ( erfc(x) + a0_k + a1_k q + a2_k q^2 + a3_k q^3 )
+//     S_k-qS_k' = m_k ( erfc(x) + k1 q exp(-x^2) + b0_k + b2_k q^2 + b3_k q^3 )        (what ion fields and forces need)
+// with the coefficients of wolf.hpp:60-71, fennell.hpp:59-73, zerodipole.hpp:61-80, zahn.hpp:60-76, ewald_truncated.hpp:71-82
+// and ewald.hpp:175-195 (zeta = 0).  NS schemes, NS accumulators: cg_eval_multi_device (include/cg_b200.h).
+template <int NS> struct ErfcMultiSrf : SrfDefaults {
+    static constexpr int kTable = kTableErfc;
+    static constexpr int kSchemes = NS;
+    double eta, k1;
+    double m[NS], a0[NS], a1[NS], a2[NS], a3[NS], b0[NS], b2[NS], b3[NS];
+    CG_HD ErfcMultiSrf() : eta(0), k1(0) {}
+    // d: the descriptor of the first scheme; the functor ids of all NS schemes are packed into d.reserved0, 8 bits each
+    CG_HD explicit ErfcMultiSrf(const cg_scheme_desc &d) : eta(d.eta), k1(d.eta * kTwoOverSqrtPi) {
+        const double c = d.erfc_eta, k1e = k1 * d.exp_eta2, c2 = c + k1e;
+        for (int k = 0; k < NS; k++) {
+            const int id = (d.reserved0 >> (8 * k)) & 255;
+            m[k] = 1.0;
+            a0[k] = a1[k] = a2[k] = a3[k] = b0[k] = b2[k] = b3[k] = 0.0;
+            if (id == CG_WOLF) {
+                a1[k] = -c;
+            } else if (id == CG_FENNELL) {
+                a1[k] = -c - c2, a2[k] = c2, b2[k] = -c2;
+            } else if (id == CG_ZERODIPOLE) {
+                a1[k] = -c - 0.5 * c2, a3[k] = 0.5 * c2, b3[k] = -c2;
+            } else if (id == CG_ZAHN) {
+                a1[k] = c2, a2[k] = -c2, b2[k] = c2;
+            } else if (id == CG_EWALDT) {
+                m[k] = 1.0 / d.F0, a0[k] = -c - k1e, a1[k] = k1e, b0[k] = -(c + k1e);
+            } // CG_EWALD (unscreened): erfc alone
+        }
+    }
+    // single-scheme interface (the per-functor probe): scheme 0
+    template <int ND, class T = double, class TAB = const double *> CG_HD void eval(T q, T *s, const TAB &tab = TAB()) const {
+        const T x = (T)eta * q;
+        T E, ec;
+        erfc_and_gauss(x, ec, E, tab);
+        const T k1E = (T)k1 * E, e2 = (T)eta * (T)eta;
+        s[0] = (T)m[0] * (ec + (T)a0[0] + q * ((T)a1[0] + q * ((T)a2[0] + q * (T)a3[0])));
+        if (ND >= 1) s[1] = (T)m[0] * (-k1E + (T)a1[0] + q * (T(2) * (T)a2[0] + q * T(3) * (T)a3[0]));
+        if (ND >= 2) s[2] = (T)m[0] * (T(2) * e2 * q * k1E + T(2) * (T)a2[0] + T(6) * q * (T)a3[0]);
+        if (ND >= 3) s[3] = (T)m[0] * (T(2) * e2 * k1E * (T(1) - T(2) * x * x) + T(6) * (T)a3[0]);
     }
 };
 

@@ -73,7 +73,7 @@ def main():
     want = single.eval(cg.MODE_MULTIPOLE, w)
     single.close()
     received = []
-    for step in range(3):
+    for step in range(6):  # both blocks several times: the publish / acknowledge words of the device-side ordering wrap around
         owned = torch.stack([a[lo:hi] for a in arr])
         sub, ids, n_out = halo.gather(owned)
         halo.set_system(ev, sub, has_q=True, has_mu=True)

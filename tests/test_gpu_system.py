@@ -436,3 +436,60 @@ def test_ewald_truncated_surface_energy(oracle_kind, tmp_path):
         if not np.isfinite(eps):
             assert got == 0.0 and e[0] == 0.0 and ref == 0.0
         ev.close()
+
+
+@pytest.mark.parametrize("pair", [("wolf", "fennell"), ("zahn", "zerodipole"), ("ewaldt", "wolf")])
+def test_two_schemes_in_one_pass(pair, oracle_kind):
+    """cg_eval_multi_device: two erfc-family schemes with one alpha evaluated in ONE pass over the pairs (shared prefilter, hit
+    lists, gathers, 1/r, erfc and Gaussian) -- against the oracle at 1e-12 and against the one-by-one evaluation."""
+    import torch
+    x, y, z, q, mu = O.generate(44, 3.0, 606, oracle_kind)  # enough i-groups for one per resident warp: no j-split
+    box = [132.0] * 3
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(st)
+    try:
+        evs = [cg.BatchedEvaluator(zoo()[nm][0]()) for nm in pair]
+        for ev in evs:
+            ev.set_stream(st.cuda_stream)
+        evs[1].share_system(evs[0])
+        dx = [torch.tensor(a, dtype=torch.float64, device=dev) for a in (x, y, z, q)]
+        N = x.size
+        for what in (cg.FORCE, cg.ENERGY | cg.FORCE | cg.FIELD | cg.POTENTIAL):
+            f = [torch.zeros((N, 3), dtype=torch.float64, device=dev) for _ in evs]
+            e = [torch.zeros((N, 3), dtype=torch.float64, device=dev) for _ in evs]
+            p = [torch.zeros(N, dtype=torch.float64, device=dev) for _ in evs]
+            sc = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in evs]
+            refs = [O.Scheme(zoo()[nm][1], oracle_kind).batched(x, y, z, q, None, box, True, cg.MODE_ION, what) for nm in pair]
+            for rep in range(2):  # exact sizing, then the sync-free path
+                evs[0].set_system_device(dx[0], dx[1], dx[2], dx[3], None, box, True)
+                cg.eval_multi_device(evs, cg.MODE_ION, what, force=f, field=e, potential=p, scalars=sc)
+                torch.cuda.synchronize()
+                for k, nm in enumerate(pair):
+                    ref = refs[k]
+                    g = dict(force=f[k].cpu().numpy(), field=e[k].cpu().numpy(), potential=p[k].cpu().numpy(), energy=sc[k][0].item(),
+                             pairs=int(sc[k][1].item()))
+                    errs = compare(g, ref, what)
+                    assert all(v <= 1.0 for v in errs.values()), (nm, what, rep, errs)
+            # one by one: same pair count, same numbers to rounding
+            f1 = torch.zeros((N, 3), dtype=torch.float64, device=dev)
+            s1 = torch.zeros(2, dtype=torch.float64, device=dev)
+            evs[0].set_system_device(dx[0], dx[1], dx[2], dx[3], None, box, True)
+            for k in range(2):
+                evs[k].eval_device(cg.MODE_ION, what, force=f1, field=torch.zeros_like(f1) if what & cg.FIELD else None,
+                                   potential=torch.zeros(N, dtype=torch.float64, device=dev) if what & cg.POTENTIAL else None, scalars=s1)
+                torch.cuda.synchronize()
+                assert s1[1].item() == sc[k][1].item()
+                assert (f1 - f[k]).abs().max().item() <= 1e-13 * f1.abs().max().item()
+        # what the fused pass does not cover is refused, not approximated
+        other = cg.BatchedEvaluator(cg.Wolf(12.0, 0.2))
+        other.set_stream(st.cuda_stream)
+        other.share_system(evs[0])
+        with pytest.raises(cg.CgError):
+            cg.eval_multi_device([evs[0], other], cg.MODE_ION, cg.FORCE, force=f, scalars=sc)
+        with pytest.raises(cg.CgError):
+            cg.eval_multi_device(evs, cg.MODE_DIPOLE, cg.FORCE, force=f, scalars=sc)
+        for ev in evs + [other]:
+            ev.close()
+    finally:
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
