@@ -199,6 +199,12 @@ class BatchedEvaluator:
         check(lib.cg_last_timings(self.h, ms), "cg_last_timings", self.h)
         return dict(sort_ms=ms[0], pair_ms=ms[1], epilogue_ms=ms[2], step_ms=ms[3])
 
+    def timings_history(self, k):
+        """timings() of each of the last k evaluations (k <= 64), oldest first; waits for the newest only."""
+        ms = (C.c_double * (4 * k))()
+        check(lib.cg_timings_history(self.h, k, ms), "cg_timings_history", self.h)
+        return [dict(sort_ms=ms[4 * i], pair_ms=ms[4 * i + 1], epilogue_ms=ms[4 * i + 2], step_ms=ms[4 * i + 3]) for i in range(k)]
+
     def counters(self):
         c = (C.c_int64 * 8)()
         check(lib.cg_last_counters(self.h, c), "cg_last_counters", self.h)

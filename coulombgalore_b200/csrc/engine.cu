@@ -905,7 +905,12 @@ struct cg_handle {
     DevBuf<double> d_erfc_table; // erfc/exp table of specfun.hpp (erfc-family schemes)
     int functor = -1;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // timing events of the last kTimingRing evaluations (slot = evaluation number % ring): a caller that enqueues many steps
+    // without waiting for any of them can still read every step's phase times afterwards (cg_timings_history)
+    static constexpr int kTimingRing = 64;
+    cudaEvent_t evring[kTimingRing][4] = {};
+    cudaEvent_t *ev = evring[0]; // the slot of the current / last evaluation
+    int64_t n_evals = 0;
     int precision = CG_FP64;
     int shard_rank = 0, shard_n = 1;
     int64_t grid_count = 0;            // particle count for the cell-size heuristic (0: the system's own n)
@@ -1067,7 +1072,8 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
         }
     }
     bool ok = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&h->ev[k]) == cudaSuccess;
+    for (int r = 0; r < cg_handle::kTimingRing && ok; r++)
+        for (int k = 0; k < 4 && ok; k++) ok = cudaEventCreate(&h->evring[r][k]) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_counts, 4 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_counts_async, 4 * sizeof(int)) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->counts_ev, cudaEventDisableTiming) == cudaSuccess;
@@ -1138,8 +1144,9 @@ int cg_destroy(cg_handle *h) {
     h->halo_counts.release();
     if (h->h_minmax) cudaFreeHost(h->h_minmax);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
-    for (auto &e : h->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto &slot : h->evring)
+        for (auto &e : slot)
+            if (e) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
     return CG_OK;
@@ -1422,9 +1429,17 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
         ng_guess[0] = h->fast.last_groups[0];
         ng_bound[0] = std::min(n / gsize + nrows_prim + 2, ng_guess[0] + ng_guess[0] / 8 + 64);
         CG_CUDA(h, h->groups[0].ensure((size_t)ng_bound[0] + 1));
-        scan_groups_kernel<<<1, kScanThreads, 0, st>>>(sp, hist, h->cell_start.p, ncell, cells_done, h->row_gstart[0].p, h->groups[0].p, ng_bound[0], gsize,
-                                                       counts);
+        // the one-CTA kernel also writes the group table, unless that is a large one (config 5: 524 288 groups), which a
+        // grid of its own writes faster
+        const bool emit_inline = ng_bound[0] <= 32768;
+        scan_groups_kernel<<<1, kScanThreads, 0, st>>>(sp, hist, h->cell_start.p, ncell, cells_done, h->row_gstart[0].p,
+                                                       emit_inline ? h->groups[0].p : nullptr, ng_bound[0], gsize, counts);
         (*launches_out)++;
+        if (!emit_inline) {
+            row_group_emit_kernel<<<(std::max(nrows_prim, 1) + 127) / 128, 128, 0, st>>>(sp, h->cell_start.p, h->row_gstart[0].p, h->groups[0].p,
+                                                                                         ng_bound[0], gsize);
+            (*launches_out)++;
+        }
     } else {
         scan_groups_kernel<<<1, kScanThreads, 0, st>>>(sp, hist, h->cell_start.p, ncell, cells_done, h->row_gstart[0].p, nullptr, 0x7fffffff, gsize, counts);
         (*launches_out)++;
@@ -1508,6 +1523,9 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     cudaSetDevice(h->device);
     cudaStream_t st = h->stream;
     int launches = 0, pair_launches = 0;
+    h->ev = h->evring[h->n_evals % cg_handle::kTimingRing];
+    h->n_evals++;
+    h->multi_of = nullptr;
     CG_CUDA(h, cudaEventRecord(h->ev[0], st));
     if (!d_scalars) {
         CG_CUDA(h, h->scalars.ensure(8));
@@ -2087,6 +2105,27 @@ int cg_last_timings(cg_handle *h, double ms[4]) {
     return CG_OK;
 }
 
+int cg_timings_history(cg_handle *h, int k, double *ms) {
+    if (!h || !ms || k < 1) return CG_ERR_INVALID;
+    if (h->multi_of) h = h->multi_of;
+    cudaSetDevice(h->device);
+    if (k > cg_handle::kTimingRing || k > h->n_evals) return CG_ERR_INVALID;
+    for (int i = 0; i < k; i++) { // oldest first
+        cudaEvent_t *e = h->evring[(h->n_evals - k + i) % cg_handle::kTimingRing];
+        CG_CUDA(h, cudaEventSynchronize(e[3]));
+        float a = 0, b = 0, c = 0, d = 0;
+        CG_CUDA(h, cudaEventElapsedTime(&a, e[0], e[1]));
+        CG_CUDA(h, cudaEventElapsedTime(&b, e[1], e[2]));
+        CG_CUDA(h, cudaEventElapsedTime(&c, e[2], e[3]));
+        CG_CUDA(h, cudaEventElapsedTime(&d, e[0], e[3]));
+        ms[4 * i + 0] = a;
+        ms[4 * i + 1] = b;
+        ms[4 * i + 2] = c;
+        ms[4 * i + 3] = d;
+    }
+    return CG_OK;
+}
+
 int cg_last_counters(cg_handle *h, int64_t c[8]) {
     if (!h || !c) return CG_ERR_INVALID;
     if (h->counts_pending && cudaEventQuery(h->counts_ev) == cudaSuccess) {
@@ -2304,6 +2343,23 @@ int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blo
     halo_pull_kernel<<<dim3((unsigned)per, (unsigned)narrays, (unsigned)nranks), 256, 0, h->stream>>>(g);
     CG_CUDA(h, cudaGetLastError());
     return CG_OK;
+}
+
+int cg_halo_exchange_step(cg_handle *h, int nranks, int rank, int narrays, int zindex, int64_t count, const double *const *owned,
+                          const double *zlo, const double *zhi, const double *box, void *own_block, void *const *blocks,
+                          void *const *prev_blocks, const int64_t *counts, double *const *dst, int64_t dst_cap, int64_t n_bound, int *n_out,
+                          int64_t step, int has_q, int has_mu) {
+    if (!h || !box || !dst || n_bound < 1 || n_bound > dst_cap || narrays < 3 + (has_q ? 1 : 0) + (has_mu ? 3 : 0)) return CG_ERR_INVALID;
+    int rc = cg_halo_publish_step(h, nranks, narrays, zindex, count, owned, zlo, zhi, box[2], own_block, step, rank, prev_blocks, n_out + 1);
+    if (rc != CG_OK) return rc;
+    rc = cg_halo_pull_step(h, nranks, rank, blocks, counts, narrays, dst, dst_cap, n_out, step);
+    if (rc != CG_OK) return rc;
+    int k = 3;
+    const double *q = has_q ? dst[k++] : nullptr;
+    const double *mx = has_mu ? dst[k] : nullptr, *my = has_mu ? dst[k + 1] : nullptr, *mz = has_mu ? dst[k + 2] : nullptr;
+    rc = cg_set_system_device(h, n_bound, dst[0], dst[1], dst[2], q, mx, my, mz, box, 1);
+    if (rc != CG_OK) return rc;
+    return cg_set_count_device(h, n_out);
 }
 
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z, double *q,

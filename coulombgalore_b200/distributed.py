@@ -315,6 +315,39 @@ class HaloExchange:
         nb = self.n_bound
         return [self.recv[a, :nb] for a in range(self.n_payload)], self.recv[self.n_payload, :nb], self.n_out
 
+    def exchange(self, ev, owned2d, has_q=True, has_mu=False):
+        """gather() + set_system() in ONE library call (cg_halo_exchange_step): for small shards the host time between the
+        launches is what the GPUs wait for.  owned2d: [n_payload, count] float64 on the device, rows x, y, z[, q][, mu].
+        -> number of rows of the evaluator's outputs (the bound of the received count).  Device-side ordering only."""
+        C = self.C
+        if not self.device_flags or self.n_bound is None:  # the first step sizes the bound (one host read)
+            sub, _, _ = self.gather(owned2d)
+            self.set_system(ev, sub, has_q=has_q, has_mu=has_mu)
+            return self.n_bound
+        self.ev.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        self._track_bound()
+        s = self.step
+        self.step += 1
+        b = s & 1
+        if getattr(self, "_src_of", None) is not owned2d:  # pointer table of the caller's (persistent) input block
+            self._src = (C.c_void_p * self.narrays)(*([owned2d[a].data_ptr() for a in range(self.n_payload)] + [self.ids_owned.data_ptr()]))
+            self._src_of = owned2d
+            self._boxc = (C.c_double * 3)(*self.box)
+        self._keep = owned2d
+        self.check(self.lib.cg_halo_exchange_step(ev.h, self.world, self.rank, self.narrays, 2, self.count, self._src, self.zlo, self.zhi,
+                                                  self._boxc, self.own_ptr[b], self.block_ptrs[b], self.block_ptrs[(s - 1) & 1] if s >= 1 else None,
+                                                  self.counts_c, self.recv_c, self.capacity, self.n_bound, self.n_out.data_ptr(), s,
+                                                  int(has_q), int(has_mu)), "cg_halo_exchange_step", ev.h)
+        ev.n = self.n_bound
+        self._n_host.copy_(self.n_out, non_blocking=True)
+        self._n_event.record(torch.cuda.current_stream(self.device))
+        self._n_pending = True
+        return self.n_bound
+
+    def ids(self):
+        """Global particle index (as float64) of every row of the evaluator's outputs after exchange()."""
+        return self.recv[self.n_payload, : self.n_bound]
+
     def _track_bound(self):
         """Grow the bound handed to the engine before the received count reaches it.  A step that does exceed it is not
         silent: the engine raises its overflow flag (energy NaN, pair count -1) when the device count is larger than the

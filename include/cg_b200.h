@@ -231,6 +231,9 @@ int cg_srf_device(cg_handle *h, int64_t n, const double *q, double *out);
 /* timings of the last evaluation in milliseconds (CUDA events on the handle's stream):
  * ms[0] binning+sort+reorder, ms[1] pair kernel(s), ms[2] reductions/epilogue, ms[3] whole step */
 int cg_last_timings(cg_handle *h, double ms[4]);
+/* the same four numbers for each of the last k evaluations (k <= 64, oldest first, ms[4 k]): for callers that enqueue many
+ * steps without waiting for any of them; waits for the newest */
+int cg_timings_history(cg_handle *h, int k, double *ms);
 /* counters of the last evaluation: [0] sorted entries incl. periodic images, [1] cells, [2] i-groups,
  * [3] pair-kernel launches, [4] total kernel launches, [5] j-split factor, [6] 1 if the evaluation took the sync-free path
  * (sizes from the previous evaluation, no host round trip), [7] work items of the pair kernel */
@@ -287,6 +290,15 @@ int cg_halo_publish_step(cg_handle *h, int nranks, int narrays, int zindex, int6
                          void *const *prev_blocks, int *err_dev);
 int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays,
                       double *const *dst, int64_t dst_cap, int *n_out, int64_t step);
+/* One exchange step in one call: cg_halo_publish_step + cg_halo_pull_step + cg_set_system_device(h, n_bound, dst...) +
+ * cg_set_count_device(h, n_out).  The arrays are x, y, z[, q][, mux, muy, muz] then anything else (e.g. the global index);
+ * n_out = two ints on the device (count received; error word, also used by the publish); blocks = all ranks' blocks of this
+ * step, prev_blocks = those of the previous step (NULL at step 0).  For small shards the host time between the launches of
+ * an exchange step is what the GPUs wait for: this entry point issues all of them back to back. */
+int cg_halo_exchange_step(cg_handle *h, int nranks, int rank, int narrays, int zindex, int64_t count, const double *const *owned,
+                          const double *zlo, const double *zhi, const double *box, void *own_block, void *const *blocks,
+                          void *const *prev_blocks, const int64_t *counts, double *const *dst, int64_t dst_cap, int64_t n_bound,
+                          int *n_out, int64_t step, int has_q, int has_mu);
 
 /* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,
