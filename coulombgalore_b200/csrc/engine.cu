@@ -939,7 +939,7 @@ struct cg_handle {
     DevBuf<int> work_counter;    // next work item of the persistent pair kernel
     int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
     int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
-    DevBuf<int> d_counts, halo_counts;
+    DevBuf<int> halo_counts;
     cudaEvent_t counts_ev = nullptr;
     bool counts_pending = false;
     // sync-free path: valid while (n, box, pbc, shard) are unchanged and the arrays sized by the last exact run still fit
@@ -1080,7 +1080,6 @@ int cg_create(const cg_scheme_desc *scheme, int device, cg_handle **out) {
     ok = ok && cudaEventCreateWithFlags(&h->sorted_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->pair_done_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&h->inputs_ev, cudaEventDisableTiming) == cudaSuccess;
-    ok = ok && h->d_counts.ensure(8) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_minmax, 6 * 64 * sizeof(double)) == cudaSuccess;
     ok = ok && cudaMallocHost((void **)&h->h_scalars, 8 * sizeof(double)) == cudaSuccess;
     if (!ok) {
@@ -1140,7 +1139,6 @@ int cg_destroy(cg_handle *h) {
     if (h->sorted_ev) cudaEventDestroy(h->sorted_ev);
     if (h->pair_done_ev) cudaEventDestroy(h->pair_done_ev);
     if (h->inputs_ev) cudaEventDestroy(h->inputs_ev);
-    h->d_counts.release();
     h->halo_counts.release();
     if (h->h_minmax) cudaFreeHost(h->h_minmax);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);

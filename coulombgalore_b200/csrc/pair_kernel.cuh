@@ -82,7 +82,7 @@ template <int MODE> constexpr int warps_per_cta() { return MODE == cgd::kModeMul
 constexpr int kMaxWarpsPerSm = 16;
 // pairs in flight per consumer lane and step
 #ifndef CG_ILP_DIP
-#define CG_ILP_DIP 1
+#define CG_ILP_DIP 2
 #endif
 #ifndef CG_ILP_MP
 #define CG_ILP_MP 1

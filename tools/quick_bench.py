@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Kernel-level timing of the BASELINE configs on one GPU (tuning aid; the judged numbers come from bench.py).
-usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,3,4s,4,5s,5}  (4s / 5s = configs 4 / 5 at n = 100 / 128)"""
+usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,2m,3,4s,4,5s,5}  (4s / 5s = configs 4 / 5 at n = 100 / 128;
+2m = Wolf + Fennell in one pass, as bench.py evaluates config 2)"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -18,12 +19,43 @@ CONFIGS = {
     "5s": dict(pot=lambda: cg.Splined().spline(cg.Poisson, 12, 4, 3), n=128, a=3.0, seed=1005, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=153),
 }
 
+def fused_config2(dev, st):
+    """config 2 as bench.py runs it: Wolf and Fennell in one pass over the pairs (cg_eval_multi_device)."""
+    import time
+    n, N = 100, 100 ** 3
+    evs = [cg.BatchedEvaluator(cg.Wolf(12, 0.25)), cg.BatchedEvaluator(cg.Fennell(12, 0.25))]
+    for ev in evs:
+        ev.set_stream(st.cuda_stream)
+    evs[1].share_system(evs[0])
+    arr = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
+    evs[0].generate_lattice_device(n, 3.0, 1002, arr[0], arr[1], arr[2], arr[3])
+    f = [torch.empty((N, 3), dtype=torch.float64, device=dev) for _ in evs]
+    sc = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in evs]
+    pm, wm = [], []
+    for it in range(8):
+        evs[0].set_system_device(arr[0], arr[1], arr[2], arr[3], None, [300.0] * 3, True)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        cg.eval_multi_device(evs, cg.MODE_ION, cg.FORCE, force=f, scalars=sc)
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        if it >= 3:
+            pm.append(evs[0].timings()["pair_ms"]); wm.append((t1 - t0) * 1e3)
+    pairs = sc[0][1].item() + sc[1][1].item()
+    p = statistics.median(pm)
+    print("cfg 2m  N=%8d pairs=%.4g (Wolf + Fennell, one pass)  pair_kernel %.3f ms  wall %.3f ms -> %.3e pairs/s  %.2f TF(F_alg=33+39) %.1f%% of 37.2" %
+          (N, pairs, p, statistics.median(wm), pairs / p * 1e3, pairs / 2 * 72 / p * 1e3 / 1e12, 100 * pairs / 2 * 72 / p * 1e3 / 37.2e12), flush=True)
+    for ev in evs:
+        ev.close()
+
+
 def main():
-    names = sys.argv[1:] or ["1", "2w", "2f", "3", "4s", "5s"]
+    names = sys.argv[1:] or ["1", "2w", "2f", "2m", "3", "4s", "5s"]
     dev = torch.device("cuda", 0)
     st = torch.cuda.Stream()
     torch.cuda.set_stream(st)
     for nm in names:
+        if nm == "2m":
+            fused_config2(dev, st)
+            continue
         c = CONFIGS[nm]
         N = c["n"] ** 3
         ev = cg.BatchedEvaluator(c["pot"]())
