@@ -1598,7 +1598,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     }();
     // j-split: only when the groups cannot give every resident warp of the machine an item; then as many slices as it takes
     int split = 1;
-    const int wave = device_sms * 16; // resident warps of the machine (pair_kernel.cuh: 16 per SM in every launch shape)
+    const int wave = device_sms * 16; // items the machine takes at once: 12 resident warps per SM (pair_kernel.cuh) and a few to even out the tail
     if (ng > 0 && ng < wave) split = std::max(1, std::min(64, wave / ng));
     if (split_env > 0) split = std::min(64, split_env);
     const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split

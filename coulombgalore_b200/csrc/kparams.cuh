@@ -12,7 +12,7 @@ namespace cgd = CoulombGalore::detail;
 
 // tuning builds: make EXTRA_NVFLAGS="-DCG_WARPS=.. -DCG_MINB=.. -DCG_ILP=.. -DCG_SLOTS=.. -DCG_GATHER=.." (pair_kernel.cuh)
 #ifndef CG_ILP
-#define CG_ILP 2
+#define CG_ILP 3
 #endif
 #ifndef CG_SLOTS
 #define CG_SLOTS 64

@@ -51,13 +51,34 @@ template <int POLICY> __device__ __forceinline__ double4 ldg256(const double4 *p
     return v;
 }
 
-// Launch shape and gather policy per mode (tuning builds: -DCG_WARPS / -DCG_MINB / -DCG_GATHER override all modes).  Every shape
-// keeps 16 warps of <= 128 registers on an SM.  Measured (B200, full-size BASELINE configs): ion kernels 16 x 1 with L1-allocating
-// gathers (Wolf 1.87 ms against 2.10 ms for 8 x 2: the longer hit lists of the single CTA hold a whole item), dipole and
-// multipole kernels 8 x 2 with streaming gathers (ReactionField dipoles 0.65 against 0.70 ms, splined multipoles 9.5 against 9.9 ms).
+// Launch shape and gather policy per mode (tuning builds: -DCG_WARPS / -DCG_MINB / -DCG_GATHER override all modes, the _ION / _DIP /
+// _MP forms one mode).  Every shape keeps 12 warps on an SM, i.e. up to 168 registers per thread: at 16 warps (128 registers) all
+// kernels but plain Wolf spill their gather sets to local memory, and the spill traffic shares the LSU data pipe the gathers are
+// bound by.  Measured (B200, full-size BASELINE configs, pair kernel only; 16-warp shapes in brackets): Wolf 1.75 ms (1.88),
+// Wolf + Fennell in one pass 1.93 (2.07), ReactionField dipoles 0.57 (0.63), qPotential multipoles 2.71 (2.93), splined Poisson
+// multipoles 8.7 (9.7).  Ion kernels run one 12-warp CTA per SM (the longer hit lists of a single CTA hold a whole item) with
+// L1-allocating gathers, dipole and multipole kernels two 6-warp CTAs with streaming gathers.  10 and 14 warps per SM are slower.
+#ifndef CG_WARPS_ION
+#define CG_WARPS_ION 12
+#endif
+#ifndef CG_MINB_ION
+#define CG_MINB_ION 1
+#endif
+#ifndef CG_WARPS_DIP
+#define CG_WARPS_DIP 6
+#endif
+#ifndef CG_MINB_DIP
+#define CG_MINB_DIP 2
+#endif
+#ifndef CG_WARPS_MP
+#define CG_WARPS_MP 6
+#endif
+#ifndef CG_MINB_MP
+#define CG_MINB_MP 2
+#endif
 #if defined(CG_WARPS) || defined(CG_MINB)
 #ifndef CG_WARPS
-#define CG_WARPS 16
+#define CG_WARPS 12
 #endif
 #ifndef CG_MINB
 #define CG_MINB 1
@@ -65,8 +86,8 @@ template <int POLICY> __device__ __forceinline__ double4 ldg256(const double4 *p
 template <int MODE> constexpr int tuned_warps() { return CG_WARPS; }
 template <int MODE> constexpr int tuned_minb() { return CG_MINB; }
 #else
-template <int MODE> constexpr int tuned_warps() { return MODE == cgd::kModeIon ? 16 : 8; }
-template <int MODE> constexpr int tuned_minb() { return MODE == cgd::kModeIon ? 1 : 2; }
+template <int MODE> constexpr int tuned_warps() { return MODE == cgd::kModeIon ? CG_WARPS_ION : (MODE == cgd::kModeDipole ? CG_WARPS_DIP : CG_WARPS_MP); }
+template <int MODE> constexpr int tuned_minb() { return MODE == cgd::kModeIon ? CG_MINB_ION : (MODE == cgd::kModeDipole ? CG_MINB_DIP : CG_MINB_MP); }
 #endif
 template <int MODE> constexpr int gather_policy() {
 #ifdef CG_GATHER
@@ -78,8 +99,8 @@ template <int MODE> constexpr int gather_policy() {
 // the quadrupole mode carries two tensors per pair in registers: half the warps (255 registers each) instead of spilling at 128
 template <int MODE> constexpr int min_blocks_per_sm() { return MODE == cgd::kModeMultipoleQuad ? 1 : tuned_minb<MODE>(); }
 template <int MODE> constexpr int warps_per_cta() { return MODE == cgd::kModeMultipoleQuad ? 8 : tuned_warps<MODE>(); }
-// resident warps per SM of the largest shape: what the engine's j-split fills
-constexpr int kMaxWarpsPerSm = 16;
+// resident warps per SM of every shape
+constexpr int kMaxWarpsPerSm = 12;
 // pairs in flight per consumer lane and step
 #ifndef CG_ILP_DIP
 #define CG_ILP_DIP 2
