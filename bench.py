@@ -586,8 +586,8 @@ def main():
 
 
 def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, allsum):
-    """Config 2 through host buffers.  1 GPU: the C ABI's host entry points (cg_set_system + cg_eval_begin / cg_eval_end),
-    one handle per scheme so the first scheme's download overlaps the second one's kernel.  N GPUs: every rank uploads its own
+    """Config 2 through host buffers.  1 GPU: the C ABI's host entry points (cg_set_system + cg_eval_multi_begin / _end), two
+    configurations in flight on two sets of handles so that uploads, pair kernels and downloads overlap.  N GPUs: every rank uploads its own
     N/R particles from pinned memory, the halo exchange brings the rest over NVLink, and the forces come back over a second
     stream (double-buffered on the device), so that the download of one step overlaps the upload and kernels of the next."""
     import numpy as np
@@ -607,41 +607,59 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
         for ev in evh.values():
             ev.set_stream(stream.cuda_stream)
         own_host = w.owned.cpu().pin_memory()  # this rank's slice, pinned
-        own_dev = torch.empty_like(own_host, device=dev)
-        sub, _, _ = halo_h.gather(own_dev.copy_(own_host))  # sizes the receive bound
-        nb = sub[0].numel()
-        copy_stream = torch.cuda.Stream(device=dev)
-        f_dev = [{k: torch.zeros((nb, 3), dtype=torch.float64, device=dev) for k in evh} for _ in range(2)]
-        f_host = [{k: torch.empty((nb, 3), dtype=torch.float64).pin_memory() for k in evh} for _ in range(2)]
+        own_dev = [torch.empty_like(own_host, device=dev) for _ in range(2)]
+        sub, _, _ = halo_h.gather(own_dev[0].copy_(own_host))  # sizes the receive bound
+        nb, cnt = sub[0].numel(), own_host.shape[1]
+        up_stream, copy_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        f_dev = {k: torch.zeros((nb, 3), dtype=torch.float64, device=dev) for k in evh}              # rows in received order
+        fo_dev = [{k: torch.zeros((cnt, 3), dtype=torch.float64, device=dev) for k in evh} for _ in range(2)]  # own rows, own order
+        f_host = [{k: torch.empty((cnt, 3), dtype=torch.float64).pin_memory() for k in evh} for _ in range(2)]
         sc_dev = [{k: torch.zeros(2, dtype=torch.float64, device=dev) for k in evh} for _ in range(2)]
         sc_host = [{k: torch.empty(2, dtype=torch.float64).pin_memory() for k in evh} for _ in range(2)]
-        done = [{k: torch.cuda.Event() for k in evh} for _ in range(2)]      # kernel finished (compute stream)
-        copied = [{k: torch.cuda.Event() for k in evh} for _ in range(2)]    # download finished (copy stream)
-        h2d_bytes, d2h_bytes = own_host.numel() * 8, 2 * (nb * 3 * 8 + 16)
-        note = ("pinned host buffers; every rank uploads its own N/R particles, the halo exchange brings the rest over NVLink; the forces "
-                "of the received particles (those of the rank's shard are non-zero) come back on a second stream, double-buffered")
+        uploaded = [torch.cuda.Event() for _ in range(2)]   # inputs of the step are on the device (upload stream)
+        consumed = [torch.cuda.Event() for _ in range(2)]   # the exchange has read them (compute stream)
+        done = [torch.cuda.Event() for _ in range(2)]       # kernels finished (compute stream)
+        copied = [torch.cuda.Event() for _ in range(2)]     # download finished (copy stream)
+        h2d_bytes, d2h_bytes = own_host.numel() * 8, 2 * (cnt * 3 * 8 + 16)
+        note = ("pinned host buffers; every rank uploads its own N/R particles (upload stream, double-buffered), the halo exchange brings "
+                "the rest over NVLink, cg_halo_collect_owned puts the forces of the rank's own particles into their original order and "
+                "they come back on a third stream, double-buffered: upload, kernels and download of consecutive steps overlap")
         state = {"s": 0}
+
+        phase_ev = []  # per step: stream events at the start, after the upload, after the exchange, after the kernels; copy stream: downloaded
 
         def step_host():
             b = state["s"] & 1
             state["s"] += 1
-            own_dev.copy_(own_host, non_blocking=True)
-            halo_h.exchange(evh["wolf"], own_dev, has_q=True, has_mu=False)
+            pe = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            phase_ev.append(pe)
+            with torch.cuda.stream(up_stream):
+                up_stream.wait_event(consumed[b])  # the exchange of two steps ago has read this buffer
+                own_dev[b].copy_(own_host, non_blocking=True)
+                uploaded[b].record(up_stream)
+            pe[0].record(stream)
+            stream.wait_event(uploaded[b])
+            pe[1].record(stream)
+            halo_h.exchange(evh["wolf"], own_dev[b], has_q=True, has_mu=False)
+            consumed[b].record(stream)
+            pe[2].record(stream)
             if w.fused:
-                for k in evh:
-                    stream.wait_event(copied[b][k])  # the download of two steps ago has left this buffer
-                cg.eval_multi_device(list(evh.values()), cg.MODE_ION, cg.FORCE, force=[f_dev[b][k] for k in evh],
+                cg.eval_multi_device(list(evh.values()), cg.MODE_ION, cg.FORCE, force=[f_dev[k] for k in evh],
                                      scalars=[sc_dev[b][k] for k in evh])
-            for k, ev in evh.items():
-                if not w.fused:
-                    stream.wait_event(copied[b][k])
-                    ev.eval_device(cg.MODE_ION, cg.FORCE, force=f_dev[b][k], scalars=sc_dev[b][k])
-                done[b][k].record(stream)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(done[b][k])
-                    f_host[b][k].copy_(f_dev[b][k], non_blocking=True)
+            else:
+                for k, ev in evh.items():
+                    ev.eval_device(cg.MODE_ION, cg.FORCE, force=f_dev[k], scalars=sc_dev[b][k])
+            stream.wait_event(copied[b])  # the download of two steps ago has left this buffer
+            halo_h.collect_owned([f_dev[k] for k in evh], [fo_dev[b][k] for k in evh])
+            done[b].record(stream)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[b])
+                for k in evh:
+                    f_host[b][k].copy_(fo_dev[b][k], non_blocking=True)
                     sc_host[b][k].copy_(sc_dev[b][k], non_blocking=True)
-                    copied[b][k].record(copy_stream)
+                copied[b].record(copy_stream)
+            pe[3].record(stream)
+            pe[4].record(copy_stream)
 
         def drain():
             copy_stream.synchronize()
@@ -659,25 +677,36 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
         note = "cg_set_system + cg_eval_begin/_end with pinned host buffers, one handle per scheme; every rank uploads all N particles"
         last = {"pairs": 0}
 
-        fused = w.fused
+        fused = w.fused and world == 1
         if fused:
-            for ev in evh.values():
-                ev.set_stream(stream.cuda_stream)
-            fd = [torch.empty((N, 3), dtype=torch.float64, device=dev) for _ in evh]
-            fh = [torch.from_numpy(outs[k]["force"]) for k in evh]
-            scd = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in evh]
-            sch = [torch.empty(2, dtype=torch.float64).pin_memory() for _ in evh]
-            note = ("cg_set_system (pinned host inputs) + cg_eval_multi_device (both schemes in one pass) + download of both force arrays "
-                    "into pinned host buffers")
+            # Two sets of handles used in turn, each set on its own stream (the C ABI's default): while one configuration's
+            # pair kernel runs, the next one's inputs go up and the previous one's forces come down.  Every step still uploads
+            # its inputs from pinned host memory and delivers both force arrays to pinned host buffers; cg_eval_multi_end is
+            # the host's wait for exactly that step.
+            depth = 2  # measured (tools/e2e_probe.py): 1 -> 3.54 ms per step, 2 -> 2.20, 3 -> 2.65, 4 -> 2.63
+            lanes = [dict(evs=list(evh.values()), outs=[outs[k] for k in evh])]
+            for _ in range(depth - 1):
+                evs = [cg.BatchedEvaluator(p, local) for p in pots.values()]
+                evs[1].share_system(evs[0])
+                lanes.append(dict(evs=evs, outs=[{"force": torch.empty((N, 3), dtype=torch.float64).pin_memory().numpy()} for _ in evs]))
+            inflight = []
+            ksteps = max(ksteps, min(args.steps, 30))
+            note = ("cg_set_system (pinned host inputs) + cg_eval_multi_begin / cg_eval_multi_end (both schemes in one pass, both force "
+                    "arrays into pinned host buffers); %d configurations in flight, one set of handles and one stream each" % depth)
+
+        def finish_oldest():
+            lane = inflight.pop(0)
+            last["pairs"] = int(sum(r["pairs"] for r in cg.eval_multi_end(lane["evs"])))
 
         def step_host():
-            if fused:  # one upload, one sort, one pass over the pairs for both schemes, two downloads
-                evh["wolf"].set_system(hx[0], hx[1], hx[2], hx[3], None, box, True)
-                cg.eval_multi_device(list(evh.values()), cg.MODE_ION, cg.FORCE, force=fd, scalars=scd)
-                for a, b_ in zip(fh + sch, fd + scd):
-                    a.copy_(b_, non_blocking=True)
-                stream.synchronize()
-                last["pairs"] = int(sum(t[1].item() for t in sch))
+            if fused:  # one upload, one sort, one pass over the pairs for both schemes, two downloads -- per configuration
+                lane = lanes[state_h["s"] % depth]
+                state_h["s"] += 1
+                if len(inflight) == depth:
+                    finish_oldest()
+                lane["evs"][0].set_system(hx[0], hx[1], hx[2], hx[3], None, box, True)
+                cg.eval_multi_begin(lane["evs"], cg.MODE_ION, cg.FORCE, lane["outs"])
+                inflight.append(lane)
                 return
             # one handle (and stream) per scheme: the first scheme's download overlaps the second one's kernel;
             # cg_eval_end blocks until that scheme's forces are in its (pinned) host buffer
@@ -686,11 +715,16 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
                 ev.eval_begin(cg.MODE_ION, cg.FORCE, out=outs[k])
             last["pairs"] = sum(ev.eval_end()["pairs"] for ev in evh.values())
 
+        state_h = {"s": 0}
+
         def drain():
+            while fused and inflight:
+                finish_oldest()
             return last["pairs"]
 
-    step_host()
-    drain()
+    for _ in range(6):  # every set of handles sizes its arrays once (the first evaluation of a shape waits for the device)
+        step_host()
+        drain()
     barrier()
     t0 = time.perf_counter()
     for _ in range(ksteps):
@@ -701,7 +735,17 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
     pe = allsum(float(pairs_last)) * ksteps  # every step evaluates the same configuration
     out = {"value": pe / dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": ksteps, "note": note}
     if halo_h is not None:
+        ph = phase_ev[-ksteps:]
+        mean = lambda f: statistics.mean(f(i) for i in range(len(ph)))  # noqa: E731
+        out["phases_ms_rank0"] = {
+            "wait_for_upload": mean(lambda i: ph[i][0].elapsed_time(ph[i][1])), "exchange": mean(lambda i: ph[i][1].elapsed_time(ph[i][2])),
+            "sort_pair_reduce": mean(lambda i: ph[i][2].elapsed_time(ph[i][3])), "kernels_done_to_downloaded": mean(lambda i: ph[i][3].elapsed_time(ph[i][4])),
+            "step_period": statistics.mean(ph[i][0].elapsed_time(ph[i + 1][0]) for i in range(len(ph) - 1)) if len(ph) > 1 else None}
+    if halo_h is not None:
         halo_h.close()
+    for lane in (lanes[1:] if halo_h is None and fused else []):
+        for ev in lane["evs"]:
+            ev.close()
     for ev in evh.values():
         ev.close()
     return out

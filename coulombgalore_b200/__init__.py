@@ -9,7 +9,7 @@
 The C ABI is include/cg_b200.h; the C++ drop-in headers are under include/coulombgalore/.
 """
 from ._capi import (ENERGY, FIELD, FORCE, MODE_DIPOLE, MODE_ION, MODE_MULTIPOLE, MODE_MULTIPOLE_QUAD, POTENTIAL, CgError, lib)  # noqa: F401
-from .batched import BatchedEvaluator, eval_multi_device  # noqa: F401
+from .batched import BatchedEvaluator, eval_multi_begin, eval_multi_device, eval_multi_end  # noqa: F401
 from .reciprocal import ReciprocalEwaldGaussian, ReciprocalEwaldState  # noqa: F401
 from .schemes import (Ewald, EwaldTruncated, Fanourgakis, Fennell, Plain, Poisson, ReactionField, SchemeBase,  # noqa: F401
                       Splined, Wolf, Zahn, ZeroDipole, createScheme, create_scheme, infinity, qPotential,

@@ -229,3 +229,32 @@ def eval_multi_device(evaluators, mode, what, force=None, field=None, potential=
     hs = (C.c_void_p * n)(*[ev.h.value for ev in evaluators])
     check(lib.cg_eval_multi_device(hs, n, mode, what, arr(force), arr(field), arr(potential), arr(scalars)), "cg_eval_multi_device",
           evaluators[0].h)
+
+
+def eval_multi_begin(evaluators, mode, what, outs):
+    """Host form of eval_multi_device, first half (cg_eval_multi_begin): `outs` is one dict of caller-owned host arrays per
+    evaluator ("force" / "field" (n,3), "potential" (n,); pinned memory makes the copies asynchronous).  Returns at once."""
+    n = len(evaluators)
+    bufs = [ev._outputs(what, o) for ev, o in zip(evaluators, outs)]
+
+    def arr(i):
+        return (C.c_void_p * n)(*[None if b[i] is None else b[i].ctypes.data for b in bufs])
+    hs = (C.c_void_p * n)(*[ev.h.value for ev in evaluators])
+    for ev, b in zip(evaluators, bufs):
+        ev._pending = (what,) + tuple(b)
+    check(lib.cg_eval_multi_begin(hs, n, mode, what, arr(0), arr(1), arr(2)), "cg_eval_multi_begin", evaluators[0].h)
+
+
+def eval_multi_end(evaluators):
+    """Second half (cg_eval_multi_end): waits; -> one result dict per evaluator, like BatchedEvaluator.eval."""
+    n = len(evaluators)
+    hs = (C.c_void_p * n)(*[ev.h.value for ev in evaluators])
+    u = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib.cg_eval_multi_end(hs, n, u, cnt), "cg_eval_multi_end", evaluators[0].h)
+    res = []
+    for k, ev in enumerate(evaluators):
+        what, f, e, p = getattr(ev, "_pending", None) or (0, None, None, None)
+        ev._pending = None
+        res.append(dict(force=f, field=e, potential=p, energy=u[k] if what & ENERGY else None, pairs=cnt[k]))
+    return res

@@ -15,6 +15,7 @@
 // layers, and handles of other schemes with the same cut-off can borrow the result (cg_share_system).
 // Also here: the O(N) terms (self-energy, neutralisation, torque), the peer-memory exchange kernels of the multi-GPU step
 // (cg_peer_gather, cg_halo_publish / cg_halo_pull) and the probes.  Reciprocal-space Ewald lives in recip.cu.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -147,9 +148,8 @@ __device__ __forceinline__ int images_1d(const SortParams &sp, int d, double v, 
 // cell_start[cell] + --cell_count[cell]: the histogram counts back down to zero, no second clearing pass; the order inside a
 // cell is arbitrary here and made deterministic by the gather (ascending key).
 template <bool SCATTER>
-__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int *cell_of,
-                           int cap, int *counts) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void bin_body(const SortParams &sp, int p, int *cell_count, const int *cell_start, unsigned int *keys, int *cell_of,
+                                         int cap, int *counts) {
     // more valid particles on the device than the arrays this evaluation was given (halo exchange: the received count
     // outgrew the caller's bound): the results would silently miss particles, so the evaluation is marked invalid
     if (p == 0 && sp.n_dev && *sp.n_dev > sp.n) counts[2] = 1;
@@ -184,12 +184,17 @@ __global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_coun
             }
 }
 
+template <bool SCATTER>
+__global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_count, const int *cell_start, unsigned int *keys, int *cell_of,
+                           int cap, int *counts) {
+    bin_body<SCATTER>(sp, blockIdx.x * blockDim.x + threadIdx.x, cell_count, cell_start, keys, cell_of, cap, counts);
+}
+
 // SoA inputs -> sorted AoS arrays.  Thread k takes the key the scatter left at position k of its cell and moves it to its RANK
 // among the keys of that cell (cells hold a handful of entries): ascending key inside every cell, i.e. a deterministic order
 // and bit-reproducible results run to run, without a separate sorting pass.
-__global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, const int *cell_of,
-                              const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void gather_body(const SortParams &sp, int k, int *counts, int cap, const unsigned int *keys, const int *cell_of,
+                                            const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
     int n_sorted = counts[0];
     if (n_sorted > cap - kDummies) { // no room (the dummy entries need slots too): flag it, stay inside the arrays
         if (k == 0) counts[2] = 1;
@@ -223,6 +228,11 @@ __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts
     // w = |c|^2 of the ROUNDED coordinates (formed in fp64, rounded once): the prefilter expands |c - x_i|^2 around it
     pos32[dst] = make_float4(fx, fy, fz, (float)((double)fx * fx + (double)fy * fy + (double)fz * fz));
     orig[dst] = p;
+}
+
+__global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, const int *cell_of,
+                              const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
+    gather_body(sp, blockIdx.x * blockDim.x + threadIdx.x, counts, cap, keys, cell_of, cell_start, pos, mu, quad, pos32, orig, far);
 }
 
 // i-groups of one primary cell row k: its sorted entries [a, b)
@@ -347,10 +357,8 @@ __device__ __forceinline__ int block_scan_tile(int (&v)[kScanItems], int *warp_s
     return total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_groups_kernel(const __grid_constant__ SortParams sp, const int *cell_count, int *cell_start,
-                                                                    int ncell, int cells_done, int *row_gstart, int2 *groups, int ng_bound,
-                                                                    int gsize, int *counts) {
-    __shared__ int warp_sums[32];
+__device__ __forceinline__ void scan_groups_body(const SortParams &sp, const int *cell_count, int *cell_start, int ncell, int cells_done,
+                                                 int *row_gstart, int2 *groups, int ng_bound, int gsize, int *counts, int *warp_sums) {
     // ---- cells (cells_done: a many-CTA scan has already filled cell_start[0 .. ncell), only the total is missing) ----
     int carry = 0;
     if (cells_done) carry = ncell > 0 ? cell_start[ncell - 1] + cell_count[ncell - 1] : 0;
@@ -410,6 +418,49 @@ __global__ void __launch_bounds__(kScanThreads) scan_groups_kernel(const __grid_
     }
 }
 
+__global__ void __launch_bounds__(kScanThreads) scan_groups_kernel(const __grid_constant__ SortParams sp, const int *cell_count, int *cell_start,
+                                                                    int ncell, int cells_done, int *row_gstart, int2 *groups, int ng_bound,
+                                                                    int gsize, int *counts) {
+    __shared__ int warp_sums[32];
+    scan_groups_body(sp, cell_count, cell_start, ncell, cells_done, row_gstart, groups, ng_bound, gsize, counts, warp_sums);
+}
+
+// Small systems (a few thousand particles: BASELINE config 1, the tail of a strong-scaling run): the whole sort phase -- clear,
+// histogram, scans and group table, scatter, gather -- in ONE launch of one thread-block cluster (8 CTAs of 1024 threads, ordered
+// by the cluster barrier).  Five dependent launches of a few microseconds each otherwise cost as much as the pair kernel they
+// prepare; a single CTA, on the other hand, has too few loads in flight for the dependent gathers.  The phases talk through the
+// same global arrays as the separate kernels do; the scans run on CTA 0.
+struct SmallSort {
+    int *cell_count; // [0, 8) the device counts, then the histogram
+    int *cell_start, *row_gstart;
+    int2 *groups;
+    unsigned int *keys;
+    int *cell_of;
+    double4 *pos, *mu, *quad;
+    float4 *pos32;
+    int *orig;
+    int ncell, ng_bound, gsize, cap;
+    double far;
+};
+constexpr int kSmallSortCtas = 8;
+__global__ void __cluster_dims__(kSmallSortCtas, 1, 1) __launch_bounds__(kScanThreads)
+    small_sort_kernel(const __grid_constant__ SortParams sp, const __grid_constant__ SmallSort a) {
+    __shared__ int warp_sums[32];
+    cooperative_groups::cluster_group cluster = cooperative_groups::this_cluster();
+    int *counts = a.cell_count, *hist = a.cell_count + 8;
+    const int tid = blockIdx.x * kScanThreads + threadIdx.x, nthr = kSmallSortCtas * kScanThreads;
+    for (int k = tid; k < a.ncell + 9; k += nthr) a.cell_count[k] = 0;
+    cluster.sync();
+    for (int p = tid; p < sp.n; p += nthr) bin_body<false>(sp, p, hist, nullptr, nullptr, nullptr, 0, counts);
+    cluster.sync();
+    if (blockIdx.x == 0) scan_groups_body(sp, hist, a.cell_start, a.ncell, 0, a.row_gstart, a.groups, a.ng_bound, a.gsize, counts, warp_sums);
+    cluster.sync();
+    for (int p = tid; p < sp.n; p += nthr) bin_body<true>(sp, p, hist, a.cell_start, a.keys, a.cell_of, a.cap, counts);
+    cluster.sync();
+    for (int k = tid; k < a.cap; k += nthr)
+        gather_body(sp, k, counts, a.cap, a.keys, a.cell_of, a.cell_start, a.pos, a.mu, a.quad, a.pos32, a.orig, a.far);
+}
+
 // ---- bounding box for open boundaries ----
 __global__ void minmax_kernel(int n, const double *x, const double *y, const double *z, double *partial) {
     __shared__ double s[6][256];
@@ -439,19 +490,38 @@ __global__ void minmax_kernel(int n, const double *x, const double *y, const dou
 }
 
 // ---- epilogue kernels ----
-__global__ void combine_kernel(int64_t len, int split, const double *part, double *out) { // out[k] = sum_s part[s][k]
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= len) return;
-    double s = 0.0;
-    for (int t = 0; t < split; t++) s += part[(int64_t)t * len + k];
-    out[k] = s;
-}
-
-// deterministic: fixed strided partial sums, then a fixed tree
-__global__ void reduce_items_kernel(const int *counts, int count_index, int split, const double *item_energy,
-                                    const unsigned long long *item_pairs, double *scalars, int *work_counter) {
+// The epilogue of an evaluation in one launch.  Blocks [0, nred): the two scalars of scheme k (deterministic: fixed strided
+// partial sums, then a fixed tree).  Further blocks (j-split evaluations only): the per-slice partial outputs summed in slice
+// order, out[k] = sum_s part[s][k].
+struct EpilogueArgs {
+    int nred;
+    const double *item_energy[4];
+    double *scalars[4];
+    int ncomb;
+    const double *part[3];
+    double *out[3];
+    long long len[3];
+};
+__global__ void __launch_bounds__(1024) epilogue_kernel(const int *counts, int count_index, int split, const unsigned long long *item_pairs,
+                                                        int *work_counter, const __grid_constant__ EpilogueArgs a) {
     __shared__ double se[1024];
     __shared__ unsigned long long sp[1024];
+    if ((int)blockIdx.x >= a.nred) {
+        const long long stride = (long long)(gridDim.x - a.nred) * 1024;
+        for (int c = 0; c < a.ncomb; c++) {
+            const long long len = a.len[c];
+            const double *part = a.part[c];
+            for (long long k = (long long)(blockIdx.x - a.nred) * 1024 + threadIdx.x; k < len; k += stride) {
+                double sum = 0.0;
+                for (int t = 0; t < split; t++) sum += part[(long long)t * len + k];
+                a.out[c][k] = sum;
+            }
+        }
+        return;
+    }
+    const double *item_energy = a.item_energy[blockIdx.x];
+    double *scalars = a.scalars[blockIdx.x];
+    if (!scalars) return;
     const int items = counts[count_index] * split;
     double e = 0.0;
     unsigned long long c = 0;
@@ -480,7 +550,7 @@ __global__ void reduce_items_kernel(const int *counts, int count_index, int spli
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        *work_counter = 0;        // the pair kernel of this evaluation is done with it: ready for the next launch
+        if (blockIdx.x == 0) *work_counter = 0; // the pair kernel of this evaluation is done with it: ready for the next launch
         scalars[0] = 0.5 * se[0]; // U = 1/2 sum_i sum_j u_ij
         scalars[1] = (double)sp[0];
         if (counts[2]) { // an array overflowed in the sync-free path: the results are invalid, make that unmistakable
@@ -992,6 +1062,26 @@ static void detach_share(cg_handle *h) {
     h->share_from = nullptr;
 }
 
+
+// Per-particle outputs computed on a halo window (rows in received order) -> the owner's own order: the rows whose global
+// index lies in [lo, lo + count) go to row (index - lo) of dst.
+struct CollectArgs {
+    const double *src[8];
+    double *dst[8];
+};
+__global__ void halo_collect_kernel(const double *__restrict__ ids, const int *__restrict__ n_dev, long long bound, long long lo,
+                                    long long count, int narrays, int width, const __grid_constant__ CollectArgs a) {
+    const long long n = min((long long)*n_dev, bound);
+    const long long total = n * width;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long row = t / width;
+        const int c = (int)(t - row * width);
+        const long long own = (long long)ids[row] - lo;
+        if (own < 0 || own >= count) continue;
+        for (int k = 0; k < narrays; k++) a.dst[k][own * width + c] = a.src[k][t];
+    }
+}
+
 extern "C" {
 
 const char *cg_version(void) { return "coulombgalore_b200 0.1 (sm_100a)"; }
@@ -1404,15 +1494,61 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
     int *hist = h->cell_count.p + 8;
     CG_CUDA(h, h->cell_start.ensure((size_t)ncell + 8));
     CG_CUDA(h, h->row_gstart[0].ensure((size_t)nrows_prim + 8));
-    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 9) * sizeof(int), st));
-    const int nb_p = (n + 255) / 256;
-    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, hist, nullptr, nullptr, nullptr, 0, counts);
-    (*launches_out)++;
     int cap_sorted = 0, ng_bound[2] = {0, 0}, ng_guess[2] = {0, 0};
     const bool need_groups[2] = {true, false};
     (void)need32;
     (void)need64;
     const int gsize = 32;
+    double far_coord; // where the dummy entries behind the sorted arrays sit: beyond every cut-off of every particle
+    {
+        double span = 0.0, lo = 0.0;
+        for (int d = 0; d < 3; d++) {
+            span = std::max(span, sp.ntot[d] / sp.inv_cs[d]);
+            lo = std::min(lo, sp.lo[d] - sp.gw[d]);
+        }
+        far_coord = lo - 4.0 * span - 4.0 * std::min(rc, 1e9) - 1.0;
+    }
+    // ---- small systems in the sync-free path: the whole sort phase in one launch of one CTA ----
+    static const bool small_enabled = [] {
+        const char *e = std::getenv("CG_SMALL_SORT");
+        return !(e && e[0] == '0');
+    }();
+    if (small_enabled && fast && n <= 16384 && ncell <= 32768 && h->fast.cap_sorted <= 65536) {
+        cap_sorted = h->fast.cap_sorted;
+        ng_guess[0] = h->fast.last_groups[0];
+        ng_bound[0] = std::min(n / gsize + nrows_prim + 2, ng_guess[0] + ng_guess[0] / 8 + 64);
+        CG_CUDA(h, h->groups[0].ensure((size_t)ng_bound[0] + 1));
+        CG_CUDA(h, h->keys.ensure((size_t)cap_sorted));
+        CG_CUDA(h, h->cell_of.ensure((size_t)cap_sorted));
+        CG_CUDA(h, h->pos.ensure((size_t)cap_sorted));
+        if (need_mu) CG_CUDA(h, h->mu.ensure((size_t)cap_sorted));
+        if (need_quad) CG_CUDA(h, h->quad.ensure(2 * (size_t)cap_sorted));
+        CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
+        CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
+        SmallSort a;
+        a.cell_count = h->cell_count.p;
+        a.cell_start = h->cell_start.p;
+        a.row_gstart = h->row_gstart[0].p;
+        a.groups = h->groups[0].p;
+        a.keys = h->keys.p;
+        a.cell_of = h->cell_of.p;
+        a.pos = h->pos.p;
+        a.mu = need_mu ? h->mu.p : nullptr;
+        a.quad = need_quad ? h->quad.p : nullptr;
+        a.pos32 = h->pos32.p;
+        a.orig = h->orig.p;
+        a.ncell = ncell;
+        a.ng_bound = ng_bound[0];
+        a.gsize = gsize;
+        a.cap = cap_sorted;
+        a.far = far_coord;
+        small_sort_kernel<<<kSmallSortCtas, kScanThreads, 0, st>>>(sp, a);
+        (*launches_out)++;
+    } else {
+    CG_CUDA(h, cudaMemsetAsync(h->cell_count.p, 0, ((size_t)ncell + 9) * sizeof(int), st));
+    const int nb_p = (n + 255) / 256;
+    bin_kernel<false><<<nb_p, 256, 0, st>>>(sp, hist, nullptr, nullptr, nullptr, 0, counts);
+    (*launches_out)++;
     // small grids (a shard of a 10^6-particle system, a few thousand particles): the one-CTA kernel scans the cells too; large
     // grids: a many-CTA scan first (measured at 157 464 cells: 12 us against 40 us for the single CTA)
     const int cells_done = ncell > 32768 ? 1 : 0;
@@ -1470,18 +1606,10 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
     CG_CUDA(h, h->pos32.ensure((size_t)cap_sorted));
     CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
     bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, hist, h->cell_start.p, h->keys.p, h->cell_of.p, cap_sorted, counts);
-    double far_coord;
-    {
-        double span = 0.0, lo = 0.0;
-        for (int d = 0; d < 3; d++) {
-            span = std::max(span, sp.ntot[d] / sp.inv_cs[d]);
-            lo = std::min(lo, sp.lo[d] - sp.gw[d]);
-        }
-        far_coord = lo - 4.0 * span - 4.0 * std::min(rc, 1e9) - 1.0;
-    }
     gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->cell_of.p, h->cell_start.p, h->pos.p,
                                                          need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p, h->orig.p, far_coord);
     *launches_out += 2;
+    } // general path
     CG_CUDA(h, cudaGetLastError());
     // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
     CG_CUDA(h, cudaMemcpyAsync(h->h_counts_async, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1598,7 +1726,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     }();
     // j-split: only when the groups cannot give every resident warp of the machine an item; then as many slices as it takes
     int split = 1;
-    const int wave = device_sms * 16; // items the machine takes at once: 12 resident warps per SM (pair_kernel.cuh) and a few to even out the tail
+    const int wave = device_sms * cgb::kMaxWarpsPerSm; // resident warps of the machine (pair_kernel.cuh): one item each
     if (ng > 0 && ng < wave) split = std::max(1, std::min(64, wave / ng));
     if (split_env > 0) split = std::min(64, split_env);
     const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split
@@ -1667,7 +1795,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         std::memcpy(&bits, &cap, sizeof(bits));
         kp.r2cap_hi = (int)(bits >> 32);
     }
-    if (!h->work_counter.p) { // zeroed once; every evaluation's reduce_items_kernel leaves it at zero for the next
+    if (!h->work_counter.p) { // zeroed once; every evaluation's epilogue_kernel leaves it at zero for the next
         CG_CUDA(h, h->work_counter.ensure(1));
         CG_CUDA(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(int), st));
     }
@@ -1769,30 +1897,37 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         h->counters[2] = s->counters[2];
     }
 
-    // ---- 7-8. epilogue ----
-    if (split > 1 && items > 0) {
-        if (o_force) {
-            combine_kernel<<<(unsigned)(((int64_t)3 * n + 255) / 256), 256, 0, st>>>((int64_t)3 * n, split, h->part_force.p, o_force);
-            launches++;
+    // ---- 7-8. epilogue: scalars of every scheme, and the sum over the j-slices, in one launch ----
+    {
+        EpilogueArgs ea;
+        std::memset(&ea, 0, sizeof(ea));
+        ea.nred = 1;
+        ea.item_energy[0] = h->item_energy.p;
+        ea.scalars[0] = d_scalars;
+        if (ma)
+            for (int k = 1; k < ma->n; k++) {
+                ea.item_energy[k] = kp.item_energy_k[k - 1];
+                ea.scalars[k] = ma->scalars[k]; // may be null: that block does nothing
+                ea.nred = k + 1;
+            }
+        long long total = 0;
+        if (split > 1 && items > 0) {
+            const double *part[3] = {h->part_force.p, h->part_field.p, h->part_pot.p};
+            double *out[3] = {o_force, o_field, o_pot};
+            const long long len[3] = {3LL * n, 3LL * n, (long long)n};
+            for (int c = 0; c < 3; c++)
+                if (out[c]) {
+                    ea.part[ea.ncomb] = part[c];
+                    ea.out[ea.ncomb] = out[c];
+                    ea.len[ea.ncomb] = len[c];
+                    total = std::max(total, len[c]);
+                    ea.ncomb++;
+                }
         }
-        if (o_field) {
-            combine_kernel<<<(unsigned)(((int64_t)3 * n + 255) / 256), 256, 0, st>>>((int64_t)3 * n, split, h->part_field.p, o_field);
-            launches++;
-        }
-        if (o_pot) {
-            combine_kernel<<<(unsigned)(((int64_t)n + 255) / 256), 256, 0, st>>>((int64_t)n, split, h->part_pot.p, o_pot);
-            launches++;
-        }
+        const unsigned blocks = (unsigned)ea.nred + (unsigned)std::min<long long>((total + 1023) / 1024, 4LL * device_sms);
+        epilogue_kernel<<<blocks, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_pairs.p, h->work_counter.p, ea);
+        launches++;
     }
-    reduce_items_kernel<<<1, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_energy.p, h->item_pairs.p, d_scalars, h->work_counter.p);
-    launches++;
-    if (ma)
-        for (int k = 1; k < ma->n; k++) {
-            double *sck = ma->scalars[k];
-            if (!sck) continue;
-            reduce_items_kernel<<<1, 1024, 0, st>>>(counts, 1, split, kp.item_energy_k[k - 1], h->item_pairs.p, sck, h->work_counter.p);
-            launches++;
-        }
     CG_CUDA(h, cudaGetLastError());
     CG_CUDA(h, cudaEventRecord(h->ev[3], st));
     h->counters[1] = ncell;
@@ -1906,7 +2041,7 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
     cudaSetDevice(h->device);
     CG_CUDA(h, cudaStreamSynchronize(h->stream));
     h->pending.active = false;
-    if (h->h_scalars[1] < 0.0) { // the sync-free sizing was too small (reduce_items_kernel says so): redo with exact sizes
+    if (h->h_scalars[1] < 0.0) { // the sync-free sizing was too small (epilogue_kernel says so): redo with exact sizes
         cg_handle *s = h->share_from ? h->share_from : h;
         s->counts_pending = false;
         s->fast.valid = false;
@@ -1924,6 +2059,98 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs) {
     }
     if (energy) *energy = h->h_scalars[0];
     if (pairs) *pairs = (int64_t)(h->h_scalars[1] + 0.5);
+    return CG_OK;
+}
+
+// The host form of cg_eval_multi_device: every scheme's device outputs live in its own handle, the launch and all copies run
+// on the first handle's stream.
+int cg_eval_multi_begin(cg_handle *const *hs, int n, int mode, int what, double *const *force, double *const *field,
+                        double *const *potential) {
+    if (!hs || n < 1 || n > 4 || !hs[0]) return CG_ERR_INVALID;
+    cg_handle *h = hs[0];
+    cudaSetDevice(h->device);
+    const cg_handle *sys = h->share_from ? h->share_from : h;
+    const size_t np = (size_t)sys->n;
+    double *df[4] = {nullptr, nullptr, nullptr, nullptr}, *de[4] = {nullptr, nullptr, nullptr, nullptr},
+           *dp[4] = {nullptr, nullptr, nullptr, nullptr}, *ds[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < n; k++) {
+        cg_handle *g = hs[k];
+        if (!g) return CG_ERR_INVALID;
+        if ((what & CG_FORCE) && force && force[k]) {
+            CG_CUDA(h, g->out_force.ensure(3 * np + 1));
+            df[k] = g->out_force.p;
+        }
+        if ((what & CG_FIELD) && field && field[k]) {
+            CG_CUDA(h, g->out_field.ensure(3 * np + 1));
+            de[k] = g->out_field.p;
+        }
+        if ((what & CG_POTENTIAL) && potential && potential[k]) {
+            CG_CUDA(h, g->out_pot.ensure(np + 1));
+            dp[k] = g->out_pot.p;
+        }
+        CG_CUDA(h, g->scalars.ensure(8));
+        ds[k] = g->scalars.p;
+        if (sys->shard_n > 1) { // particles outside the shard are not written by the kernels
+            if (df[k]) CG_CUDA(h, cudaMemsetAsync(df[k], 0, 3 * np * sizeof(double), h->stream));
+            if (de[k]) CG_CUDA(h, cudaMemsetAsync(de[k], 0, 3 * np * sizeof(double), h->stream));
+            if (dp[k]) CG_CUDA(h, cudaMemsetAsync(dp[k], 0, np * sizeof(double), h->stream));
+        }
+    }
+    const int rc = cg_eval_multi_device(hs, n, mode, what, df, de, dp, ds);
+    if (rc != CG_OK) return rc;
+    cudaStream_t st = h->stream;
+    for (int k = 0; k < n; k++) {
+        cg_handle *g = hs[k];
+        if (df[k]) CG_CUDA(h, cudaMemcpyAsync(force[k], df[k], 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (de[k]) CG_CUDA(h, cudaMemcpyAsync(field[k], de[k], 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (dp[k]) CG_CUDA(h, cudaMemcpyAsync(potential[k], dp[k], np * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CG_CUDA(h, cudaMemcpyAsync(g->h_scalars, ds[k], 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        g->pending = {true, mode, what, df[k] ? force[k] : nullptr, de[k] ? field[k] : nullptr, dp[k] ? potential[k] : nullptr};
+    }
+    return CG_OK;
+}
+
+int cg_eval_multi_end(cg_handle *const *hs, int n, double *energy, int64_t *pairs) {
+    if (!hs || n < 1 || n > 4 || !hs[0]) return CG_ERR_INVALID;
+    cg_handle *h = hs[0];
+    for (int k = 0; k < n; k++)
+        if (!hs[k] || !hs[k]->pending.active) {
+            h->err = "cg_eval_multi_end without cg_eval_multi_begin";
+            return CG_ERR_STATE;
+        }
+    cudaSetDevice(h->device);
+    CG_CUDA(h, cudaStreamSynchronize(h->stream));
+    bool redo = false;
+    for (int k = 0; k < n; k++) {
+        hs[k]->pending.active = false;
+        redo = redo || hs[k]->h_scalars[1] < 0.0;
+    }
+    if (redo) { // the sync-free sizing was too small: once more, sized exactly (the next sort of the system does that)
+        cg_handle *s = h->share_from ? h->share_from : h;
+        s->counts_pending = false;
+        s->fast.valid = false;
+        if (s != h) {
+            int l = 0;
+            const int rcs = sort_system(s, s->sorted.has_mu, s->sorted.has_quad, s->want_groups[0], s->want_groups[1], &l);
+            if (rcs != CG_OK) {
+                h->err = s->err;
+                return rcs;
+            }
+        }
+        double *f[4], *e[4], *p[4];
+        for (int k = 0; k < n; k++) {
+            f[k] = hs[k]->pending.force;
+            e[k] = hs[k]->pending.field;
+            p[k] = hs[k]->pending.potential;
+        }
+        const int rc = cg_eval_multi_begin(hs, n, hs[0]->pending.mode, hs[0]->pending.what, f, e, p);
+        if (rc != CG_OK) return rc;
+        return cg_eval_multi_end(hs, n, energy, pairs);
+    }
+    for (int k = 0; k < n; k++) {
+        if (energy) energy[k] = hs[k]->h_scalars[0];
+        if (pairs) pairs[k] = (int64_t)(hs[k]->h_scalars[1] + 0.5);
+    }
     return CG_OK;
 }
 
@@ -2358,6 +2585,24 @@ int cg_halo_exchange_step(cg_handle *h, int nranks, int rank, int narrays, int z
     rc = cg_set_system_device(h, n_bound, dst[0], dst[1], dst[2], q, mx, my, mz, box, 1);
     if (rc != CG_OK) return rc;
     return cg_set_count_device(h, n_out);
+}
+
+int cg_halo_collect_owned(cg_handle *h, const double *ids, const int *n_dev, int64_t bound, int64_t lo, int64_t count, int narrays,
+                          int width, const double *const *src, double *const *dst) {
+    if (!h || !ids || !n_dev || !src || !dst || bound < 0 || count < 0 || narrays < 1 || narrays > 8 || width < 1) return CG_ERR_INVALID;
+    if (bound == 0 || count == 0) return CG_OK;
+    cudaSetDevice(h->device);
+    CollectArgs a;
+    for (int k = 0; k < 8; k++) {
+        a.src[k] = k < narrays ? src[k] : nullptr;
+        a.dst[k] = k < narrays ? dst[k] : nullptr;
+        if (k < narrays && (!a.src[k] || !a.dst[k])) return CG_ERR_INVALID;
+    }
+    const long long total = (long long)bound * width;
+    const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+    halo_collect_kernel<<<blocks, 256, 0, h->stream>>>(ids, n_dev, bound, lo, count, narrays, width, a);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
 }
 
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z, double *q,

@@ -19,6 +19,7 @@ namespace cgd = CoulombGalore::detail;
 #endif
 // CG_SLOTS: most candidate batches (of 32) whose per-lane hit masks are parked before the FP64 phase; the launch takes what the
 // shared memory of an SM allows (pair_kernel.cuh: pair_list_slots)
+constexpr int kMaxWarpsPerSm = 12; // resident warps per SM of every launch shape of the pair kernel (pair_kernel.cuh): the j-split fills them
 constexpr int kDummies = 32;     // far-away entries behind the sorted arrays: what a lane without work evaluates
 
 // Spatially sorted system.  With periodic boundaries the arrays also hold the periodic images that lie within one

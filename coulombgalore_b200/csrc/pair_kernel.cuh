@@ -99,8 +99,6 @@ template <int MODE> constexpr int gather_policy() {
 // the quadrupole mode carries two tensors per pair in registers: half the warps (255 registers each) instead of spilling at 128
 template <int MODE> constexpr int min_blocks_per_sm() { return MODE == cgd::kModeMultipoleQuad ? 1 : tuned_minb<MODE>(); }
 template <int MODE> constexpr int warps_per_cta() { return MODE == cgd::kModeMultipoleQuad ? 8 : tuned_warps<MODE>(); }
-// resident warps per SM of every shape
-constexpr int kMaxWarpsPerSm = 12;
 // pairs in flight per consumer lane and step
 #ifndef CG_ILP_DIP
 #define CG_ILP_DIP 2

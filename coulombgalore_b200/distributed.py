@@ -348,6 +348,19 @@ class HaloExchange:
         """Global particle index (as float64) of every row of the evaluator's outputs after exchange()."""
         return self.recv[self.n_payload, : self.n_bound]
 
+    def collect_owned(self, src, dst):
+        """Rows of the rank's own particles from outputs in received order (lists of [n_bound, w] device tensors) into `dst`
+        (lists of [count, w] tensors, the order of the owned arrays given to exchange()): cg_halo_collect_owned, one launch."""
+        C = self.C
+        n = len(src)
+        width = src[0].shape[1] if src[0].dim() > 1 else 1
+        sp = (C.c_void_p * n)(*[t.data_ptr() for t in src])
+        dp = (C.c_void_p * n)(*[t.data_ptr() for t in dst])
+        rc = self.lib.cg_halo_collect_owned(self.ev.h, self.ids().data_ptr(), self.n_out.data_ptr(), self.n_bound, self.lo, self.count, n,
+                                            width, sp, dp)
+        if rc != 0:
+            raise RuntimeError("cg_halo_collect_owned failed (%d)" % rc)
+
     def _track_bound(self):
         """Grow the bound handed to the engine before the received count reaches it.  A step that does exceed it is not
         silent: the engine raises its overflow flag (energy NaN, pair count -1) when the device count is larger than the

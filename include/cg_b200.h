@@ -203,6 +203,14 @@ int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *fiel
  * counters of the launch are reported for every handle. */
 int cg_eval_multi_device(cg_handle *const *hs, int n, int mode, int what, double *const *force, double *const *field,
                          double *const *potential, double *const *scalars);
+/* The same with HOST output buffers, in two halves like cg_eval_begin / cg_eval_end: force / field / potential are arrays of n
+ * host pointers (NULL arrays or entries allowed; pinned buffers make the copies asynchronous), energy[n] and pairs[n] receive
+ * every scheme's U and pair count.  Everything runs on hs[0]'s stream.  Two sets of handles used in turn -- set B's
+ * cg_set_system + cg_eval_multi_begin issued before set A's cg_eval_multi_end -- overlap the upload of one configuration and
+ * the download of another with the pair kernel of a third (bench.py's `e2e` figure). */
+int cg_eval_multi_begin(cg_handle *const *hs, int n, int mode, int what, double *const *force, double *const *field,
+                        double *const *potential);
+int cg_eval_multi_end(cg_handle *const *hs, int n, double *energy, int64_t *pairs);
 /* two scalars written by cg_eval_device (a DEVICE pointer) -> host; waits for the handle's stream */
 int cg_read_scalars(cg_handle *h, const double *scalars_dev, double host2[2]);
 
@@ -299,6 +307,13 @@ int cg_halo_exchange_step(cg_handle *h, int nranks, int rank, int narrays, int z
                           const double *zlo, const double *zhi, const double *box, void *own_block, void *const *blocks,
                           void *const *prev_blocks, const int64_t *counts, double *const *dst, int64_t dst_cap, int64_t n_bound,
                           int *n_out, int64_t step, int has_q, int has_mu);
+/* Per-particle results of an evaluation on a halo window come in received order (row r belongs to the particle whose global
+ * index the exchanged index array holds).  This brings the rows of the rank's OWN particles -- the only ones its kernels
+ * computed -- into the order of the `owned` arrays it published: dst[k][(ids[r] - lo) * width + c] = src[k][r * width + c] for
+ * ids[r] in [lo, lo + count), r < min(*n_dev, bound).  ids, n_dev, src and dst are DEVICE pointers; narrays <= 8 output arrays
+ * of `width` doubles per row (3 for force / field, 1 for the potential) are handled by one launch on the handle's stream. */
+int cg_halo_collect_owned(cg_handle *h, const double *ids, const int *n_dev, int64_t bound, int64_t lo, int64_t count, int narrays,
+                          int width, const double *const *src, double *const *dst);
 
 /* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,

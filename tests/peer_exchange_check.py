@@ -90,6 +90,12 @@ def main():
         assert idx.unique().numel() == n_got  # no particle twice
         full_f[idx] = f[:n_got]
         full_e[idx] = e[:n_got]
+        # cg_halo_collect_owned: this rank's own rows, in the order of the arrays it published
+        own_f = torch.full((hi - lo, 3), float("nan"), dtype=torch.float64, device=dev)
+        own_e = torch.full_like(own_f, float("nan"))
+        halo.collect_owned([f, e], [own_f, own_e])
+        stream.synchronize()
+        assert torch.equal(own_f, full_f[lo:hi]) and torch.equal(own_e, full_e[lo:hi]), "collect_owned, step %d" % step
         dist.all_reduce(full_f)
         dist.all_reduce(full_e)
         dist.all_reduce(sc2)

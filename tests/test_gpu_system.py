@@ -493,3 +493,37 @@ def test_two_schemes_in_one_pass(pair, oracle_kind):
             ev.close()
     finally:
         torch.cuda.set_stream(torch.cuda.default_stream(dev))
+
+
+def test_two_schemes_host_pipeline(oracle_kind):
+    """cg_eval_multi_begin / cg_eval_multi_end: the one-pass evaluation with host buffers, three different configurations in
+    flight on three sets of handles (each on its own stream) -- every set must deliver its own configuration's results."""
+    import torch
+    pair = ("wolf", "fennell")
+    box = [132.0] * 3
+    cfgs = [O.generate(44, 3.0, 700 + k, oracle_kind) for k in range(3)]
+    refs = [[O.Scheme(zoo()[nm][1], oracle_kind).batched(c[0], c[1], c[2], c[3], None, box, True, cg.MODE_ION, cg.FORCE | cg.ENERGY)
+             for nm in pair] for c in cfgs]
+    lanes = []
+    for _ in range(3):
+        evs = [cg.BatchedEvaluator(zoo()[nm][0]()) for nm in pair]
+        evs[1].share_system(evs[0])
+        N = cfgs[0][0].size
+        outs = [{"force": torch.empty((N, 3), dtype=torch.float64).pin_memory().numpy()} for _ in evs]
+        lanes.append((evs, outs))
+    for rnd in range(3):  # exact sizing, then the sync-free path; the configurations rotate through the sets
+        for k, (evs, outs) in enumerate(lanes):
+            c = cfgs[(k + rnd) % 3]
+            evs[0].set_system(c[0], c[1], c[2], c[3], None, box, True)
+            cg.eval_multi_begin(evs, cg.MODE_ION, cg.FORCE | cg.ENERGY, outs)
+        for k, (evs, outs) in enumerate(lanes):
+            res = cg.eval_multi_end(evs)
+            for j, nm in enumerate(pair):
+                assert res[j]["force"] is outs[j]["force"]
+                errs = compare(res[j], refs[(k + rnd) % 3][j], cg.FORCE | cg.ENERGY)
+                assert all(v <= 1.0 for v in errs.values()), (nm, rnd, k, errs)
+    with pytest.raises(cg.CgError):
+        cg.eval_multi_end(lanes[0][0])  # nothing in flight
+    for evs, _ in lanes:
+        for ev in evs:
+            ev.close()
