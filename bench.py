@@ -256,7 +256,7 @@ class Workload:
                 cg.eval_multi_device([self.evs[nm] for nm in self.names], self.cfg["mode"], self.cfg["what"], force=fk,
                                      scalars=[self.scal[nm] for nm in self.names])
                 launches += self.lead.counters()["launches"]
-            except cg.CgError:  # e.g. a system too small for it: one by one from now on
+            except cg.CgError:  # a combination the one-pass evaluation does not cover: one by one from now on
                 self.fused = False
         if not self.fused:
             for nm in self.names:  # the first scheme owns (bins, sorts) the system the others borrow

@@ -194,11 +194,22 @@ __global__ void bin_kernel(const __grid_constant__ SortParams sp, int *cell_coun
 // among the keys of that cell (cells hold a handful of entries): ascending key inside every cell, i.e. a deterministic order
 // and bit-reproducible results run to run, without a separate sorting pass.
 __device__ __forceinline__ void gather_body(const SortParams &sp, int k, int *counts, int cap, const unsigned int *keys, const int *cell_of,
-                                            const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
+                                            const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far,
+                                            volatile int *host_counts) {
     int n_sorted = counts[0];
     if (n_sorted > cap - kDummies) { // no room (the dummy entries need slots too): flag it, stay inside the arrays
         if (k == 0) counts[2] = 1;
         n_sorted = cap - kDummies;
+    }
+    if (k == 0 && host_counts) {
+        // the device counts of this sort go straight to pinned host memory (the next evaluation sizes its arrays from them): a
+        // posted write instead of a copy operation in the stream, which costs the stream ~5 us per evaluation.  Nothing after
+        // this point of the sort raises the overflow flag (the pair kernel clamps, it does not flag).
+        host_counts[0] = counts[0];
+        host_counts[1] = counts[1];
+        host_counts[2] = counts[2];
+        host_counts[3] = counts[3];
+        __threadfence_system();
     }
     if (k >= n_sorted + kDummies) return;
     if (k >= n_sorted) { // dummy entries far outside the system: chargeless, momentless, beyond every cut-off
@@ -231,8 +242,9 @@ __device__ __forceinline__ void gather_body(const SortParams &sp, int k, int *co
 }
 
 __global__ void gather_kernel(const __grid_constant__ SortParams sp, int *counts, int cap, const unsigned int *keys, const int *cell_of,
-                              const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far) {
-    gather_body(sp, blockIdx.x * blockDim.x + threadIdx.x, counts, cap, keys, cell_of, cell_start, pos, mu, quad, pos32, orig, far);
+                              const int *cell_start, double4 *pos, double4 *mu, double4 *quad, float4 *pos32, int *orig, double far,
+                              int *host_counts) {
+    gather_body(sp, blockIdx.x * blockDim.x + threadIdx.x, counts, cap, keys, cell_of, cell_start, pos, mu, quad, pos32, orig, far, host_counts);
 }
 
 // i-groups of one primary cell row k: its sorted entries [a, b)
@@ -441,6 +453,7 @@ struct SmallSort {
     int *orig;
     int ncell, ng_bound, gsize, cap;
     double far;
+    int *host_counts; // pinned
 };
 constexpr int kSmallSortCtas = 8;
 __global__ void __cluster_dims__(kSmallSortCtas, 1, 1) __launch_bounds__(kScanThreads)
@@ -458,7 +471,7 @@ __global__ void __cluster_dims__(kSmallSortCtas, 1, 1) __launch_bounds__(kScanTh
     for (int p = tid; p < sp.n; p += nthr) bin_body<true>(sp, p, hist, a.cell_start, a.keys, a.cell_of, a.cap, counts);
     cluster.sync();
     for (int k = tid; k < a.cap; k += nthr)
-        gather_body(sp, k, counts, a.cap, a.keys, a.cell_of, a.cell_start, a.pos, a.mu, a.quad, a.pos32, a.orig, a.far);
+        gather_body(sp, k, counts, a.cap, a.keys, a.cell_of, a.cell_start, a.pos, a.mu, a.quad, a.pos32, a.orig, a.far, a.host_counts);
 }
 
 // ---- bounding box for open boundaries ----
@@ -498,9 +511,9 @@ struct EpilogueArgs {
     const double *item_energy[4];
     double *scalars[4];
     int ncomb;
-    const double *part[3];
-    double *out[3];
-    long long len[3];
+    const double *part[9];
+    double *out[9];
+    long long len[9];
 };
 __global__ void __launch_bounds__(1024) epilogue_kernel(const int *counts, int count_index, int split, const unsigned long long *item_pairs,
                                                         int *work_counter, const __grid_constant__ EpilogueArgs a) {
@@ -1542,6 +1555,7 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
         a.gsize = gsize;
         a.cap = cap_sorted;
         a.far = far_coord;
+        a.host_counts = h->h_counts_async;
         small_sort_kernel<<<kSmallSortCtas, kScanThreads, 0, st>>>(sp, a);
         (*launches_out)++;
     } else {
@@ -1607,12 +1621,12 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
     CG_CUDA(h, h->orig.ensure((size_t)cap_sorted));
     bin_kernel<true><<<nb_p, 256, 0, st>>>(sp, hist, h->cell_start.p, h->keys.p, h->cell_of.p, cap_sorted, counts);
     gather_kernel<<<(cap_sorted + 255) / 256, 256, 0, st>>>(sp, counts, cap_sorted, h->keys.p, h->cell_of.p, h->cell_start.p, h->pos.p,
-                                                         need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p, h->orig.p, far_coord);
+                                                         need_mu ? h->mu.p : nullptr, need_quad ? h->quad.p : nullptr, h->pos32.p, h->orig.p, far_coord,
+                                                         h->h_counts_async);
     *launches_out += 2;
     } // general path
     CG_CUDA(h, cudaGetLastError());
-    // the device counts travel to pinned memory ahead of the pair kernel; the next call (or cg_eval's final sync) reads them
-    CG_CUDA(h, cudaMemcpyAsync(h->h_counts_async, counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    // the gather has written the device counts to pinned memory; the next call (or cg_eval's final sync) reads them
     CG_CUDA(h, cudaEventRecord(h->counts_ev, st));
     h->counts_pending = true;
     S.rc = rc;
@@ -1724,9 +1738,14 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         const char *e = std::getenv("CG_SPLIT");
         return e ? std::atoi(e) : 0;
     }();
-    // j-split: only when the groups cannot give every resident warp of the machine an item; then as many slices as it takes
+    // j-split: only when the groups cannot give every resident warp of the machine an item; then `split` warps share a group,
+    // each taking every split-th candidate batch of every row (139 groups of config 1: 12 slices, one item per warp).  Splitting
+    // launches that have a few groups per warp, to make the last round finer, was measured and lost: an 1/8 shard of config 2
+    // (4062 groups, 2.3 per warp) 0.296 ms with 2 slices against 0.286 ms, an 1/8 shard of config 3 (1024 groups) 0.45 ms with 5
+    // slices against 0.14 ms -- a slice re-walks all rows of its group for a fifth of the batches, and its short hit lists fill
+    // the lanes badly.
     int split = 1;
-    const int wave = device_sms * cgb::kMaxWarpsPerSm; // resident warps of the machine (pair_kernel.cuh): one item each
+    const int wave = device_sms * cgb::kMaxWarpsPerSm; // resident warps of the machine (pair_kernel.cuh)
     if (ng > 0 && ng < wave) split = std::max(1, std::min(64, wave / ng));
     if (split_env > 0) split = std::min(64, split_env);
     const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split
@@ -1835,23 +1854,55 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.potential = o_pot;
     }
     (void)cwhat;
+    // partial outputs summed by the epilogue: {per-slice buffer, destination, length}
+    struct Comb {
+        const double *part;
+        double *out;
+        long long len;
+    } comb[9];
+    int ncomb = 0;
+    if (split > 1) {
+        if (o_force) comb[ncomb++] = {h->part_force.p, o_force, 3LL * n};
+        if (o_field) comb[ncomb++] = {h->part_field.p, o_field, 3LL * n};
+        if (o_pot) comb[ncomb++] = {h->part_pot.p, o_pot, (long long)n};
+    }
     const FunctorEntry *fe = functor_entry(ma ? (int)kFnErfcMulti2 : h->functor);
     if (!fe) return CG_ERR_INVALID;
     cg_scheme_desc Dm = D; // the descriptor the functor is built from
     if (ma) {
-        if (split > 1) {
-            h->err = "cg_eval_multi_device: the system is too small (j-split evaluation); evaluate the schemes one by one";
-            return CG_ERR_UNSUPPORTED;
-        }
         Dm.reserved0 = 0;
         CG_CUDA(h, h->item_energy.ensure((size_t)std::max(items, 1) * (size_t)ma->n));
         kp.item_energy = h->item_energy.p;
         for (int k = 0; k < ma->n; k++) {
             Dm.reserved0 |= (ma->hs[k]->desc.functor & 255) << (8 * k);
             if (k == 0) continue;
-            kp.force_k[k - 1] = (what & CG_FORCE) ? ma->force[k] : nullptr;
-            kp.field_k[k - 1] = (what & CG_FIELD) ? ma->field[k] : nullptr;
-            kp.potential_k[k - 1] = (what & CG_POTENTIAL) ? ma->pot[k] : nullptr;
+            cg_handle *g = ma->hs[k];
+            double *of = (what & CG_FORCE) ? ma->force[k] : nullptr, *oe = (what & CG_FIELD) ? ma->field[k] : nullptr,
+                   *op = (what & CG_POTENTIAL) ? ma->pot[k] : nullptr;
+            if (split > 1) { // the further schemes' slices go to their own handles' partial buffers
+                const bool clear = s->shard_n > 1;
+                if (of) {
+                    CG_CUDA(h, g->part_force.ensure((size_t)split * n * 3));
+                    if (clear) CG_CUDA(h, cudaMemsetAsync(g->part_force.p, 0, (size_t)split * n * 3 * sizeof(double), st));
+                    comb[ncomb++] = {g->part_force.p, of, 3LL * n};
+                    of = g->part_force.p;
+                }
+                if (oe) {
+                    CG_CUDA(h, g->part_field.ensure((size_t)split * n * 3));
+                    if (clear) CG_CUDA(h, cudaMemsetAsync(g->part_field.p, 0, (size_t)split * n * 3 * sizeof(double), st));
+                    comb[ncomb++] = {g->part_field.p, oe, 3LL * n};
+                    oe = g->part_field.p;
+                }
+                if (op) {
+                    CG_CUDA(h, g->part_pot.ensure((size_t)split * n));
+                    if (clear) CG_CUDA(h, cudaMemsetAsync(g->part_pot.p, 0, (size_t)split * n * sizeof(double), st));
+                    comb[ncomb++] = {g->part_pot.p, op, (long long)n};
+                    op = g->part_pot.p;
+                }
+            }
+            kp.force_k[k - 1] = of;
+            kp.field_k[k - 1] = oe;
+            kp.potential_k[k - 1] = op;
             kp.item_energy_k[k - 1] = h->item_energy.p + (size_t)k * (size_t)std::max(items, 1);
         }
     }
@@ -1911,19 +1962,14 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
                 ea.nred = k + 1;
             }
         long long total = 0;
-        if (split > 1 && items > 0) {
-            const double *part[3] = {h->part_force.p, h->part_field.p, h->part_pot.p};
-            double *out[3] = {o_force, o_field, o_pot};
-            const long long len[3] = {3LL * n, 3LL * n, (long long)n};
-            for (int c = 0; c < 3; c++)
-                if (out[c]) {
-                    ea.part[ea.ncomb] = part[c];
-                    ea.out[ea.ncomb] = out[c];
-                    ea.len[ea.ncomb] = len[c];
-                    total = std::max(total, len[c]);
-                    ea.ncomb++;
-                }
-        }
+        if (items > 0)
+            for (int c = 0; c < ncomb; c++) {
+                ea.part[c] = comb[c].part;
+                ea.out[c] = comb[c].out;
+                ea.len[c] = comb[c].len;
+                total = std::max(total, comb[c].len);
+                ea.ncomb = c + 1;
+            }
         const unsigned blocks = (unsigned)ea.nred + (unsigned)std::min<long long>((total + 1023) / 1024, 4LL * device_sms);
         epilogue_kernel<<<blocks, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_pairs.p, h->work_counter.p, ea);
         launches++;

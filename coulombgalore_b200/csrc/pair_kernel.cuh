@@ -97,8 +97,14 @@ template <int MODE> constexpr int gather_policy() {
 #endif
 }
 // the quadrupole mode carries two tensors per pair in registers: half the warps (255 registers each) instead of spilling at 128
-template <int MODE> constexpr int min_blocks_per_sm() { return MODE == cgd::kModeMultipoleQuad ? 1 : tuned_minb<MODE>(); }
-template <int MODE> constexpr int warps_per_cta() { return MODE == cgd::kModeMultipoleQuad ? 8 : tuned_warps<MODE>(); }
+#ifndef CG_WARPS_QUAD
+#define CG_WARPS_QUAD 8
+#endif
+#ifndef CG_MINB_QUAD
+#define CG_MINB_QUAD 1
+#endif
+template <int MODE> constexpr int min_blocks_per_sm() { return MODE == cgd::kModeMultipoleQuad ? CG_MINB_QUAD : tuned_minb<MODE>(); }
+template <int MODE> constexpr int warps_per_cta() { return MODE == cgd::kModeMultipoleQuad ? CG_WARPS_QUAD : tuned_warps<MODE>(); }
 // pairs in flight per consumer lane and step
 #ifndef CG_ILP_DIP
 #define CG_ILP_DIP 2

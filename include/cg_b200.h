@@ -197,8 +197,8 @@ int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *fiel
  * of n DEVICE pointers (NULL arrays or entries allowed), one per scheme.  The binning, the prefilter, the walk over the hit
  * lists, the gathers, the distance and 1/r are done once per pair; schemes of the erfc family that share alpha also share
  * erfc(eta q) and exp(-eta^2 q^2) and differ by a cubic polynomial each (detail/srf.hpp: ErfcMultiSrf).  Supported: n = 2,
- * CG_MODE_ION, unscreened Wolf / Fennell / ZeroDipole / Zahn / Ewald / EwaldTruncated with one alpha and one cut-off, systems
- * large enough not to need the j-split; CG_ERR_UNSUPPORTED otherwise (evaluate one by one then).  n = 1 is cg_eval_device.
+ * CG_MODE_ION, unscreened Wolf / Fennell / ZeroDipole / Zahn / Ewald / EwaldTruncated with one alpha and one cut-off;
+ * CG_ERR_UNSUPPORTED otherwise (evaluate one by one then).  n = 1 is cg_eval_device.
  * The results agree with the one-by-one evaluation to rounding (1e-15 relative), the pair counts exactly.  Timings and
  * counters of the launch are reported for every handle. */
 int cg_eval_multi_device(cg_handle *const *hs, int n, int mode, int what, double *const *force, double *const *field,

@@ -527,3 +527,57 @@ def test_two_schemes_host_pipeline(oracle_kind):
     for evs, _ in lanes:
         for ev in evs:
             ev.close()
+
+
+@pytest.mark.parametrize("n_side,shard", [(14, None), (24, (1, 4))])
+def test_two_schemes_in_one_pass_with_j_split(n_side, shard, oracle_kind):
+    """The one-pass evaluation where the engine cuts the candidate runs of every group into slices (few groups per resident
+    warp: a small system, or one rank's shard of a larger one): per-scheme partial outputs, summed by the epilogue."""
+    import torch
+    pair = ("wolf", "fennell")
+    x, y, z, q, mu = O.generate(n_side, 3.0, 811, oracle_kind)
+    box = [3.0 * n_side] * 3
+    dev = torch.device("cuda", 0)
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(st)
+    try:
+        evs = [cg.BatchedEvaluator(zoo()[nm][0]()) for nm in pair]
+        for ev in evs:
+            ev.set_stream(st.cuda_stream)
+        if shard:
+            evs[0].set_shard(*shard)
+        evs[1].share_system(evs[0])
+        dx = [torch.tensor(a, dtype=torch.float64, device=dev) for a in (x, y, z, q)]
+        N = x.size
+        what = cg.ENERGY | cg.FORCE | cg.POTENTIAL
+        refs = [O.Scheme(zoo()[nm][1], oracle_kind).batched(x, y, z, q, None, box, True, cg.MODE_ION, what) for nm in pair]
+        for rep in range(2):
+            f = [torch.full((N, 3), float("nan"), dtype=torch.float64, device=dev) for _ in evs]
+            p = [torch.full((N,), float("nan"), dtype=torch.float64, device=dev) for _ in evs]
+            sc = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in evs]
+            evs[0].set_system_device(dx[0], dx[1], dx[2], dx[3], None, box, True)
+            cg.eval_multi_device(evs, cg.MODE_ION, what, force=f, potential=p, scalars=sc)
+            torch.cuda.synchronize()
+            assert evs[0].counters()["split"] > 1
+            for k, nm in enumerate(pair):
+                fk, pk = f[k].cpu().numpy(), p[k].cpu().numpy()
+                if shard:  # only the shard's own particles are evaluated: compare those (the one-by-one evaluation tells which)
+                    f1 = torch.full((N, 3), float("nan"), dtype=torch.float64, device=dev)
+                    s1 = torch.zeros(2, dtype=torch.float64, device=dev)
+                    evs[k].eval_device(cg.MODE_ION, what, force=f1, potential=torch.zeros(N, dtype=torch.float64, device=dev), scalars=s1)
+                    torch.cuda.synchronize()
+                    f1n = f1.cpu().numpy()  # the j-split epilogue writes every row: zeros for the particles of other shards
+                    own = np.any(f1n != 0.0, axis=1) & ~np.isnan(f1n[:, 0])
+                    assert 0 < own.sum() < N and np.array_equal(own, np.any(fk != 0.0, axis=1) & ~np.isnan(fk[:, 0]))
+                    assert s1[1].item() == sc[k][1].item()
+                    scale = np.abs(refs[k]["force"]).max()
+                    assert np.abs(fk[own] - refs[k]["force"][own]).max() <= 1e-12 * scale
+                    assert np.abs(fk[own] - f1.cpu().numpy()[own]).max() <= 1e-13 * scale
+                else:
+                    g = dict(force=fk, potential=pk, energy=sc[k][0].item(), pairs=int(sc[k][1].item()))
+                    errs = compare(g, refs[k], what)
+                    assert all(v <= 1.0 for v in errs.values()), (nm, rep, errs)
+        for ev in evs:
+            ev.close()
+    finally:
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Kernel-level timing of the BASELINE configs on one GPU (tuning aid; the judged numbers come from bench.py).
-usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,2m,3,4s,4,5s,5}  (4s / 5s = configs 4 / 5 at n = 100 / 128;
-2m = Wolf + Fennell in one pass, as bench.py evaluates config 2)"""
+usage: python tools/quick_bench.py [cfg ...]   cfg in {1,2w,2f,2m,3,4s,4,5s,5,q}  (4s / 5s = configs 4 / 5 at n = 100 / 128;
+2m = Wolf + Fennell in one pass, as bench.py evaluates config 2; q = Ewald with quadrupoles, n = 64)"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -16,6 +16,7 @@ CONFIGS = {
     "4s": dict(pot=lambda: cg.Ewald(10, 0.3, INF, 30.0), n=100, a=3.0, seed=1004, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=133),
     "4": dict(pot=lambda: cg.Ewald(10, 0.3, INF, 30.0), n=160, a=3.0, seed=1004, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=133),
     "5": dict(pot=lambda: cg.Splined().spline(cg.Poisson, 12, 4, 3), n=256, a=3.0, seed=1005, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=153),
+    "q": dict(pot=lambda: cg.Ewald(10, 0.3, INF, INF), n=64, a=3.0, seed=1006, pbc=True, mode=cg.MODE_MULTIPOLE_QUAD, what=cg.ENERGY | cg.FORCE, falg=400),
     "5s": dict(pot=lambda: cg.Splined().spline(cg.Poisson, 12, 4, 3), n=128, a=3.0, seed=1005, pbc=True, mode=cg.MODE_MULTIPOLE, what=cg.ENERGY | cg.FORCE, falg=153),
 }
 
@@ -70,6 +71,9 @@ def main():
         need_mu = c["mode"] != cg.MODE_ION
         need_q = c["mode"] != cg.MODE_DIPOLE
         ev.set_system_device(arr[0], arr[1], arr[2], arr[3] if need_q else None, (arr[4], arr[5], arr[6]) if need_mu else None, [L] * 3, c["pbc"])
+        if c["mode"] == cg.MODE_MULTIPOLE_QUAD:  # random (neither symmetric nor traceless) quadrupole tensors
+            quad = torch.rand((N, 9), dtype=torch.float64, device=dev, generator=torch.Generator(device=dev).manual_seed(c["seed"])) - 0.5
+            ev.set_quadrupoles_device(quad)
         f = torch.empty((N, 3), dtype=torch.float64, device=dev)
         e = torch.empty((N, 3), dtype=torch.float64, device=dev)
         sc = torch.zeros(2, dtype=torch.float64, device=dev)
