@@ -1020,6 +1020,7 @@ struct cg_handle {
     DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
     DevBuf<unsigned long long> item_pairs;
     DevBuf<int> work_counter;    // next work item of the persistent pair kernel
+    DevBuf<int> ap_counts;       // all-pairs path: the counts the epilogue kernel reads (written by allpairs_kernel)
     int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
     int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
     DevBuf<int> halo_counts;
@@ -1651,6 +1652,191 @@ struct MultiArgs {
     double *const *force, *const *field, *const *pot, *const *scalars;
 };
 
+// ---- all-pairs path (allpairs_kernel.cuh): small open systems are evaluated straight from the caller's SoA arrays ----
+// Largest system that takes it: the fp32 prefilter of n^2 candidates costs ~15 us at n = 8192, less than the sort phase of
+// the cell-list path, whatever the cut-off culls.  CG_ALLPAIRS_MAX=0 switches the path off.
+static int allpairs_max() { // read per evaluation: the tests compare both paths in one process
+    const char *e = std::getenv("CG_ALLPAIRS_MAX");
+    return e ? std::atoi(e) : 8192;
+}
+// the smallest instantiated (mode, what) superset of a request
+static int combo_for(int mode, int what) {
+    int ci = -1;
+    for (int k = 0; k < kNumCombos; k++) {
+        const Combo c = combo(k);
+        if (c.mode != mode || (c.what & what) != what) continue;
+        if (ci < 0 || __builtin_popcount(c.what) < __builtin_popcount(combo(ci).what)) ci = k;
+    }
+    return ci;
+}
+static bool allpairs_applies(const cg_handle *h, const cg_handle *sys, int mode, const MultiArgs *ma) {
+    const int n = (int)sys->n;
+    if (n < 2 || n > allpairs_max() || sys->pbc || sys->shard_n > 1 || sys->n_dev || h->precision != CG_FP64) return false;
+    if (mode == CG_MODE_MULTIPOLE_QUAD) return false;
+    // handles that lend or borrow a sorted system keep the cell-list path (the one-pass evaluation of two schemes is a launch
+    // of the first handle, whatever the others borrow)
+    if (!ma && (h->share_from || !h->borrowers.empty())) return false;
+    if (ma && sys != h) return false;
+    if (mode != CG_MODE_ION && !sys->in[4]) return false;
+    for (int k = 0; k < 7; k++)
+        if (sys->in[k] && ((uintptr_t)sys->in[k] & 15) != 0) return false; // TMA bulk copies: 16-byte aligned sources
+    return true;
+}
+static int eval_allpairs(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars,
+                         const MultiArgs *ma, bool *taken) {
+    *taken = false;
+    const int ci = combo_for(mode, what);
+    if (ci < 0) return CG_ERR_INVALID;
+    const FunctorEntry *fe = functor_entry(ma ? (int)kFnErfcMulti2 : h->functor);
+    if (!fe || !fe->ap[ci]) return CG_OK;
+    const double *dev_table = nullptr;
+    int table_doubles = 0;
+    if (fe->table_kind == cgd::kTableSpline) {
+        dev_table = h->d_table.p;
+        table_doubles = h->table_doubles;
+    } else if (fe->table_kind == cgd::kTableErfc) {
+        dev_table = h->d_erfc_table.p;
+        table_doubles = 2 * cgd::kErfcTableEntries;
+    }
+    int warps = 12, ctas_per_sm = 1;
+    fe->ap_dims(ci, &warps, &ctas_per_sm);
+    const ApLayout L = ap_layout(table_doubles, mode == CG_MODE_ION ? 4 : 7, warps);
+    if (L.total > (size_t)227 * 1024) return CG_OK; // a table that leaves no room for the tiles: cell-list path
+    *taken = true;
+    cudaStream_t st = h->stream;
+    const int n = (int)h->n;
+    const cg_scheme_desc &D = h->desc;
+    CG_CUDA(h, cudaEventRecord(h->ev[1], st)); // no sort phase
+    int device_sms = 148;
+    cudaDeviceGetAttribute(&device_sms, cudaDevAttrMultiProcessorCount, h->device);
+    // grid: blocks of `warps` i-groups x j-slices, one CTA per resident slot of the machine when the system is that small
+    const int n_groups = (n + 31) / 32, n_iblocks = (n_groups + warps - 1) / warps;
+    if ((int64_t)L.total * ctas_per_sm > (int64_t)227 * 1024) ctas_per_sm = 1;
+    int n_slices = std::max(1, device_sms * ctas_per_sm / n_iblocks);
+    n_slices = std::min(n_slices, std::min(kApMaxSlices, (n + 63) / 64));
+    const char *slices_e = std::getenv("CG_AP_SLICES"); // tests: long slices (several tiles per CTA) on small systems
+    const int slices_env = slices_e ? std::atoi(slices_e) : 0;
+    if (slices_env > 0) n_slices = std::min(slices_env, kApMaxSlices);
+    const int slice_len = (((n + n_slices - 1) / n_slices) + 31) & ~31;
+    n_slices = (n + slice_len - 1) / slice_len;
+    const int items = n_groups * n_slices;
+
+    APParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.n = n;
+    ap.x = h->in[0];
+    ap.y = h->in[1];
+    ap.z = h->in[2];
+    ap.q = h->in[3];
+    if (mode != CG_MODE_ION) {
+        ap.mx = h->in[4];
+        ap.my = h->in[5];
+        ap.mz = h->in[6];
+    }
+    ap.n_slices = n_slices;
+    ap.slice_len = slice_len;
+    ap.rc2 = D.cutoff_squared;
+    ap.rc2f = (float)std::min(D.cutoff_squared, 3e38);
+    {
+        const double cap = D.cutoff_squared < 1e300 ? 4.0 * D.cutoff_squared : 1.7e308;
+        long long bits;
+        std::memcpy(&bits, &cap, sizeof(bits));
+        ap.r2cap_hi = (int)(bits >> 32);
+    }
+    ap.core.inverse_cutoff = D.inverse_cutoff;
+    ap.core.cutoff_squared = D.cutoff_squared;
+    ap.core.kappa = D.inverse_debye_length;
+    CG_CUDA(h, h->ap_counts.ensure(4));
+    ap.counts = h->ap_counts.p;
+    const int nsch = ma ? ma->n : 1;
+    CG_CUDA(h, h->item_energy.ensure((size_t)items * (size_t)nsch));
+    CG_CUDA(h, h->item_pairs.ensure((size_t)items));
+    ap.item_energy = h->item_energy.p;
+    ap.item_pairs = h->item_pairs.p;
+    if (!h->work_counter.p) { // the epilogue kernel resets it
+        CG_CUDA(h, h->work_counter.ensure(1));
+        CG_CUDA(h, cudaMemsetAsync(h->work_counter.p, 0, sizeof(int), st));
+    }
+    struct Comb {
+        const double *part;
+        double *out;
+        long long len;
+    } comb[9];
+    int ncomb = 0;
+    // outputs of scheme k: the caller's arrays with one slice, per-slice partial buffers of the scheme's own handle otherwise
+    for (int k = 0; k < nsch; k++) {
+        cg_handle *g = ma ? ma->hs[k] : h;
+        double *of = (what & CG_FORCE) ? (ma ? ma->force[k] : d_force) : nullptr, *oe = (what & CG_FIELD) ? (ma ? ma->field[k] : d_field) : nullptr,
+               *op = (what & CG_POTENTIAL) ? (ma ? ma->pot[k] : d_pot) : nullptr;
+        if (n_slices > 1) {
+            if (of) {
+                CG_CUDA(h, g->part_force.ensure((size_t)n_slices * n * 3));
+                comb[ncomb++] = {g->part_force.p, of, 3LL * n};
+                of = g->part_force.p;
+            }
+            if (oe) {
+                CG_CUDA(h, g->part_field.ensure((size_t)n_slices * n * 3));
+                comb[ncomb++] = {g->part_field.p, oe, 3LL * n};
+                oe = g->part_field.p;
+            }
+            if (op) {
+                CG_CUDA(h, g->part_pot.ensure((size_t)n_slices * n));
+                comb[ncomb++] = {g->part_pot.p, op, (long long)n};
+                op = g->part_pot.p;
+            }
+        }
+        if (k == 0) {
+            ap.force = of;
+            ap.field = oe;
+            ap.potential = op;
+        } else {
+            ap.force_k[k - 1] = of;
+            ap.field_k[k - 1] = oe;
+            ap.potential_k[k - 1] = op;
+            ap.item_energy_k[k - 1] = h->item_energy.p + (size_t)k * (size_t)items;
+        }
+    }
+    cg_scheme_desc Dm = D;
+    if (ma) {
+        Dm.reserved0 = 0;
+        for (int k = 0; k < ma->n; k++) Dm.reserved0 |= (ma->hs[k]->desc.functor & 255) << (8 * k);
+    }
+    CG_CUDA(h, fe->ap[ci](ap, Dm, dev_table, table_doubles, device_sms, st));
+    CG_CUDA(h, cudaEventRecord(h->ev[2], st));
+    {
+        EpilogueArgs ea;
+        std::memset(&ea, 0, sizeof(ea));
+        ea.nred = nsch;
+        for (int k = 0; k < nsch; k++) {
+            ea.item_energy[k] = h->item_energy.p + (size_t)k * (size_t)items;
+            ea.scalars[k] = k == 0 ? d_scalars : ma->scalars[k];
+        }
+        long long total = 0;
+        for (int c = 0; c < ncomb; c++) {
+            ea.part[c] = comb[c].part;
+            ea.out[c] = comb[c].out;
+            ea.len[c] = comb[c].len;
+            total = std::max(total, comb[c].len);
+            ea.ncomb = c + 1;
+        }
+        const unsigned blocks = (unsigned)ea.nred + (unsigned)std::min<long long>((total + 1023) / 1024, 4LL * device_sms);
+        epilogue_kernel<<<blocks, 1024, 0, st>>>(h->ap_counts.p, 1, n_slices, h->item_pairs.p, h->work_counter.p, ea);
+    }
+    CG_CUDA(h, cudaGetLastError());
+    CG_CUDA(h, cudaEventRecord(h->ev[3], st));
+    h->sorted.valid = false; // nothing was sorted: a later borrower must ask for a sort
+    h->counters[0] = n;
+    h->counters[1] = 0;
+    h->counters[2] = n_groups;
+    h->last_gt = 0;
+    h->counters[3] = 1;
+    h->counters[4] = 2;
+    h->counters[5] = n_slices;
+    h->counters[6] = 1;
+    h->counters[7] = items;
+    return CG_OK;
+}
+
 // the evaluation proper; outputs are device pointers (may be null)
 static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, double *d_field, double *d_pot, double *d_scalars,
                             const MultiArgs *ma = nullptr) {
@@ -1679,6 +1865,11 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     }
     const cg_scheme_desc &D = h->desc;
     const double rc = D.cutoff;
+    if (allpairs_applies(h, sys, mode, ma)) { // small open systems: no sort, one pair launch on the caller's arrays
+        bool taken = false;
+        const int rca = eval_allpairs(h, mode, what, d_force, d_field, d_pot, d_scalars, ma, &taken);
+        if (rca != CG_OK || taken) return rca;
+    }
 
     // ---- 0-5. the sorted system: the handle's own, or borrowed from the handle named by cg_share_system ----
     cg_handle *s = h->share_from ? h->share_from : h;

@@ -58,6 +58,44 @@ struct KParams {
     unsigned long long *item_pairs;   // [items]
 };
 
+// All-pairs path for small systems (allpairs_kernel.cuh): no sort, no cell list -- the kernel reads the caller's SoA arrays
+// as they are.  Work item = (block of i-groups, j-slice); every CTA streams its j-slice through shared memory in tiles
+// (TMA bulk copies, two stages) and every warp keeps 32 i-particles in registers.
+constexpr int kApTile = 512;      // most j's of one tile (a multiple of 32)
+constexpr int kApMaxSlices = 64;  // j-slices per i-block: what the epilogue's slice sum is sized for
+struct APParams {
+    int n;                         // particles
+    const double *x, *y, *z, *q;   // SoA inputs, 16-byte aligned (q may be null: no charges)
+    const double *mx, *my, *mz;    // dipole moments (null in ion mode)
+    int n_slices, slice_len;       // j-slices and their length (a multiple of 32; the last one may be shorter)
+    double box[3];                 // periodic box (minimum image, box >= 2 cut-offs per dimension); 0 = open
+    double rc2;                    // exact gate: r2 < cutoff^2 (strict)
+    float rc2f;                    // the same for the fp32 prefilter (before the margin); +inf for an unbounded cut-off
+    int r2cap_hi;                  // see KParams
+    cgd::CoreParams core;
+    int *counts;                   // [4]: written by the kernel for the epilogue: {n, i-groups, 0, 0}
+    double *force, *field, *potential; // [n_slices][n] partial outputs (the caller's arrays when n_slices == 1)
+    double *force_k[3], *field_k[3], *potential_k[3], *item_energy_k[3];
+    double *item_energy;           // [i-groups * n_slices]
+    unsigned long long *item_pairs;
+};
+typedef cudaError_t (*ap_launch_fn)(const APParams &p, const cg_scheme_desc &desc, const double *dev_table, int table_doubles,
+                                    int sms, cudaStream_t stream);
+// shared-memory layout of the all-pairs kernel (byte offsets): functor table | stages [2][arrays][kApTile + kDummies] doubles |
+// fp32 tile [2][kApTile] float4 | hit lists [warps][(kApTile / 32 + 1) * 32] uint2 | mbarriers [2] | tile maxima [2]
+struct ApLayout {
+    size_t stage, f32, lists, bars, total;
+};
+inline ApLayout ap_layout(int table_doubles, int arrays, int warps) {
+    ApLayout L;
+    L.stage = ((size_t)table_doubles * 8 + 127) & ~(size_t)127;
+    L.f32 = L.stage + (size_t)2 * arrays * (kApTile + kDummies) * sizeof(double);
+    L.lists = L.f32 + (size_t)2 * kApTile * sizeof(float4);
+    L.bars = L.lists + (size_t)warps * (kApTile / 32 + 1) * 32 * sizeof(uint2);
+    L.total = L.bars + 2 * sizeof(unsigned long long) + 2 * sizeof(int) + 8;
+    return L;
+}
+
 typedef cudaError_t (*pair_launch_fn)(const KParams &p, const cg_scheme_desc &desc, const double *dev_table,
                                       int table_doubles, int items, int sms, cudaStream_t stream);
 typedef cudaError_t (*srf_launch_fn)(const cg_scheme_desc &desc, const double *dev_table, int table_doubles, int64_t n,
@@ -84,6 +122,8 @@ __host__ __device__ constexpr Combo combo(int i) {
 struct FunctorEntry {
     pair_launch_fn pair[kNumCombos];   // fp64 pair arithmetic
     pair_launch_fn pair32[kNumCombos]; // fp32 pair arithmetic (CG_FP32); the quadrupole combinations are fp64 in both tables
+    ap_launch_fn ap[kNumCombos];       // all-pairs path (fp64; no quadrupole combinations)
+    void (*ap_dims)(int combo, int *warps, int *ctas_per_sm);
     srf_launch_fn srf;
     int table_kind; // cgd::kTableNone / kTableSpline / kTableErfc: which table the engine must pass
 };

@@ -624,7 +624,8 @@ cudaError_t launch_srf(const cg_scheme_desc &desc, const double *dev_table, int 
 }
 
 // table of launchers for one functor: the ten instantiated (mode, what) combinations, in fp64 and fp32
-// (the two quadrupole combinations exist in fp64 only)
+// (the two quadrupole combinations exist in fp64 only), and the all-pairs kernel's (allpairs_kernel.cuh, which the
+// instantiating translation units include)
 #define CGB_PAIR_ROW(FUNCTOR, YUK, T)                                                                                          \
     {launch_pair<FUNCTOR, YUK, combo(0).mode, combo(0).what, T>, launch_pair<FUNCTOR, YUK, combo(1).mode, combo(1).what, T>,   \
      launch_pair<FUNCTOR, YUK, combo(2).mode, combo(2).what, T>, launch_pair<FUNCTOR, YUK, combo(3).mode, combo(3).what, T>,   \
@@ -639,16 +640,16 @@ cudaError_t launch_srf(const cg_scheme_desc &desc, const double *dev_table, int 
 #define CGB_DEFINE_FUNCTOR_ENTRY_ION(NAME, FUNCTOR)                                                                        \
     namespace cgb {                                                                                                       \
     const FunctorEntry *NAME() {                                                                                          \
-        static const FunctorEntry e = {CGB_PAIR_ROW_ION(FUNCTOR, double), CGB_PAIR_ROW_ION(FUNCTOR, float), launch_srf<FUNCTOR>, \
-                                       FUNCTOR::kTable};                                                                 \
+        static const FunctorEntry e = {CGB_PAIR_ROW_ION(FUNCTOR, double), CGB_PAIR_ROW_ION(FUNCTOR, float), CGB_AP_ROW_ION(FUNCTOR), \
+                                       ap_dims, launch_srf<FUNCTOR>, FUNCTOR::kTable};                                   \
         return &e;                                                                                                        \
     }                                                                                                                     \
     }
 #define CGB_DEFINE_FUNCTOR_ENTRY(NAME, FUNCTOR, YUK)                                                                  \
     namespace cgb {                                                                                                   \
     const FunctorEntry *NAME() {                                                                                      \
-        static const FunctorEntry e = {CGB_PAIR_ROW(FUNCTOR, YUK, double), CGB_PAIR_ROW(FUNCTOR, YUK, float), launch_srf<FUNCTOR>, \
-                                       FUNCTOR::kTable};                                                             \
+        static const FunctorEntry e = {CGB_PAIR_ROW(FUNCTOR, YUK, double), CGB_PAIR_ROW(FUNCTOR, YUK, float), CGB_AP_ROW(FUNCTOR, YUK), \
+                                       ap_dims, launch_srf<FUNCTOR>, FUNCTOR::kTable};                               \
         return &e;                                                                                                    \
     }                                                                                                                 \
     }
