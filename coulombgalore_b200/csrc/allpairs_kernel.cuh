@@ -19,6 +19,8 @@
 //     pair) instead of L2.  The exact reference gate r2 < cutoff^2 is applied in fp64.
 // Open boundaries only (the engine routes periodic systems to the cell-list kernel), fp64 arithmetic, no quadrupoles.
 #pragma once
+#include <cstdio>
+
 #include "pair_kernel.cuh"
 
 namespace cgb {
@@ -49,17 +51,40 @@ __device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void *src, unsi
                  : "memory");
 }
 
+// launch shape of the all-pairs kernel (tuning builds: -DCG_AP_WARPS_ION=.. etc.); defaults = the cell-list kernel's
+#ifndef CG_AP_WARPS_ION
+#define CG_AP_WARPS_ION CG_WARPS_ION
+#endif
+#ifndef CG_AP_MINB_ION
+#define CG_AP_MINB_ION CG_MINB_ION
+#endif
+#ifndef CG_AP_WARPS_DIP
+#define CG_AP_WARPS_DIP CG_WARPS_DIP
+#endif
+#ifndef CG_AP_MINB_DIP
+#define CG_AP_MINB_DIP CG_MINB_DIP
+#endif
+#ifndef CG_AP_SETS
+#define CG_AP_SETS 2
+#endif
+#ifndef CG_AP_ILP_ION
+#define CG_AP_ILP_ION CG_ILP
+#endif
+template <int MODE> constexpr int ap_warps() { return MODE == cgd::kModeIon ? CG_AP_WARPS_ION : CG_AP_WARPS_DIP; }
+template <int MODE> constexpr int ap_minb() { return MODE == cgd::kModeIon ? CG_AP_MINB_ION : CG_AP_MINB_DIP; }
+template <int MODE> constexpr int ap_ilp() { return MODE == cgd::kModeIon ? CG_AP_ILP_ION : pairs_in_flight<MODE>(); }
+
 constexpr int kApStride = kApTile + kDummies; // doubles per SoA component and stage: the tile, then the dummy entries
 template <int MODE> constexpr int ap_arrays() { return MODE == cgd::kModeIon ? 4 : 7; }
 
 template <class F, bool YUK, int MODE, int WHAT>
-__global__ void __launch_bounds__(32 * warps_per_cta<MODE>(), min_blocks_per_sm<MODE>())
+__global__ void __launch_bounds__(32 * ap_warps<MODE>(), ap_minb<MODE>())
 allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f, const double *__restrict__ dev_table, int table_doubles) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int kWarps = warps_per_cta<MODE>();
+    constexpr int kWarps = ap_warps<MODE>();
     constexpr int kArr = ap_arrays<MODE>();
-    constexpr int kIlp = pairs_in_flight<MODE>();
-    constexpr int kSets = 2;
+    constexpr int kIlp = ap_ilp<MODE>();
+    constexpr int kSets = CG_AP_SETS;
     constexpr int kNS = F::kSchemes;
     typedef double T;
     typedef cgd::Vec3T<T> V3;
@@ -77,9 +102,22 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
     unsigned long long *s_bar = reinterpret_cast<unsigned long long *>(smem_raw + o_bars);
     int *s_wmax = reinterpret_cast<int *>(s_bar + 2);
 
-    const int slice = blockIdx.y;
-    const int jbeg = slice * p.slice_len, jend = min(p.n, jbeg + p.slice_len);
-    const int ntiles = (jend - jbeg + kApTile - 1) / kApTile;
+#ifdef CG_AP_PROF
+    long long apt[8];
+    int apk = 0;
+#define AP_MARK() apt[apk++] = clock64()
+#else
+#define AP_MARK()
+#endif
+    AP_MARK();
+    // slice s of the j-range = the batches of 32 consecutive particles s, s + S, s + 2 S, ...: every slice samples the whole
+    // system, so every (i-block, slice) item sees the same density of neighbours (contiguous slices of a spatially ordered
+    // input would give the items next to the diagonal several times the work of the others)
+    const int slice = blockIdx.y, S = p.n_slices;
+    const int nbatch = (p.n + 31) >> 5;                               // batches of the system
+    const int nbs = slice < nbatch ? (nbatch - 1 - slice) / S + 1 : 0; // batches of this slice
+    constexpr int kTileBatches = kApTile / 32;
+    const int ntiles = (nbs + kTileBatches - 1) / kTileBatches;
     const double *src[7] = {p.x, p.y, p.z, p.q, p.mx, p.my, p.mz};
     const unsigned present = (p.x ? 1u : 0u) | (p.y ? 2u : 0u) | (p.z ? 4u : 0u) | (p.q ? 8u : 0u) | (p.mx ? 16u : 0u) | (p.my ? 32u : 0u) |
                              (p.mz ? 64u : 0u);
@@ -109,33 +147,44 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
     }
     __syncthreads();
 
-    // issue tile t into stage t & 1 (one thread): bulk copies of every SoA array, the odd last element by a plain store
+    // issue tile t into stage t & 1 (warp 0): one bulk copy per batch and SoA array (256 bytes; the system's last batch may be
+    // shorter, and an odd last element is stored by hand: the copies move 16-byte granules).  Lane 0 arms the barrier with the
+    // byte count of the whole tile, then the lanes share the copies.
     auto issue = [&](int t) {
-        const int s = t & 1, j0 = jbeg + t * kApTile, cnt = min(kApTile, jend - j0), ce = cnt & ~1;
+        const int s = t & 1, k0 = t * kTileBatches, nbt = min(kTileBatches, nbs - k0);
         double *st = s_stage + (size_t)s * kArr * kApStride;
-        s_wmax[s] = 0;
-        int narr = 0;
-#pragma unroll
-        for (int c = 0; c < kArr; c++)
-            if (src[c]) {
-                narr++;
-                if (cnt & 1) st[c * kApStride + cnt - 1] = src[c][j0 + cnt - 1];
-            }
         const unsigned bar = smem_addr(s_bar + s);
-        mbar_arrive_expect_tx(bar, (unsigned)(ce * 8 * narr));
-        if (ce > 0) {
+        const int narr = __popc(present & ((1u << kArr) - 1u));
+        if (lane == 0) {
+            s_wmax[s] = 0;
+            const int last = slice + (k0 + nbt - 1) * S;                     // the tile's last batch
+            const int cnt_last = min(32, p.n - 32 * last), ce_last = cnt_last & ~1;
+            if (cnt_last & 1) {
 #pragma unroll
-            for (int c = 0; c < kArr; c++)
-                if (src[c]) tma_bulk_g2s(smem_addr(st + c * kApStride), src[c] + j0, (unsigned)(ce * 8), bar);
+                for (int c = 0; c < kArr; c++)
+                    if ((present >> c) & 1u) st[c * kApStride + 32 * (nbt - 1) + cnt_last - 1] = src[c][32 * last + cnt_last - 1];
+            }
+            mbar_arrive_expect_tx(bar, (unsigned)((32 * (nbt - 1) + ce_last) * 8 * narr));
+        }
+        __syncwarp();
+        for (int w = lane; w < nbt * kArr; w += 32) {
+            const int k = w / kArr, c = w - k * kArr;
+            if (!((present >> c) & 1u)) continue;
+            const int b = slice + (k0 + k) * S;
+            const int ce = min(32, p.n - 32 * b) & ~1;
+            const double *g = c == 0 ? p.x : c == 1 ? p.y : c == 2 ? p.z : c == 3 ? p.q : c == 4 ? p.mx : c == 5 ? p.my : p.mz;
+            if (ce > 0) tma_bulk_g2s(smem_addr(st + c * kApStride + 32 * k), g + 32 * b, (unsigned)(ce * 8), bar);
         }
     };
-    if (tid == 0) {
+    if (warp == 0 && ntiles > 0) {
         issue(0);
         if (ntiles > 1) issue(1);
     }
 
     // the lane's own particle
-    const int ig = blockIdx.x * kWarps + warp;
+    // i-groups are dealt to the CTAs round robin (warp w of i-block b: group b + w * i-blocks): an open system has half the
+    // neighbours at its faces, and every SM should get the same mix of light and heavy groups
+    const int ig = blockIdx.x + warp * gridDim.x;
     const int i = ig * 32 + lane;
     const bool act = i < p.n;
     const int il = act ? i : 0;
@@ -155,16 +204,18 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
     unsigned int npairs = 0;
 
     for (int t = 0; t < ntiles; t++) {
-        const int s = t & 1, j0 = jbeg + t * kApTile, cnt = min(kApTile, jend - j0);
+        const int s = t & 1, k0 = t * kTileBatches, nbt = min(kTileBatches, nbs - k0);
         const double *st = s_stage + (size_t)s * kArr * kApStride;
         float4 *c32 = s_f32 + s * kApTile;
+        if (t == 0) AP_MARK();
         mbar_wait(smem_addr(s_bar + s), (unsigned)((t >> 1) & 1));
+        if (t == 0) AP_MARK();
         // ---- fp32 copy of the tile for the prefilter, and the largest |c'|^2 of the tile (for the margin) ----
         {
             float wm = 0.0f;
-            for (int k = tid; k < ((cnt + 31) & ~31); k += 32 * kWarps) {
+            for (int k = tid; k < 32 * nbt; k += 32 * kWarps) {
                 float4 v = make_float4(0.0f, 0.0f, 0.0f, INFINITY);
-                if (k < cnt) {
+                if (32 * (slice + (k0 + (k >> 5)) * S) + (k & 31) < p.n) { // only the system's last batch can be short
                     v.x = (float)(st[k] - Ox);
                     v.y = (float)(st[kApStride + k] - Oy);
                     v.z = (float)(st[2 * kApStride + k] - Oz);
@@ -177,6 +228,7 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
             if (lane == 0) atomicMax(s_wmax + s, __float_as_int(wm));
         }
         __syncthreads();
+        if (t == 0) AP_MARK();
         // ---- PHASE 1 ----
         // Error budget of the fp32 test against the exact r2 < rc2 (S = |x'_i| + max |c'|): both positions rounded to fp32
         // 2^-23 S^2, |c'|^2 in three roundings 3 2^-24 S^2, three FFMA partial sums <= S^2 each 3 2^-24 S^2, the rounding of
@@ -186,9 +238,8 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
             const float S = (xnorm + sqrtf(__int_as_float(s_wmax[s]))) * 1.0001f;
             thr = thr0 + 1.5f * 5.9604645e-8f * (10.0f * S * S + fabsf(thr0) + (float)xn2);
         }
-        const int nb = (cnt + 31) >> 5;
         int qn = 0, total = 0;
-        for (int b = 0; b < nb; b++) {
+        for (int b = 0; b < nbt; b++) {
             const float4 *c4 = c32 + 32 * b;
             unsigned m = 0u;
 #pragma unroll
@@ -199,7 +250,7 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
                 d = fmaf(az, v.z, d);
                 m |= d < thr ? (1u << c) : 0u;
             }
-            const unsigned rel_self = (unsigned)(i - (j0 + 32 * b)); // the lane's own particle is not a neighbour
+            const unsigned rel_self = (unsigned)(i - 32 * (slice + (k0 + b) * S)); // the lane's own particle is not a neighbour
             if (rel_self < 32u) m &= ~(1u << rel_self);
             if (m != 0u) hits[(qn++) * 32] = make_uint2(m, (unsigned)(32 * b));
             total += __popc(m);
@@ -207,6 +258,7 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
         hits[qn * 32] = make_uint2(0xffffffffu, (unsigned)kApTile); // sentinel: the dummy entries behind the tile
         const int rounds = (__reduce_max_sync(full, total) + kSets * kIlp - 1) / (kSets * kIlp);
         __syncwarp();
+        if (t == 0) AP_MARK();
         // ---- PHASE 2 ----
         if (rounds > 0) {
             const unsigned list = smem_addr(hits);
@@ -270,8 +322,10 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
                 }
             }
         }
+        if (t == 0) AP_MARK();
         __syncthreads(); // every warp is done with stage s: refill it
-        if (tid == 0 && t + 2 < ntiles) issue(t + 2);
+        if (t == 0) AP_MARK();
+        if (warp == 0 && t + 2 < ntiles) issue(t + 2);
     }
 
     // ---- per-particle partial outputs of this slice, one reduction per (i-group, slice) for the scalars ----
@@ -312,6 +366,13 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
         for (int off = 16; off > 0; off >>= 1) u += __shfl_down_sync(full, u, off);
         if (lane == 0) o_energy[item] = u;
     }
+#ifdef CG_AP_PROF
+    AP_MARK();
+    if (lane == 0 && (warp == 0 || warp == 5) && (blockIdx.x == 0 || blockIdx.x == 5) && blockIdx.y < 2)
+        printf("ap prof cta (%d,%d) warp %d: init %lld wait %lld convert %lld phase1 %lld phase2 %lld sync %lld out %lld total %lld cycles\n",
+               blockIdx.x, blockIdx.y, warp, apt[1] - apt[0], apt[2] - apt[1], apt[3] - apt[2], apt[4] - apt[3], apt[5] - apt[4],
+               apt[6] - apt[5], apt[7] - apt[6], apt[7] - apt[0]);
+#endif
 }
 
 template <class F, bool YUK, int MODE, int WHAT>
@@ -319,7 +380,7 @@ cudaError_t launch_allpairs(const APParams &p, const cg_scheme_desc &desc, const
                             cudaStream_t stream) {
     const F f(desc);
     if (F::kTable == cgd::kTableNone) table_doubles = 0;
-    constexpr int warps = warps_per_cta<MODE>();
+    constexpr int warps = ap_warps<MODE>();
     const ApLayout L = ap_layout(table_doubles, ap_arrays<MODE>(), warps);
     auto kern = allpairs_kernel<F, YUK, MODE, WHAT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -332,8 +393,8 @@ cudaError_t launch_allpairs(const APParams &p, const cg_scheme_desc &desc, const
 }
 
 template <int MODE> void ap_dims_of(int *warps, int *ctas_per_sm) {
-    *warps = warps_per_cta<MODE>();
-    *ctas_per_sm = min_blocks_per_sm<MODE>();
+    *warps = ap_warps<MODE>();
+    *ctas_per_sm = ap_minb<MODE>();
 }
 inline void ap_dims(int ci, int *warps, int *ctas_per_sm) {
     const int mode = combo(ci).mode;

@@ -67,7 +67,7 @@ struct APParams {
     int n;                         // particles
     const double *x, *y, *z, *q;   // SoA inputs, 16-byte aligned (q may be null: no charges)
     const double *mx, *my, *mz;    // dipole moments (null in ion mode)
-    int n_slices, slice_len;       // j-slices and their length (a multiple of 32; the last one may be shorter)
+    int n_slices;                  // j-slices: slice s = the batches of 32 consecutive particles s, s + n_slices, ...
     double box[3];                 // periodic box (minimum image, box >= 2 cut-offs per dimension); 0 = open
     double rc2;                    // exact gate: r2 < cutoff^2 (strict)
     float rc2f;                    // the same for the fp32 prefilter (before the margin); +inf for an unbounded cut-off
