@@ -514,6 +514,13 @@ struct EpilogueArgs {
     const double *part[9];
     double *out[9];
     long long len[9];
+    // tail split of the pair kernel (kparams.cuh: tail_plan): partial outputs of the row slices of the last groups
+    int tail_wave, ntail;
+    const int2 *groups;
+    const int *orig;
+    const double *tail_part[12];
+    double *tail_dst[12];
+    int tail_width[12];
 };
 __global__ void __launch_bounds__(1024) epilogue_kernel(const int *counts, int count_index, int split, const unsigned long long *item_pairs,
                                                         int *work_counter, const __grid_constant__ EpilogueArgs a) {
@@ -530,12 +537,33 @@ __global__ void __launch_bounds__(1024) epilogue_kernel(const int *counts, int c
                 a.out[c][k] = sum;
             }
         }
+        if (a.tail_wave > 0 && a.ntail > 0) { // one warp per group of the tail: lane = particle, slices summed in order
+            int n_whole, ts;
+            const int ng = counts[count_index];
+            cgb::tail_plan(ng, a.tail_wave, n_whole, ts);
+            if (ts > 1) {
+                const int lane = threadIdx.x & 31, nwarps = (gridDim.x - a.nred) * 32;
+                for (int t = (blockIdx.x - a.nred) * 32 + (threadIdx.x >> 5); t < ng - n_whole; t += nwarps) {
+                    const int2 grp = a.groups[n_whole + t];
+                    if (lane >= grp.y) continue;
+                    const size_t o = (size_t)a.orig[grp.x + lane];
+                    for (int c = 0; c < a.ntail; c++) {
+                        const int w = a.tail_width[c];
+                        for (int e = 0; e < w; e++) {
+                            double sum = 0.0;
+                            for (int sl = 0; sl < ts; sl++) sum += a.tail_part[c][((size_t)(t * ts + sl) * 32 + lane) * w + e];
+                            a.tail_dst[c][o * w + e] = sum;
+                        }
+                    }
+                }
+            }
+        }
         return;
     }
     const double *item_energy = a.item_energy[blockIdx.x];
     double *scalars = a.scalars[blockIdx.x];
     if (!scalars) return;
-    const int items = counts[count_index] * split;
+    const int items = a.tail_wave > 0 ? cgb::tail_items(counts[count_index], a.tail_wave) : counts[count_index] * split;
     double e = 0.0;
     unsigned long long c = 0;
     int k = threadIdx.x;
@@ -1020,6 +1048,7 @@ struct cg_handle {
     DevBuf<double> out_force, out_field, out_pot, part_force, part_field, part_pot, item_energy, scalars;
     DevBuf<unsigned long long> item_pairs;
     DevBuf<int> work_counter;    // next work item of the persistent pair kernel
+    DevBuf<double> tail_buf;     // tail split of the pair kernel: partial outputs of the last round's row slices
     DevBuf<int> ap_counts;       // all-pairs path: the counts the epilogue kernel reads (written by allpairs_kernel)
     int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
     int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
@@ -1237,6 +1266,8 @@ int cg_destroy(cg_handle *h) {
     h->scalars.release();
     h->item_pairs.release();
     h->work_counter.release();
+    h->tail_buf.release();
+    h->ap_counts.release();
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_counts_async) cudaFreeHost(h->h_counts_async);
     if (h->counts_ev) cudaEventDestroy(h->counts_ev);
@@ -1940,7 +1971,13 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     const int wave = device_sms * cgb::kMaxWarpsPerSm; // resident warps of the machine (pair_kernel.cuh)
     if (ng > 0 && ng < wave) split = std::max(1, std::min(64, wave / ng));
     if (split_env > 0) split = std::min(64, split_env);
-    const int items = ng_bound * split; // launch bound; the kernel stops at counts[1] * split
+    // tail split (kparams.cuh: tail_plan): with whole groups as items the persistent grid ends in a partial round that takes
+    // as long as a full one (an 1/8 shard of config 2: 4056 groups on 1776 warps, three rounds for 2.3 rounds of work); the
+    // groups of that round are cut into row slices instead.  CG_TAIL=0 switches it off.
+    const char *tail_e = std::getenv("CG_TAIL"); // read per evaluation: the tests compare both
+    const bool tail_env = !tail_e || std::atoi(tail_e) != 0;
+    const bool tail = tail_env && split == 1 && mode != CG_MODE_MULTIPOLE_QUAD;
+    const int items = tail ? ng_bound + wave : ng_bound * split; // launch bound; the kernel stops at the device count
 
     // smallest instantiated (mode, what) superset
     int ci = -1;
@@ -2046,6 +2083,36 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
         kp.potential = o_pot;
     }
     (void)cwhat;
+    // tail buffers: [scheme][force, field, potential], wave * 32 slots each
+    struct Tail {
+        const double *part;
+        double *dst;
+        int width;
+    } tails[12];
+    int ntail = 0;
+    if (tail) {
+        kp.tail_wave = wave;
+        const int nsch = ma ? ma->n : 1;
+        const size_t slots = (size_t)wave * 32;
+        CG_CUDA(h, h->tail_buf.ensure(slots * 7 * (size_t)nsch));
+        for (int k = 0; k < nsch; k++) {
+            double *base = h->tail_buf.p + slots * 7 * (size_t)k;
+            double *of = (what & CG_FORCE) ? (ma ? ma->force[k] : d_force) : nullptr, *oe = (what & CG_FIELD) ? (ma ? ma->field[k] : d_field) : nullptr,
+                   *op = (what & CG_POTENTIAL) ? (ma ? ma->pot[k] : d_pot) : nullptr;
+            if (of) {
+                kp.tail_out[k][0] = base;
+                tails[ntail++] = {base, of, 3};
+            }
+            if (oe) {
+                kp.tail_out[k][1] = base + slots * 3;
+                tails[ntail++] = {base + slots * 3, oe, 3};
+            }
+            if (op) {
+                kp.tail_out[k][2] = base + slots * 6;
+                tails[ntail++] = {base + slots * 6, op, 1};
+            }
+        }
+    }
     // partial outputs summed by the epilogue: {per-slice buffer, destination, length}
     struct Comb {
         const double *part;
@@ -2162,6 +2229,20 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
                 total = std::max(total, comb[c].len);
                 ea.ncomb = c + 1;
             }
+        if (tail && ntail > 0 && items > 0) {
+            ea.tail_wave = wave;
+            ea.ntail = ntail;
+            ea.groups = s->groups[gt].p;
+            ea.orig = s->orig.p;
+            for (int c = 0; c < ntail; c++) {
+                ea.tail_part[c] = tails[c].part;
+                ea.tail_dst[c] = tails[c].dst;
+                ea.tail_width[c] = tails[c].width;
+            }
+            total = std::max(total, 16LL * wave); // half a wave of groups at most, one warp each
+        } else if (tail) {
+            ea.tail_wave = wave; // the item count of the scalar reduction follows the same plan
+        }
         const unsigned blocks = (unsigned)ea.nred + (unsigned)std::min<long long>((total + 1023) / 1024, 4LL * device_sms);
         epilogue_kernel<<<blocks, 1024, 0, st>>>(counts, gt ? 3 : 1, split, h->item_pairs.p, h->work_counter.p, ea);
         launches++;

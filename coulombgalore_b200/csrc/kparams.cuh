@@ -56,7 +56,31 @@ struct KParams {
     double *force_k[3], *field_k[3], *potential_k[3], *item_energy_k[3];
     double *item_energy;              // [items] sum_j u_ij over the item's pairs (not yet halved)
     unsigned long long *item_pairs;   // [items]
+    // Tail split (split == 1 only; 0 = off): tail_wave = resident warps of the machine.  The groups beyond the last full
+    // round of whole-group items are cut into `ts` row slices each (tail_plan), so that the last round of the persistent
+    // grid is a round of short items; their partial outputs go to tail_out[scheme][force, field, potential]
+    // (slot (item - n_whole) * 32 + lane: at most tail_wave * 32 slots) and are summed in slice order by the epilogue kernel.
+    int tail_wave;
+    double *tail_out[4][3];
 };
+constexpr int kMaxTailSplit = 4;
+// groups evaluated whole, and the number of row slices of each of the others
+__host__ __device__ inline void tail_plan(int ng, int wave, int &n_whole, int &ts) {
+    n_whole = ng;
+    ts = 1;
+    if (wave <= 0 || ng <= wave) return;
+    const int whole = (ng / wave) * wave, rem = ng - whole;
+    if (rem == 0) return;
+    const int t = wave / rem < kMaxTailSplit ? wave / rem : kMaxTailSplit;
+    if (t < 2) return;
+    n_whole = whole;
+    ts = t;
+}
+__host__ __device__ inline int tail_items(int ng, int wave) {
+    int n_whole, ts;
+    tail_plan(ng, wave, n_whole, ts);
+    return n_whole + (ng - n_whole) * ts;
+}
 
 // All-pairs path for small systems (allpairs_kernel.cuh): no sort, no cell list -- the kernel reads the caller's SoA arrays
 // as they are.  Work item = (block of i-groups, j-slice); every CTA streams its j-slice through shared memory in tiles

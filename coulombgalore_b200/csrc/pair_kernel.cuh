@@ -193,7 +193,13 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     uint2 *hits = reinterpret_cast<uint2 *>(smem_raw + table_bytes) + (size_t)warp * (size_t)(slots + 1) * 32 + lane;
     // `items` is only the launch bound (the sync-free path does not know the group count on the host); CTAs beyond the
     // real work leave before they touch anything.  After an overflow the cell table points past the sorted arrays.
-    const int real_items = p.counts[2] != 0 ? 0 : min(items, p.counts[p.count_index] * p.split);
+    // tail split (kparams.cuh: tail_plan; launches with split == 1 only): the groups beyond `n_whole` become `tsplit` items each
+    int real_items;
+    {
+        int n_whole = p.counts[p.count_index], tsplit = 1;
+        if (p.tail_wave > 0 && p.split == 1) tail_plan(p.counts[p.count_index], p.tail_wave, n_whole, tsplit);
+        real_items = p.counts[2] != 0 ? 0 : min(items, p.split > 1 ? p.counts[p.count_index] * p.split : n_whole + (p.counts[p.count_index] - n_whole) * tsplit);
+    }
     if ((int)blockIdx.x * kWarps >= real_items) return;
     const double *tab = nullptr;
     if constexpr (F::kTable != cgd::kTableNone) { // Splined: the four Andrea tables; erfc family: the erfc/exp table
@@ -227,7 +233,21 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         if (lane == 0) item = atomicAdd(p.work_counter, 1);
         item = __shfl_sync(full, item, 0);
         if (item >= real_items) break;
-        const int g = p.group_begin + item / split, slice = item - (item / split) * split;
+        int g = p.group_begin + item / split;
+        int slice = item - (item / split) * split;
+        // tail items (launches with split == 1 only): row slice `slice` of `rs` of a group of the last round -- every rs-th
+        // row of the walk, where a j-split slice takes every split-th batch of every row
+        int tail = 1; // (slot of the item's partial outputs) << 3 | row slices of the group (1: a whole group)
+        if (p.tail_wave > 0 && split == 1) {
+            int n_whole, tsplit;
+            tail_plan(p.counts[p.count_index], p.tail_wave, n_whole, tsplit);
+            if (item >= n_whole && tsplit > 1) {
+                const int r = item - n_whole;
+                g = p.group_begin + n_whole + r / tsplit;
+                slice = r - (r / tsplit) * tsplit;
+                tail = (r << 3) | tsplit;
+            }
+        }
         const int2 grp = p.groups[g];
         // the lane's own particle: sorted entry grp.x + lane
         const bool act = lane < grp.y;
@@ -315,11 +335,13 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
         auto next_batch = [&](int &j0, int &n) -> bool {
             while (cur_j >= cur_end) { // next run
                 if (have == 0) {       // next 32 rows
-                    if (row_next >= nrows) return false;
-                    const int rr = row_next + lane;
+                    const int rs = tail & 7, ro = rs > 1 ? slice : 0;
+                    if (row_next * rs + ro >= nrows) return false;
+                    const int rr = (row_next + lane) * rs + ro;
+                    const bool mine = rr < nrows;
                     row_next += 32;
                     jb = je = 0;
-                    if (rr < nrows) {
+                    if (mine) {
                         const int rp = (int)(((unsigned)rr * (unsigned)rstride) % (unsigned)nrows); // the rr-th row of the walk
                         const int rzi = rp / nyr;
                         const int ry = cy0 + (rp - rzi * nyr), rz = cz0 + rzi;
@@ -535,9 +557,15 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
             double *o_force = k == 0 ? p.force : p.force_k[k > 0 ? k - 1 : 0], *o_field = k == 0 ? p.field : p.field_k[k > 0 ? k - 1 : 0];
             double *o_pot = k == 0 ? p.potential : p.potential_k[k > 0 ? k - 1 : 0];
             double *o_energy = k == 0 ? p.item_energy : p.item_energy_k[k > 0 ? k - 1 : 0];
+            if (tail > 1) { // a tail item's partial outputs
+                o_force = p.tail_out[k][0];
+                o_field = p.tail_out[k][1];
+                o_pot = p.tail_out[k][2];
+            }
             double u = 0.0;
             if (act) {
-                const size_t o = (size_t)slice * (size_t)p.n + (size_t)p.orig[i];
+                // tail items write slot (item - n_whole) * 32 + lane of the tail buffers, the others their particle's entry
+                const size_t o = tail > 1 ? (size_t)(tail >> 3) * 32 + (size_t)lane : (size_t)slice * (size_t)p.n + (size_t)p.orig[i];
                 if constexpr ((WHAT & cgd::kWhatForce) != 0) {
                     if (o_force) {
                         o_force[3 * o + 0] = acc64[k].Fx;

@@ -27,6 +27,8 @@ def fused_config2(dev, st):
     evs = [cg.BatchedEvaluator(cg.Wolf(12, 0.25)), cg.BatchedEvaluator(cg.Fennell(12, 0.25))]
     for ev in evs:
         ev.set_stream(st.cuda_stream)
+    if os.environ.get("CG_SHARD"):  # emulate one rank of an R-rank run
+        evs[0].set_shard(*[int(v) for v in os.environ["CG_SHARD"].split(",")])
     evs[1].share_system(evs[0])
     arr = [torch.empty(N, dtype=torch.float64, device=dev) for _ in range(4)]
     evs[0].generate_lattice_device(n, 3.0, 1002, arr[0], arr[1], arr[2], arr[3])
