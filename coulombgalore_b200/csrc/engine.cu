@@ -973,7 +973,15 @@ __global__ void halo_pull_kernel(const __grid_constant__ HaloPull g) {
     const double *s = reinterpret_cast<const double *>(g.block[r] + 256) + ((long long)g.rank * g.narrays + a) * g.cap[r];
     double *d = g.dst[a] + off;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) d[k] = s[k];
+    long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; k + 3 * stride < n; k += 4 * stride) { // four NVLink reads in flight per thread
+        const double v0 = s[k], v1 = s[k + stride], v2 = s[k + 2 * stride], v3 = s[k + 3 * stride];
+        d[k] = v0;
+        d[k + stride] = v1;
+        d[k + 2 * stride] = v2;
+        d[k + 3 * stride] = v3;
+    }
+    for (; k < n; k += stride) d[k] = s[k];
 }
 
 template <class T> struct DevBuf {
@@ -1597,7 +1605,7 @@ static int sort_system(cg_handle *h, bool need_mu, bool need_quad, bool need32, 
     (*launches_out)++;
     // small grids (a shard of a 10^6-particle system, a few thousand particles): the one-CTA kernel scans the cells too; large
     // grids: a many-CTA scan first (measured at 157 464 cells: 12 us against 40 us for the single CTA)
-    const int cells_done = ncell > 32768 ? 1 : 0;
+    const int cells_done = ncell > 100000 ? 1 : 0; // one CTA scans up to 25 tiles (~10 us) faster than three more launches do
     if (cells_done) {
         CG_CUDA(h, h->scan_tmp.ensure(4 * ((size_t)ncell / kWideTile + 8) + 64));
         CG_CUDA(h, exclusive_scan(hist, h->cell_start.p, ncell, h->scan_tmp.p, st, launches_out));
@@ -2173,6 +2181,18 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     } else if (fe->table_kind == cgd::kTableErfc) {
         dev_table = h->d_erfc_table.p;
         table_doubles = 2 * cgd::kErfcTableEntries;
+        kp.erfc_rep = 1;
+        kp.erfc_kmax = cgd::kErfcTableEntries - 1;
+        // schemes whose erfc argument is eta q <= eta (ErfcFamilySrf, ErfcMultiSrf; not the screened Ewald functor): eight
+        // bank-interleaved copies of the entries up to eta, when they fit beside the hit lists (eta <= 4)
+        const char *rep_e = std::getenv("CG_ERFC_REP");
+        const bool bounded = ma || (h->functor != kFnEwaldScreened);
+        const int k_used = std::min((int)cgd::kErfcTableEntries, (int)(D.eta * cgd::kErfcTableInvStep) + 3);
+        if (bounded && h->precision == CG_FP64 && D.eta > 0.0 && k_used * 128 <= 64 * 1024 && !(rep_e && std::atoi(rep_e) == 0)) {
+            kp.erfc_rep = 8;
+            kp.erfc_kmax = k_used - 1;
+            table_doubles = 16 * k_used;
+        }
     }
 #ifdef CG_KPROF
     static const bool kprof = std::getenv("CG_KPROF") != nullptr;

@@ -62,6 +62,8 @@ struct KParams {
     // (slot (item - n_whole) * 32 + lane: at most tail_wave * 32 slots) and are summed in slice order by the epilogue kernel.
     int tail_wave;
     double *tail_out[4][3];
+    // erfc table in shared memory (specfun.hpp: ErfcTabRep): copies (1 or 8) and the last entry they hold
+    int erfc_rep, erfc_kmax;
 };
 constexpr int kMaxTailSplit = 4;
 // groups evaluated whole, and the number of row slices of each of the others

@@ -203,10 +203,27 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
     if ((int)blockIdx.x * kWarps >= real_items) return;
     const double *tab = nullptr;
     if constexpr (F::kTable != cgd::kTableNone) { // Splined: the four Andrea tables; erfc family: the erfc/exp table
-        for (int k = threadIdx.x; k < table_doubles; k += 32 * kWarps) s_table[k] = dev_table[k];
+        if (F::kTable == cgd::kTableErfc && p.erfc_rep > 1) { // eight interleaved copies of the entries [0, erfc_kmax]
+            for (int k = threadIdx.x; k < 8 * (p.erfc_kmax + 1); k += 32 * kWarps) {
+                s_table[2 * k] = dev_table[2 * (k >> 3)];
+                s_table[2 * k + 1] = dev_table[2 * (k >> 3) + 1];
+            }
+        } else {
+            for (int k = threadIdx.x; k < table_doubles; k += 32 * kWarps) s_table[k] = dev_table[k];
+        }
         __syncthreads();
         tab = s_table;
     }
+    // what the functors get as their table: the pointer, or for the erfc family in fp64 the (replicated) table's addressing
+    auto tabx = [&] {
+        if constexpr (F::kTable == cgd::kTableErfc && std::is_same<T, double>::value) {
+            const unsigned base = smem_addr(s_table);
+            return p.erfc_rep > 1 ? cgd::ErfcTabRep{base + 16u * (threadIdx.x & 7u), 128u, (unsigned)p.erfc_kmax}
+                                  : cgd::ErfcTabRep{base, 16u, (unsigned)p.erfc_kmax};
+        } else {
+            return tab;
+        }
+    }();
     const unsigned full = 0xffffffffu;
     const int split = p.split;
     const int dummy0 = min(p.counts[0], p.cap_sorted - kDummies); // first of the far-away dummy entries
@@ -492,13 +509,13 @@ pair_kernel(const __grid_constant__ KParams p, const __grid_constant__ F f, cons
                         V3 muj = {T(0), T(0), T(0)};
                         if constexpr (MODE != cgd::kModeIon) muj = {(T)mm[s][u].x, (T)mm[s][u].y, (T)mm[s][u].z};
                         if constexpr (kNS > 1) {
-                            cgd::pair_accumulate_multi<F, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, acc, pass);
+                            cgd::pair_accumulate_multi<F, WHAT, T>(f, p.core, tabx, d, (T)r2c, zi, (T)pp[s][u].w, acc, pass);
                         } else if constexpr (MODE == cgd::kModeMultipoleQuad) {
                             const double4 qa = ldg256<kGather>(p.quad + 2 * jj[s][u]), qb = ldg256<kGather>(p.quad + 2 * jj[s][u] + 1);
                             const cgd::QuadT<T> quadj = {(T)qa.x, (T)qa.y, (T)qa.z, (T)qa.w, (T)qb.x, (T)qb.y, (T)qb.z};
-                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc[0], pass, &quadi, &quadj);
+                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tabx, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc[0], pass, &quadi, &quadj);
                         } else {
-                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tab, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc[0], pass);
+                            cgd::pair_accumulate<F, YUK, MODE, WHAT, T>(f, p.core, tabx, d, (T)r2c, zi, (T)pp[s][u].w, mui, muj, acc[0], pass);
                         }
                     }
                 };

@@ -41,6 +41,14 @@ struct ErfcCtx {
     unsigned tab;
     double c[10];
 };
+// The table as the cell-list pair kernel addresses it: entry k at shared address tab + stride k, k clamped to kmax.  Eight
+// interleaved copies (stride 128, tab = base + 16 (lane & 7)) put the eight lanes of a quarter-warp on eight different
+// 16-byte bank groups whatever their arguments: four wavefronts per warp-wide lookup where a single copy costs about nine
+// (random bank conflicts).  Schemes whose argument is eta q <= eta use it (the copies hold the entries up to eta only); an
+// index beyond kmax can only belong to a pair that failed the cut-off gate, whose value is discarded.
+struct ErfcTabRep {
+    unsigned tab, stride, kmax;
+};
 
 #ifdef __CUDA_ARCH__
 // 1/sqrt(x), x > 0 normal: MUFU.RSQ64H seed (2^-22) + one third-order (Halley) step -> full double precision
@@ -54,16 +62,17 @@ __device__ __forceinline__ double rsqrt_device(double x) {
 // ec = erfc(x), E = exp(-x^2) for x >= 0 from the shared-memory table at address `tab` (interleaved {erfc(x_k), exp(-x_k^2)}).
 // Branch-free: beyond the table (x >= 8, where erfc < 1.2e-29 and exp(-x^2) < 1.7e-28) the last entry is expanded
 // around the argument's own grid point, which returns values of that same negligible magnitude.
-__device__ __forceinline__ void erfc_gauss_table(double x, unsigned tab, const double (&c)[10], double &ec, double &E) {
+__device__ __forceinline__ void erfc_gauss_table(double x, unsigned tab, const double (&c)[10], double &ec, double &E, unsigned stride = 16u,
+                                                 unsigned kmax = (unsigned)(kErfcTableEntries - 1)) {
     const double magic = 6755399441055744.0; // 2^52 + 2^51: the low word of (x*128 + magic) is round(x*128)
     const double t = fma(x, kErfcTableInvStep, magic);
     // x >= 0: one unsigned min clamps the index (a negative low word would read as huge and clamp too)
-    const int k = (int)min((unsigned)__double2loint(t), (unsigned)(kErfcTableEntries - 1));
+    const int k = (int)min((unsigned)__double2loint(t), kmax);
     const double kf = t - magic;
     const double d = fma(kf, -kErfcTableStep, x); // x - x_k, exact
     const double xk = kf * kErfcTableStep;
     double2 T; // the table lives in shared memory: address it as such (a generic load would cost an aperture check)
-    asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(T.x), "=d"(T.y) : "r"(tab + 16u * (unsigned)k));
+    asm("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(T.x), "=d"(T.y) : "r"(tab + stride * (unsigned)k));
     const double w = d * (x + xk);
     double e = fma(w, c[0], c[1]);
     e = fma(e, w, c[2]);
@@ -83,6 +92,9 @@ __device__ __forceinline__ void erfc_gauss_table(double x, unsigned tab, const d
     ec = fma(c[7] * T.y, I2, T.x);
 }
 __device__ __forceinline__ void erfc_gauss_table(double x, const ErfcCtx &cx, double &ec, double &E) { erfc_gauss_table(x, cx.tab, cx.c, ec, E); }
+__device__ __forceinline__ void erfc_gauss_table(double x, const ErfcTabRep &r, double &ec, double &E) {
+    erfc_gauss_table(x, r.tab, cg_specfun_c, ec, E, r.stride, r.kmax);
+}
 __device__ __forceinline__ void erfc_gauss_table(double x, const double *tab, double &ec, double &E) {
     erfc_gauss_table(x, (unsigned)__cvta_generic_to_shared(tab), cg_specfun_c, ec, E);
 }

@@ -28,6 +28,7 @@ struct SrfDefaults {
     static constexpr bool kHasAngcor = false;
     // schemes evaluated per pair (ErfcMultiSrf: several, each with its own accumulators)
     static constexpr int kSchemes = 1;
+    static constexpr bool kErfcArgIsEtaQ = false; // erfc family: the only erfc / Gaussian argument is eta q (<= eta inside the cut-off)
 };
 
 // 2/sqrt(pi); the reference forms it as 2/(2*sqrt(atan(1))) (e.g. wolf.hpp:36), equal to within one ulp
@@ -130,6 +131,7 @@ enum ErfcKind { kWolf, kFennell, kZeroDipole, kZahn, kEwaldT, kEwaldPlain };
 
 template <int KIND> struct ErfcFamilySrf : SrfDefaults {
     static constexpr int kTable = kTableErfc;
+    static constexpr bool kErfcArgIsEtaQ = true;
     static constexpr bool kHasAngcor = true;
     double eta, eta2, k1, c, e, c2, invF0;
     CG_HD ErfcFamilySrf() : eta(0), eta2(0), k1(0), c(0), e(0), c2(0), invF0(1) {}
@@ -202,6 +204,7 @@ template <int KIND> struct ErfcFamilySrf : SrfDefaults {
 // and ewald.hpp:175-195 (zeta = 0).  NS schemes, NS accumulators: cg_eval_multi_device (include/cg_b200.h).
 template <int NS> struct ErfcMultiSrf : SrfDefaults {
     static constexpr int kTable = kTableErfc;
+    static constexpr bool kErfcArgIsEtaQ = true;
     static constexpr int kSchemes = NS;
     double eta, k1;
     double m[NS], a0[NS], a1[NS], a2[NS], a3[NS], b0[NS], b2[NS], b3[NS];
