@@ -2823,6 +2823,35 @@ size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count) {
     return 256 + sizeof(double) * (size_t)nranks * (size_t)narrays * (size_t)std::max<int64_t>(count, 1);
 }
 
+// CG_HALO_PROF=1 (tuning aid): events around the four kernels of an exchange step; the means of the last steps are printed
+// when the process exits
+struct HaloProf {
+    static constexpr int kRing = 32;
+    cudaEvent_t ev[kRing][5];
+    long long step = 0;
+    HaloProf() {
+        for (auto &r : ev)
+            for (auto &e : r) cudaEventCreate(&e);
+    }
+    cudaEvent_t next(int k) { return ev[step % kRing][k]; }
+    void report() { // called after the last event of a ring was recorded
+        cudaEventSynchronize(ev[kRing - 1][4]);
+        double sum[4] = {0, 0, 0, 0};
+        for (int r = 0; r < kRing; r++)
+            for (int k = 0; k < 4; k++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev[r][k], ev[r][k + 1]);
+                sum[k] += ms;
+            }
+        std::fprintf(stderr, "halo prof (mean of %d steps, us): count %.1f scan %.1f scatter %.1f pull %.1f\n", kRing, 1e3 * sum[0] / kRing,
+                     1e3 * sum[1] / kRing, 1e3 * sum[2] / kRing, 1e3 * sum[3] / kRing);
+    }
+};
+static HaloProf *halo_prof() {
+    static HaloProf *p = std::getenv("CG_HALO_PROF") ? new HaloProf() : nullptr;
+    return p;
+}
+
 int cg_halo_publish(cg_handle *h, int nranks, int narrays, int zindex, int64_t count, const double *const *owned, const double *zlo,
                     const double *zhi, double period, void *block) {
     return cg_halo_publish_step(h, nranks, narrays, zindex, count, owned, zlo, zhi, period, block, -1, 0, nullptr, nullptr);
@@ -2863,9 +2892,14 @@ int cg_halo_publish_step(cg_handle *h, int nranks, int narrays, int zindex, int6
     CG_CUDA(h, h->halo_counts.ensure((size_t)nblocks * nranks));
     hp.block_counts = h->halo_counts.p;
     cudaStream_t st = h->stream;
+    HaloProf *hpf = halo_prof();
+    if (hpf) cudaEventRecord(hpf->next(0), st);
     halo_count_kernel<<<nblocks, kHaloThreads, 0, st>>>(hp);
+    if (hpf) cudaEventRecord(hpf->next(1), st);
     halo_scan_kernel<<<nranks, 1024, 0, st>>>(hp, nblocks, err_dev);
+    if (hpf) cudaEventRecord(hpf->next(2), st);
     halo_scatter_kernel<<<nblocks, kHaloThreads, 0, st>>>(hp);
+    if (hpf) cudaEventRecord(hpf->next(3), st);
     CG_CUDA(h, cudaGetLastError());
     return CG_OK;
 }
@@ -2905,6 +2939,11 @@ int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     const int per = (int)std::max<long long>(1, std::min<long long>((cmax + 255) / 256, std::max(1, 8 * sms / (nranks * narrays))));
     halo_pull_kernel<<<dim3((unsigned)per, (unsigned)narrays, (unsigned)nranks), 256, 0, h->stream>>>(g);
+    if (HaloProf *hpf = halo_prof()) {
+        cudaEventRecord(hpf->next(4), h->stream);
+        hpf->step++;
+        if (hpf->step % HaloProf::kRing == 0) hpf->report();
+    }
     CG_CUDA(h, cudaGetLastError());
     return CG_OK;
 }

@@ -143,27 +143,40 @@ CG_HD void pair_accumulate(const F &f, const CoreParams &cp, const TAB &tab, con
     if (MODE == kModeDipole) {
         // dipole_potential :294-307, dipole_field :380-399, dipole_dipole_energy :543-546, dipole_dipole_force :677-702
         if (WHAT & kWhatPotential) acc.phi += mjd * ek3 * R.angcor;
-        if (WHAT & (kWhatField | kWhatEnergy)) {
-            const T cd = T(3) * mjd * rinv2 * R.totcor * ek3; // coefficient of d
-            const T cm = -R.angcor * ek3;                     // coefficient of mu_j  (B - A = -angcor)
-            const T ex = cd * d.x + cm * muj.x, ey = cd * d.y + cm * muj.y, ez = cd * d.z + cm * muj.z;
-            if (WHAT & kWhatField) {
-                acc.Ex += ex;
-                acc.Ey += ey;
-                acc.Ez += ez;
-            }
-            if (WHAT & kWhatEnergy) acc.U -= mui.x * ex + mui.y * ey + mui.z * ez;
+        // Shared factors: Z = angcor e / r^3 and B = 3 totcor e / r^5.  The field is  B (mu_j.d) d - Z mu_j  (B - A = -angcor), the
+        // energy  -mu_i.E = Z (mu_i.mu_j) - B (mu_i.d)(mu_j.d), and B (mu_j.d), B (mu_i.d) are also the force's coefficients of
+        // mu_i and mu_j: every product is formed once and every sum is an FMA into its accumulator.
+        const T Z = R.angcor * ek3;
+        const T B = (T(3) * R.totcor) * (ek3 * rinv2);
+        const T ci = B * mjd;
+        if (WHAT & kWhatField) {
+            acc.Ex += ci * d.x; // one FMA per statement
+            acc.Ex -= Z * muj.x;
+            acc.Ey += ci * d.y;
+            acc.Ey -= Z * muj.y;
+            acc.Ez += ci * d.z;
+            acc.Ez -= Z * muj.z;
         }
-        if (WHAT & kWhatForce) {
+        if (WHAT & (kWhatEnergy | kWhatForce)) {
             const T mid = dot(mui, d), mm = dot(mui, muj);
-            const T ab = mid * mjd * rinv2;
-            const T t3 = T(3) * R.totcor;
-            const T e5 = ek3 * rinv2; // exp(-kr)/r^5
-            const T cd = -(t3 * (T(5) * ab - mm) + ab * R.r3corr) * e5;
-            const T ci = t3 * mjd * e5, cj = t3 * mid * e5;
-            acc.Fx += cd * d.x + ci * mui.x + cj * muj.x;
-            acc.Fy += cd * d.y + ci * mui.y + cj * muj.y;
-            acc.Fz += cd * d.z + ci * mui.z + cj * muj.z;
+            if (WHAT & kWhatEnergy) {
+                acc.U += Z * mm;
+                acc.U -= ci * mid;
+            }
+            if (WHAT & kWhatForce) {
+                const T ab = mid * mjd * rinv2;
+                const T cj = B * mid;
+                const T cd = -(B * (T(5) * ab - mm) + (ab * R.r3corr) * (ek3 * rinv2));
+                acc.Fx += cd * d.x;
+                acc.Fx += ci * mui.x;
+                acc.Fx += cj * muj.x;
+                acc.Fy += cd * d.y;
+                acc.Fy += ci * mui.y;
+                acc.Fy += cj * muj.y;
+                acc.Fz += cd * d.z;
+                acc.Fz += ci * mui.z;
+                acc.Fz += cj * muj.z;
+            }
         }
         return;
     }
