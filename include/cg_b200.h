@@ -188,7 +188,12 @@ int cg_eval_end(cg_handle *h, double *energy, int64_t *pairs);
  * them -- or should a device-side particle count (cg_set_count_device) exceed the arrays given to cg_set_system_device --
  * the evaluation is INVALID and says so: scalars[0] = NaN, scalars[1] = -1, per-particle outputs partial.  A caller of this
  * entry point checks scalars[1] < 0 and evaluates again (the next call sizes exactly); cg_eval / cg_eval_end do that
- * themselves. */
+ * themselves.
+ * Two kernels serve the evaluation.  Open systems of up to 8192 particles (environment: CG_ALLPAIRS_MAX) whose arrays are
+ * 16-byte aligned are evaluated straight from the SoA arrays by the all-pairs tile kernel (no sort; j-tiles staged through
+ * shared memory by TMA bulk copies); everything else is binned into cells and evaluated by the cell-list kernel.  The results
+ * agree to rounding, the pair counts exactly.  Handles that lend or borrow a system (cg_share_system), shards, device-side
+ * counts, fp32 arithmetic and quadrupoles always take the cell-list kernel. */
 int cg_eval_device(cg_handle *h, int mode, int what, double *force, double *field, double *potential,
                    double *scalars);
 
@@ -244,7 +249,8 @@ int cg_last_timings(cg_handle *h, double ms[4]);
 int cg_timings_history(cg_handle *h, int k, double *ms);
 /* counters of the last evaluation: [0] sorted entries incl. periodic images, [1] cells, [2] i-groups,
  * [3] pair-kernel launches, [4] total kernel launches, [5] j-split factor, [6] 1 if the evaluation took the sync-free path
- * (sizes from the previous evaluation, no host round trip), [7] work items of the pair kernel */
+ * (sizes from the previous evaluation, no host round trip), [7] work items of the pair kernel.  After an evaluation by the
+ * all-pairs kernel: [0] = n, [1] = 0 (no cells), [2] = i-groups of 32 consecutive particles, [5] = j-slices */
 int cg_last_counters(cg_handle *h, int64_t c[8]);
 
 /* Exchange step over peer memory, one process per GPU: each rank keeps its owned particles in a block
