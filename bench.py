@@ -629,26 +629,43 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
         nb, cnt = sub[0].numel(), own_host.shape[1]
         up_stream, copy_stream = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
         f_dev = {k: torch.zeros((nb, 3), dtype=torch.float64, device=dev) for k in evh}              # rows in received order
-        fo_dev = [{k: torch.zeros((cnt, 3), dtype=torch.float64, device=dev) for k in evh} for _ in range(2)]  # own rows, own order
-        f_host = [{k: torch.empty((cnt, 3), dtype=torch.float64).pin_memory() for k in evh} for _ in range(2)]
+        # What goes back to the host: the forces of the particles THIS rank evaluated (its block of cell rows), compacted by
+        # cg_collect_evaluated together with their global indices -- every particle of the system comes back from exactly one
+        # rank, whoever owns it.  Rows: 32 per i-group of the shard (sized after one evaluation, with room for the sync-free bound).
+        halo_h.set_system(evh["wolf"], sub, has_q=True, has_mu=False)
+        cg.eval_multi_device(list(evh.values()), cg.MODE_ION, cg.FORCE, force=[f_dev[k] for k in evh]) if w.fused else \
+            evh["wolf"].eval_device(cg.MODE_ION, cg.FORCE, force=f_dev["wolf"])
+        torch.cuda.synchronize()
+        rows = evh["wolf"].collect_rows_bound()
+        rows_exact = 32 * evh["wolf"].counters()["groups"]
+        rows += rows // 4 + 1024
+        fo_dev = [{k: torch.zeros((rows, 3), dtype=torch.float64, device=dev) for k in evh} for _ in range(2)]
+        id_dev = [torch.full((rows,), -1.0, dtype=torch.float64, device=dev) for _ in range(2)]
+        f_host = [{k: torch.empty((rows, 3), dtype=torch.float64).pin_memory() for k in evh} for _ in range(2)]
+        id_host = [torch.empty((rows,), dtype=torch.float64).pin_memory() for _ in range(2)]
         sc_dev = [{k: torch.zeros(2, dtype=torch.float64, device=dev) for k in evh} for _ in range(2)]
         sc_host = [{k: torch.empty(2, dtype=torch.float64).pin_memory() for k in evh} for _ in range(2)]
         uploaded = [torch.cuda.Event() for _ in range(2)]   # inputs of the step are on the device (upload stream)
         consumed = [torch.cuda.Event() for _ in range(2)]   # the exchange has read them (compute stream)
         done = [torch.cuda.Event() for _ in range(2)]       # kernels finished (compute stream)
         copied = [torch.cuda.Event() for _ in range(2)]     # download finished (copy stream)
-        h2d_bytes, d2h_bytes = own_host.numel() * 8, 2 * (cnt * 3 * 8 + 16)
+        used0 = 32 * (rows_exact // 32 * 51 // 50 + 8)  # what a step downloads (see step_host)
+        h2d_bytes, d2h_bytes = own_host.numel() * 8, 2 * (used0 * 3 * 8 + 16) + used0 * 8
         note = ("pinned host buffers; every rank uploads its own N/R particles (upload stream, double-buffered), the halo exchange brings "
-                "the rest over NVLink, cg_halo_collect_owned puts the forces of the rank's own particles into their original order and "
-                "they come back on a third stream, double-buffered: upload, kernels and download of consecutive steps overlap")
+                "the rest over NVLink, cg_collect_evaluated compacts the forces of the particles the rank evaluated (its block of cell "
+                "rows) together with their global indices, and they come back on a third stream, double-buffered: upload, kernels and "
+                "download of consecutive steps overlap; after the run the indices the ranks received back are checked to cover every "
+                "particle exactly once")
         state = {"s": 0}
 
         phase_ev = []  # per step: stream events at the start, after the upload, after the exchange, after the kernels; copy stream: downloaded
 
+        pool = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(ksteps + 8)]  # created outside the timed loop
+
         def step_host():
             b = state["s"] & 1
+            pe = pool[state["s"] % len(pool)]
             state["s"] += 1
-            pe = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
             phase_ev.append(pe)
             with torch.cuda.stream(up_stream):
                 up_stream.wait_event(consumed[b])  # the exchange of two steps ago has read this buffer
@@ -667,12 +684,18 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
                 for k, ev in evh.items():
                     ev.eval_device(cg.MODE_ION, cg.FORCE, force=f_dev[k], scalars=sc_dev[b][k])
             stream.wait_event(copied[b])  # the download of two steps ago has left this buffer
-            halo_h.collect_owned([f_dev[k] for k in evh], [fo_dev[b][k] for k in evh])
+            evh["wolf"].collect_evaluated([f_dev[k] for k in evh], [fo_dev[b][k] for k in evh], id_dev[b], ids=halo_h.ids())
             done[b].record(stream)
+            # rows that can hold a particle: 32 per i-group of the previous evaluation (+2 %: the configuration moves slowly);
+            # delivered() below verifies that nothing was cut off
+            ng = evh["wolf"].counters()["groups"]
+            used = min(rows, 32 * (ng + ng // 50 + 8))
+            state["used"] = used
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[b])
+                id_host[b][:used].copy_(id_dev[b][:used], non_blocking=True)
                 for k in evh:
-                    f_host[b][k].copy_(fo_dev[b][k], non_blocking=True)
+                    f_host[b][k][:used].copy_(fo_dev[b][k][:used], non_blocking=True)
                     sc_host[b][k].copy_(sc_dev[b][k], non_blocking=True)
                 copied[b].record(copy_stream)
             pe[3].record(stream)
@@ -682,6 +705,16 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
             copy_stream.synchronize()
             stream.synchronize()
             return int(sum(v[1].item() for v in sc_host[(state["s"] - 1) & 1].values()))
+
+        def delivered():
+            """-> (particles whose forces reached this rank's host buffers in the last step, all of them distinct and finite)"""
+            b = (state["s"] - 1) & 1
+            used = state["used"]
+            ids = id_host[b].numpy()[:used]
+            ok = ids >= 0
+            got = ids[ok].astype(np.int64)
+            fine = np.unique(got).size == got.size and all(np.isfinite(f_host[b][k].numpy()[:used][ok]).all() for k in evh)
+            return int(got.size), bool(fine)
     else:
         host = [t.cpu().numpy() for t in (w.full[:4] if w.full is not None else [])]
         if not host:  # multi-GPU without CUDA IPC: regenerate the inputs on the host side of this rank
@@ -746,12 +779,19 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
     t0 = time.perf_counter()
     for _ in range(ksteps):
         step_host()
+    t_enq = time.perf_counter() - t0  # host time to enqueue the steps (a step period below this is the host's, not the GPU's)
     pairs_last = drain()  # every step's results have reached the host buffers
     torch.cuda.synchronize()
     dt = allmax(time.perf_counter() - t0)
     pe = allsum(float(pairs_last)) * ksteps  # every step evaluates the same configuration
-    out = {"value": pe / dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": ksteps, "note": note}
+    out = {"value": pe / dt, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": ksteps, "note": note,
+           "host_enqueue_ms_per_step": 1e3 * allmax(t_enq) / ksteps}
     if halo_h is not None:
+        got, fine = delivered()
+        total = allsum(float(got))
+        out["delivered"] = {"particles_all_ranks": int(total), "expected": N, "distinct_and_finite_on_every_rank": allsum(0.0 if fine else 1.0) == 0.0}
+        if int(total) != N or not out["delivered"]["distinct_and_finite_on_every_rank"]:
+            raise RuntimeError("e2e: the forces that came back do not cover every particle once: %r" % (out["delivered"],))
         ph = phase_ev[-ksteps:]
         mean = lambda f: statistics.mean(f(i) for i in range(len(ph)))  # noqa: E731
         out["phases_ms_rank0"] = {

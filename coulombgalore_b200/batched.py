@@ -205,6 +205,29 @@ class BatchedEvaluator:
         check(lib.cg_timings_history(self.h, k, ms), "cg_timings_history", self.h)
         return [dict(sort_ms=ms[4 * i], pair_ms=ms[4 * i + 1], epilogue_ms=ms[4 * i + 2], step_ms=ms[4 * i + 3]) for i in range(k)]
 
+    def collect_rows_bound(self):
+        """Rows a collect_evaluated() output needs after the last (cell-list) evaluation: 32 x the group bound."""
+        rb = C.c_int64(0)
+        check(lib.cg_collect_evaluated(self.h, None, 1, 1, (C.c_void_p * 1)(None), (C.c_void_p * 1)(None), C.c_void_p(1), 0, C.byref(rb)),
+              "cg_collect_evaluated", self.h)
+        return int(rb.value)
+
+    def collect_evaluated(self, src, dst, ids_out, ids=None):
+        """cg_collect_evaluated: the rows of the per-particle outputs `src` (device tensors [n, w]) that this handle's shard
+        evaluated, compacted into `dst` ([rows, w]) with their identities in `ids_out` ([rows] float64; -1 = unused slot).
+        ids: the global-index array that travelled with the data (HaloExchange.ids()), or None for row numbers."""
+        n = len(src)
+        width = src[0].shape[1] if src[0].dim() > 1 else 1
+        cache = self.__dict__.setdefault("_collect_cache", {})
+        key = (tuple(t.data_ptr() for t in src), tuple(t.data_ptr() for t in dst))
+        if key not in cache:
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = ((C.c_void_p * n)(*key[0]), (C.c_void_p * n)(*key[1]))
+        sp, dp = cache[key]
+        check(lib.cg_collect_evaluated(self.h, None if ids is None else ids.data_ptr(), n, width, sp, dp, ids_out.data_ptr(), ids_out.numel(), None),
+              "cg_collect_evaluated", self.h)
+
     def counters(self):
         c = (C.c_int64 * 8)()
         check(lib.cg_last_counters(self.h, c), "cg_last_counters", self.h)

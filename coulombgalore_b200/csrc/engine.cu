@@ -941,6 +941,7 @@ struct HaloPull {
     double *dst[kMaxPeerArrays];
     long long dst_cap;
     int *n_out; // [0] particles received, [1] 1 = dst_cap too small, 2 = a peer did not publish in time
+    int *n_mirror; // optional: device-visible pinned HOST memory that receives n_out[0..1] as well (cg_halo_set_count_mirror)
     int step;   // >= 0: wait for the owners' `published` flags; -1: the caller has ordered the ranks
 };
 // grid: (chunks, narrays, nranks).  Every CTA reads the nranks counts from the peer headers (a few NVLink words).
@@ -967,6 +968,11 @@ __global__ void halo_pull_kernel(const __grid_constant__ HaloPull g) {
     if (a == 0 && r == g.nranks - 1 && blockIdx.x == 0 && threadIdx.x == 0) {
         g.n_out[0] = (int)min(off + mine, g.dst_cap);
         if (off + mine > g.dst_cap) g.n_out[1] = 1;
+        if (g.n_mirror) { // posted write to the host: no copy operation in the stream (it would queue behind the caller's downloads)
+            g.n_mirror[0] = (int)min(off + mine, g.dst_cap);
+            g.n_mirror[1] = off + mine > g.dst_cap ? 1 : 0;
+            __threadfence_system();
+        }
     }
     long long n = mine;
     if (off + n > g.dst_cap) n = max(0LL, g.dst_cap - off);
@@ -1061,6 +1067,7 @@ struct cg_handle {
     int *h_counts = nullptr;     // pinned: [0] n_sorted, [1] n_groups, [2] overflow (exact path: read after a sync)
     int *h_counts_async = nullptr; // pinned copy of the device counts of the last evaluation (read at the next call)
     DevBuf<int> halo_counts;
+    int *halo_mirror = nullptr; // cg_halo_set_count_mirror
     cudaEvent_t counts_ev = nullptr;
     bool counts_pending = false;
     // sync-free path: valid while (n, box, pbc, shard) are unchanged and the arrays sized by the last exact run still fit
@@ -1130,6 +1137,30 @@ __global__ void halo_collect_kernel(const double *__restrict__ ids, const int *_
         const long long own = (long long)ids[row] - lo;
         if (own < 0 || own >= count) continue;
         for (int k = 0; k < narrays; k++) a.dst[k][own * width + c] = a.src[k][t];
+    }
+}
+
+// Results of the particles a shard evaluated, compacted: slot g * 32 + lane of the output <-> particle `lane` of i-group g (the
+// groups of a sorted system are exactly the particles of the shard's block of cell rows; periodic images are never group members).
+// ids_out[slot] = the particle's identity (ids[row] when an index array travels with the data, else the row itself), -1 for the
+// empty lanes of a short group and for every slot beyond the last group.
+__global__ void collect_evaluated_kernel(const int *__restrict__ counts, const int2 *__restrict__ groups, const int *__restrict__ orig,
+                                         const double *__restrict__ ids, long long cap_rows, int narrays, int width,
+                                         double *__restrict__ ids_out, const __grid_constant__ CollectArgs a) {
+    const int ng = counts[2] != 0 ? 0 : counts[1];
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < cap_rows; slot += (long long)gridDim.x * blockDim.x) {
+        const long long g = slot >> 5;
+        const int lane = (int)(slot & 31);
+        int2 grp = make_int2(0, 0);
+        if (g < ng) grp = groups[g];
+        if (lane < grp.y) {
+            const long long row = orig[grp.x + lane];
+            ids_out[slot] = ids ? ids[row] : (double)row;
+            for (int k = 0; k < narrays; k++)
+                for (int c = 0; c < width; c++) a.dst[k][slot * width + c] = a.src[k][row * width + c];
+        } else {
+            ids_out[slot] = -1.0;
+        }
     }
 }
 
@@ -2904,6 +2935,12 @@ int cg_halo_publish_step(cg_handle *h, int nranks, int narrays, int zindex, int6
     return CG_OK;
 }
 
+int cg_halo_set_count_mirror(cg_handle *h, int *host_mapped) {
+    if (!h) return CG_ERR_INVALID;
+    h->halo_mirror = host_mapped;
+    return CG_OK;
+}
+
 int cg_halo_pull(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays, double *const *dst,
                  int64_t dst_cap, int *n_out) {
     return cg_halo_pull_step(h, nranks, rank, blocks, counts, narrays, dst, dst_cap, n_out, -1);
@@ -2934,6 +2971,7 @@ int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blo
     }
     g.dst_cap = dst_cap;
     g.n_out = n_out;
+    g.n_mirror = h->halo_mirror;
     g.step = (int)step;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
@@ -2979,6 +3017,29 @@ int cg_halo_collect_owned(cg_handle *h, const double *ids, const int *n_dev, int
     const long long total = (long long)bound * width;
     const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
     halo_collect_kernel<<<blocks, 256, 0, h->stream>>>(ids, n_dev, bound, lo, count, narrays, width, a);
+    CG_CUDA(h, cudaGetLastError());
+    return CG_OK;
+}
+
+int cg_collect_evaluated(cg_handle *h, const double *ids, int narrays, int width, const double *const *src, double *const *dst,
+                         double *ids_out, int64_t cap_rows, int64_t *rows_bound) {
+    if (!h || !src || !dst || !ids_out || narrays < 1 || narrays > 8 || width < 1 || cap_rows < 0) return CG_ERR_INVALID;
+    cg_handle *s = h->share_from ? h->share_from : h;
+    if (!s->sorted.valid || !s->sorted.has_groups[0]) {
+        h->err = "cg_collect_evaluated: the last evaluation did not go through the cell-list kernel (no sorted system)";
+        return CG_ERR_STATE;
+    }
+    if (rows_bound) *rows_bound = 32LL * s->sorted.ng_bound[0];
+    if (cap_rows == 0) return CG_OK;
+    cudaSetDevice(h->device);
+    CollectArgs a;
+    for (int k = 0; k < 8; k++) {
+        a.src[k] = k < narrays ? src[k] : nullptr;
+        a.dst[k] = k < narrays ? dst[k] : nullptr;
+        if (k < narrays && (!a.src[k] || !a.dst[k])) return CG_ERR_INVALID;
+    }
+    const unsigned blocks = (unsigned)std::min<long long>((cap_rows + 255) / 256, 148 * 16);
+    collect_evaluated_kernel<<<blocks, 256, 0, h->stream>>>(s->cell_count.p, s->groups[0].p, s->orig.p, ids, cap_rows, narrays, width, ids_out, a);
     CG_CUDA(h, cudaGetLastError());
     return CG_OK;
 }

@@ -260,6 +260,8 @@ class HaloExchange:
         self._n_host = torch.zeros(2, dtype=torch.int32).pin_memory() if self.device.type == "cuda" else torch.zeros(2, dtype=torch.int32)
         self._n_event = torch.cuda.Event() if self.device.type == "cuda" else None
         self._n_pending, self.last_count = False, 0
+        # the pull kernel posts the received count straight into the pinned words: no copy operation in the stream
+        self._mirror = self.device.type == "cuda" and lib.cg_halo_set_count_mirror(evaluator.h, self._n_host.data_ptr()) == 0
 
     @staticmethod
     def create(evaluator, n_total, box, n_payload, device, group=None):
@@ -309,7 +311,8 @@ class HaloExchange:
                 raise RuntimeError("HaloExchange: capacity %d too small" % self.capacity)
             self.n_bound = min(self.capacity, int(got[0]) + int(got[0]) // 8 + 1024)
         else:  # the count of this step travels to pinned memory behind the pull; a later gather() reads it without waiting
-            self._n_host.copy_(self.n_out, non_blocking=True)
+            if not self._mirror:
+                self._n_host.copy_(self.n_out, non_blocking=True)
             self._n_event.record(torch.cuda.current_stream(self.device))
             self._n_pending = True
         nb = self.n_bound
@@ -329,17 +332,22 @@ class HaloExchange:
         s = self.step
         self.step += 1
         b = s & 1
-        if getattr(self, "_src_of", None) is not owned2d:  # pointer table of the caller's (persistent) input block
-            self._src = (C.c_void_p * self.narrays)(*([owned2d[a].data_ptr() for a in range(self.n_payload)] + [self.ids_owned.data_ptr()]))
-            self._src_of = owned2d
+        cache = self.__dict__.setdefault("_src_cache", {})  # pointer tables of the caller's (persistent, e.g. double-buffered) input blocks
+        key = owned2d.data_ptr()
+        if key not in cache:
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = (C.c_void_p * self.narrays)(*([owned2d[a].data_ptr() for a in range(self.n_payload)] + [self.ids_owned.data_ptr()]))
             self._boxc = (C.c_double * 3)(*self.box)
+        self._src = cache[key]
         self._keep = owned2d
         self.check(self.lib.cg_halo_exchange_step(ev.h, self.world, self.rank, self.narrays, 2, self.count, self._src, self.zlo, self.zhi,
                                                   self._boxc, self.own_ptr[b], self.block_ptrs[b], self.block_ptrs[(s - 1) & 1] if s >= 1 else None,
                                                   self.counts_c, self.recv_c, self.capacity, self.n_bound, self.n_out.data_ptr(), s,
                                                   int(has_q), int(has_mu)), "cg_halo_exchange_step", ev.h)
         ev.n = self.n_bound
-        self._n_host.copy_(self.n_out, non_blocking=True)
+        if not self._mirror:
+            self._n_host.copy_(self.n_out, non_blocking=True)
         self._n_event.record(torch.cuda.current_stream(self.device))
         self._n_pending = True
         return self.n_bound
@@ -354,8 +362,13 @@ class HaloExchange:
         C = self.C
         n = len(src)
         width = src[0].shape[1] if src[0].dim() > 1 else 1
-        sp = (C.c_void_p * n)(*[t.data_ptr() for t in src])
-        dp = (C.c_void_p * n)(*[t.data_ptr() for t in dst])
+        cache = self.__dict__.setdefault("_collect_cache", {})
+        key = (tuple(t.data_ptr() for t in src), tuple(t.data_ptr() for t in dst))
+        if key not in cache:
+            if len(cache) > 8:
+                cache.clear()
+            cache[key] = ((C.c_void_p * n)(*key[0]), (C.c_void_p * n)(*key[1]))
+        sp, dp = cache[key]
         rc = self.lib.cg_halo_collect_owned(self.ev.h, self.ids().data_ptr(), self.n_out.data_ptr(), self.n_bound, self.lo, self.count, n,
                                             width, sp, dp)
         if rc != 0:

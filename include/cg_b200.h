@@ -304,6 +304,10 @@ int cg_halo_publish_step(cg_handle *h, int nranks, int narrays, int zindex, int6
                          void *const *prev_blocks, int *err_dev);
 int cg_halo_pull_step(cg_handle *h, int nranks, int rank, const void *const *blocks, const int64_t *counts, int narrays,
                       double *const *dst, int64_t dst_cap, int *n_out, int64_t step);
+/* Optional: a device-visible pinned HOST location (two ints) that every later cg_halo_pull[_step] of this handle also writes
+ * n_out[0..1] to, straight from the kernel.  A caller that follows the received count on the host then needs no copy operation
+ * in the stream (which would queue behind its own downloads on the copy engine).  NULL switches it off. */
+int cg_halo_set_count_mirror(cg_handle *h, int *host_mapped);
 /* One exchange step in one call: cg_halo_publish_step + cg_halo_pull_step + cg_set_system_device(h, n_bound, dst...) +
  * cg_set_count_device(h, n_out).  The arrays are x, y, z[, q][, mux, muy, muz] then anything else (e.g. the global index);
  * n_out = two ints on the device (count received; error word, also used by the publish); blocks = all ranks' blocks of this
@@ -314,12 +318,23 @@ int cg_halo_exchange_step(cg_handle *h, int nranks, int rank, int narrays, int z
                           void *const *prev_blocks, const int64_t *counts, double *const *dst, int64_t dst_cap, int64_t n_bound,
                           int *n_out, int64_t step, int has_q, int has_mu);
 /* Per-particle results of an evaluation on a halo window come in received order (row r belongs to the particle whose global
- * index the exchanged index array holds).  This brings the rows of the rank's OWN particles -- the only ones its kernels
- * computed -- into the order of the `owned` arrays it published: dst[k][(ids[r] - lo) * width + c] = src[k][r * width + c] for
+ * index the exchanged index array holds).  This brings the rows of the rank's OWN particles into the order of the `owned`
+ * arrays it published -- complete when ownership is spatial (every rank owns the particles of its block of cell rows);
+ * owned particles that another rank evaluates are not touched (see cg_collect_evaluated for arbitrary ownership): dst[k][(ids[r] - lo) * width + c] = src[k][r * width + c] for
  * ids[r] in [lo, lo + count), r < min(*n_dev, bound).  ids, n_dev, src and dst are DEVICE pointers; narrays <= 8 output arrays
  * of `width` doubles per row (3 for force / field, 1 for the potential) are handled by one launch on the handle's stream. */
 int cg_halo_collect_owned(cg_handle *h, const double *ids, const int *n_dev, int64_t bound, int64_t lo, int64_t count, int narrays,
                           int width, const double *const *src, double *const *dst);
+
+/* The per-particle results a shard (or a whole system) evaluated, compacted for the way back: slot g * 32 + l of dst / ids_out
+ * belongs to particle l of i-group g of the last cell-list evaluation of this handle.  ids_out[slot] = ids[row] (the global
+ * index that travelled with the data; ids == NULL: the row in the arrays given to cg_set_system_device), -1 for unused
+ * slots; dst[k][slot * width + c] = src[k][row * width + c].  Every particle of the shard's block of cell rows appears exactly
+ * once, whoever owns it, so the ranks' outputs together hold every particle of the system once.  cap_rows = rows of dst /
+ * ids_out (at least *rows_bound = 32 x the group bound of the last evaluation; cap_rows = 0 only queries it).  All pointers
+ * but rows_bound are DEVICE pointers; one launch on the handle's stream. */
+int cg_collect_evaluated(cg_handle *h, const double *ids, int narrays, int width, const double *const *src, double *const *dst,
+                         double *ids_out, int64_t cap_rows, int64_t *rows_bound);
 
 /* synthetic jittered lattice of SURVEY.md 8d generated on the device (n^3 particles) into DEVICE SoA buffers */
 int cg_generate_lattice_device(cg_handle *h, int32_t n, double a, uint64_t seed, double *x, double *y, double *z,

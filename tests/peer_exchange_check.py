@@ -90,12 +90,35 @@ def main():
         assert idx.unique().numel() == n_got  # no particle twice
         full_f[idx] = f[:n_got]
         full_e[idx] = e[:n_got]
-        # cg_halo_collect_owned: this rank's own rows, in the order of the arrays it published
+        # cg_halo_collect_owned: the rows of this rank's own particles that it received, in the order of the arrays it published;
+        # owned particles outside its window (ownership is by index here, not by position) are not touched
         own_f = torch.full((hi - lo, 3), float("nan"), dtype=torch.float64, device=dev)
         own_e = torch.full_like(own_f, float("nan"))
         halo.collect_owned([f, e], [own_f, own_e])
         stream.synchronize()
-        assert torch.equal(own_f, full_f[lo:hi]) and torch.equal(own_e, full_e[lo:hi]), "collect_owned, step %d" % step
+        got_mask = torch.zeros(N, dtype=torch.bool, device=dev)
+        got_mask[idx] = True
+        mine = got_mask[lo:hi]
+        assert torch.equal(own_f[mine], full_f[lo:hi][mine]) and torch.equal(own_e[mine], full_e[lo:hi][mine]), "collect_owned, step %d" % step
+        assert torch.isnan(own_f[~mine]).all()
+        # cg_collect_evaluated: the particles this rank evaluated (its block of cell rows), compacted with their global indices;
+        # all ranks together return every particle exactly once
+        rows = ev.collect_rows_bound()
+        ce_f = torch.full((rows, 3), float("nan"), dtype=torch.float64, device=dev)
+        ce_e = torch.full_like(ce_f, float("nan"))
+        ce_id = torch.full((rows,), -2.0, dtype=torch.float64, device=dev)
+        ev.collect_evaluated([f, e], [ce_f, ce_e], ce_id, ids=halo.ids())
+        stream.synchronize()
+        assert (ce_id != -2.0).all()
+        valid = ce_id >= 0
+        cid = ce_id[valid].long()
+        assert cid.unique().numel() == cid.numel()
+        assert torch.equal(ce_f[valid], full_f[cid]) and torch.equal(ce_e[valid], full_e[cid]), "collect_evaluated, step %d" % step
+        seen = torch.zeros(N, dtype=torch.float64, device=dev)
+        seen[cid] = 1.0
+        assert (full_f[seen == 0] == 0).all()  # what was not collected was not evaluated here
+        dist.all_reduce(seen)
+        assert (seen == 1.0).all(), "every particle is evaluated by exactly one rank"
         dist.all_reduce(full_f)
         dist.all_reduce(full_e)
         dist.all_reduce(sc2)
