@@ -134,10 +134,15 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
         tab = s_table;
     }
     // dummy entries behind both stages (far away: they fail the gate), zeros for an absent array
-    for (int k = tid; k < 2 * kArr * kApStride; k += 32 * kWarps) {
-        const int c = (k / kApStride) % kArr, e = k % kApStride;
-        if (e >= kApTile) s_stage[k] = c < 3 ? 1e30 : 0.0;
-        else if (!((present >> c) & 1u)) s_stage[k] = 0.0;
+    for (int k = tid; k < 2 * kArr * kDummies; k += 32 * kWarps) {
+        const int sc = k / kDummies, c = sc % kArr, e = k - sc * kDummies;
+        s_stage[sc * kApStride + kApTile + e] = c < 3 ? 1e30 : 0.0;
+    }
+    if ((present & ((1u << kArr) - 1u)) != (1u << kArr) - 1u) {
+        for (int k = tid; k < 2 * kArr * kApTile; k += 32 * kWarps) {
+            const int sc = k / kApTile, c = sc % kArr, e = k - sc * kApTile;
+            if (!((present >> c) & 1u)) s_stage[sc * kApStride + e] = 0.0;
+        }
     }
     if (tid == 0) {
         mbar_init(smem_addr(s_bar), 1);

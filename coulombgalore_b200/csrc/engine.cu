@@ -2307,7 +2307,7 @@ static int eval_device_impl(cg_handle *h, int mode, int what, double *d_force, d
     h->counters[4] = launches;
     h->counters[5] = split;
     h->counters[6] = fast ? 1 : 0;
-    h->counters[7] = (int64_t)ng_guess * split;
+    h->counters[7] = tail ? (int64_t)tail_items(ng_guess, wave) : (int64_t)ng_guess * split;
     return CG_OK;
 }
 

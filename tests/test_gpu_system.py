@@ -581,3 +581,34 @@ def test_two_schemes_in_one_pass_with_j_split(n_side, shard, oracle_kind):
             ev.close()
     finally:
         torch.cuda.set_stream(torch.cuda.default_stream(dev))
+
+
+@pytest.mark.parametrize("name,mode,what", [("wolf", cg.MODE_ION, cg.ENERGY | cg.FORCE | cg.FIELD | cg.POTENTIAL),
+                                            ("reactionfield", cg.MODE_DIPOLE, cg.ENERGY | cg.FORCE | cg.FIELD),
+                                            ("ewald_screened", cg.MODE_MULTIPOLE, cg.ENERGY | cg.FORCE)])
+def test_tail_split_of_the_last_round(name, mode, what, oracle_kind):
+    """A system with somewhat more i-groups than resident warps: the groups beyond the last full round are cut into row slices
+    (kparams.cuh: tail_plan) whose partial outputs the epilogue kernel sums.  Parity of every particle against the oracle, the same
+    pair count and (to rounding) the same outputs as with whole groups (CG_TAIL=0), and the item counter shows the extra items."""
+    x, y, z, q, mu = O.generate(40, 3.0, 2024 + mode, oracle_kind)
+    mk, p = zoo()[name]
+    L = 120.0
+    res = {}
+    for key in ("tail", "whole"):
+        if key == "whole":
+            os.environ["CG_TAIL"] = "0"
+        try:
+            res[key] = run_case(mk(), O.Scheme(p, oracle_kind), x, y, z, q, mu, [L] * 3, True, mode, what)
+        finally:
+            os.environ.pop("CG_TAIL", None)
+    g, r = res["tail"]
+    gw, _ = res["whole"]
+    groups = g["counters"]["groups"]
+    assert gw["counters"]["items"] == groups and g["counters"]["split"] == 1
+    assert g["counters"]["items"] > groups, (g["counters"], "the tail split did not engage: pick a size with ng mod wave < wave / 2")
+    errs = compare(g, r, what)
+    assert all(v <= 1.0 for v in errs.values()), errs
+    assert g["pairs"] == gw["pairs"]
+    for k in ("force", "field", "potential"):
+        if k in g and g[k] is not None and k in gw and gw[k] is not None:
+            assert np.abs(g[k] - gw[k]).max() <= 1e-12 * np.abs(gw[k]).max()
