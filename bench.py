@@ -11,6 +11,8 @@ all per-particle forces on it and the reductions (positions are treated as new e
 in-cutoff pair (i <- j); `value` = pairs evaluated by all ranks per second with the inputs resident in HBM; `e2e` is the same
 metric with HOST buffers: H2D of positions / charges and D2H of the forces inside the timing.
 
+Config 1 (4096 charges, open box) is evaluated by the all-pairs tile kernel on one GPU (no sort; TMA-staged j-tiles).
+
 N > 1: every rank owns N/R particles.  Per step every rank sorts its particles into one segment per
 destination rank inside a peer-mapped block (cg_halo_publish) and pulls, over NVLink peer memory, only the particles of the
 cell layers within one cut-off of its block of cell rows (cg_halo_pull); then it bins what it received and evaluates its
@@ -790,8 +792,10 @@ def e2e_headline(w, args, rank, world, local, dev, stream, barrier, allmax, alls
         got, fine = delivered()
         total = allsum(float(got))
         out["delivered"] = {"particles_all_ranks": int(total), "expected": N, "distinct_and_finite_on_every_rank": allsum(0.0 if fine else 1.0) == 0.0}
-        if int(total) != N or not out["delivered"]["distinct_and_finite_on_every_rank"]:
-            raise RuntimeError("e2e: the forces that came back do not cover every particle once: %r" % (out["delivered"],))
+        out["delivered"]["ok"] = int(total) == N and out["delivered"]["distinct_and_finite_on_every_rank"]
+        if not out["delivered"]["ok"]:  # reported, not fatal: the line still carries the device-resident numbers
+            sys.stderr.write("bench.py: e2e: the forces that came back do not cover every particle once: %r\n" % (out["delivered"],))
+            out["value_is_valid"] = False
         ph = phase_ev[-ksteps:]
         mean = lambda f: statistics.mean(f(i) for i in range(len(ph)))  # noqa: E731
         out["phases_ms_rank0"] = {

@@ -235,13 +235,13 @@ allpairs_kernel(const __grid_constant__ APParams p, const __grid_constant__ F f,
         __syncthreads();
         if (t == 0) AP_MARK();
         // ---- PHASE 1 ----
-        // Error budget of the fp32 test against the exact r2 < rc2 (S = |x'_i| + max |c'|): both positions rounded to fp32
-        // 2^-23 S^2, |c'|^2 in three roundings 3 2^-24 S^2, three FFMA partial sums <= S^2 each 3 2^-24 S^2, the rounding of
-        // thr 2^-24 (rc2 + S^2): <= 2^-24 (9 S^2 + rc2); the margin takes 1.5 x (10 S^2 + rc2).
+        // Error budget of the fp32 test against the exact r2 < rc2, in units of 2^-24 (S = |x'_i| + max |c'| of the tile): both
+        // positions rounded to fp32: 2 S^2; |c'|^2 in three roundings: 3 S^2; three FFMA partial sums <= S^2 each: 3 S^2; the
+        // rounding of thr0 and of thr0 + margin: 2 (rc2 + S^2).  Needed: 10 S^2 + 2 rc2; the margin takes 1.5 x that.
         float thr = -INFINITY;
         if (act) {
             const float S = (xnorm + sqrtf(__int_as_float(s_wmax[s]))) * 1.0001f;
-            thr = thr0 + 1.5f * 5.9604645e-8f * (10.0f * S * S + fabsf(thr0) + (float)xn2);
+            thr = thr0 + 1.5f * 5.9604645e-8f * (10.0f * S * S + 2.0f * (fabsf(thr0) + (float)xn2)); // |thr0| + |x'|^2 >= rc2
         }
         int qn = 0, total = 0;
         for (int b = 0; b < nbt; b++) {
