@@ -97,6 +97,7 @@ def _load():
         "cg_eval_multi_end": [C.POINTER(C.c_void_p), C.c_int, _dp, C.POINTER(C.c_int64)],
         "cg_halo_collect_owned": [H, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_void_p),
                                   C.POINTER(C.c_void_p)],
+        "cg_tail_plan_probe": [C.c_int, C.c_int, C.POINTER(C.c_int)],
         "cg_collect_evaluated": [H, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p, C.c_int64,
                                  C.POINTER(C.c_int64)],
         "cg_dipole_moments": [H, _dp],
@@ -182,7 +183,7 @@ EXPORTED = ["cg_scheme_plain", "cg_scheme_reactionfield", "cg_scheme_poisson", "
             "cg_scheme_splined", "cg_scheme_splined_tables", "cg_srf_host", "cg_device_count", "cg_create",
             "cg_destroy", "cg_last_error", "cg_version", "cg_set_stream", "cg_set_precision", "cg_share_system", "cg_set_shard",
             "cg_set_system", "cg_set_system_device", "cg_eval", "cg_eval_begin", "cg_eval_end", "cg_eval_device", "cg_eval_multi_device", "cg_eval_multi_begin", "cg_eval_multi_end", "cg_set_quadrupoles", "cg_set_quadrupoles_device", "cg_self_terms", "cg_self_terms_device", "cg_dipole_moments", "cg_dipole_moments_device", "cg_read_scalars", "cg_dipole_torque", "cg_dipole_torque_device", "cg_srf_device", "cg_last_timings", "cg_timings_history",
-            "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_set_grid_count", "cg_set_count_device", "cg_shard_window", "cg_halo_block_bytes", "cg_layout_probe", "cg_halo_publish",
+            "cg_last_counters", "cg_peer_alloc", "cg_peer_free", "cg_peer_open", "cg_peer_close", "cg_peer_gather", "cg_set_grid_count", "cg_set_count_device", "cg_shard_window", "cg_halo_block_bytes", "cg_layout_probe", "cg_tail_plan_probe", "cg_halo_publish",
             "cg_halo_pull", "cg_halo_set_count_mirror", "cg_halo_publish_step", "cg_halo_pull_step", "cg_halo_exchange_step", "cg_halo_collect_owned", "cg_collect_evaluated", "cg_generate_lattice_device", "cg_recip_create", "cg_recip_destroy", "cg_recip_last_error",
             "cg_recip_set_stream", "cg_recip_num_kvectors", "cg_recip_kvectors", "cg_recip_q_device", "cg_recip_get_q", "cg_recip_set_q",
             "cg_recip_update", "cg_recip_update_device", "cg_recip_energy", "cg_recip_energy_device", "cg_recip_force_field",

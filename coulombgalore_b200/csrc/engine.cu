@@ -2829,6 +2829,16 @@ int cg_shard_window(cg_handle *h, const double *box, int rank, int nranks, int64
 
 // host-only view of the layout a shard would use (no handle, no GPU): for tests and for callers that plan the exchange
 // out_i: nprim[3], ghost[3], row0, row1, z0, nzl;  out_d: cell size[3], window[2]
+int cg_tail_plan_probe(int groups, int resident_warps, int out[3]) {
+    if (!out || groups < 0) return CG_ERR_INVALID;
+    int n_whole = 0, ts = 1;
+    tail_plan(groups, resident_warps, n_whole, ts);
+    out[0] = n_whole;
+    out[1] = ts;
+    out[2] = tail_items(groups, resident_warps);
+    return CG_OK;
+}
+
 int cg_layout_probe(double cutoff, const double *box, int pbc, int rank, int nranks, int64_t n_global, int out_i[10], double out_d[5]) {
     if (!(cutoff > 0.0) || !box || !out_i || !out_d || nranks < 1 || rank < 0 || rank >= nranks || n_global < 1) return CG_ERR_INVALID;
     SortParams sp;

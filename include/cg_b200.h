@@ -282,6 +282,11 @@ int cg_set_grid_count(cg_handle *h, int64_t n_global);
 int cg_set_count_device(cg_handle *h, const int *n_dev);
 int cg_shard_window(cg_handle *h, const double *box, int rank, int nranks, int64_t n_global, double window[2]);
 size_t cg_halo_block_bytes(int nranks, int narrays, int64_t count);
+/* Host-only probe of the pair kernel's work plan (csrc/kparams.cuh: tail_plan), for tests: with `groups` i-groups and
+ * `resident_warps` warps on the machine, out[0] = groups evaluated whole, out[1] = row slices of each of the other groups
+ * (1 = no tail split), out[2] = work items of the launch. */
+int cg_tail_plan_probe(int groups, int resident_warps, int out[3]);
+
 /* The cell layout and shard window as plain numbers, computed on the host without a handle or a GPU: out_i = cells per
  * dimension [3], ghost layers [3], the shard's primary cell rows [row0, row1) (row = z_cell * cells_y + y_cell), its first
  * cell layer and layer count in the ghost-extended grid; out_d = cell edge [3], z-window [2] (as cg_shard_window). */

@@ -141,3 +141,23 @@ def test_shard_layout_tiles_the_box_and_windows_hold_every_neighbour(nranks):
             zj = (zi + rng.uniform(-rc, rc)) % box[2]
             lo, hi = lay[t][1][3], lay[t][1][4]
             assert any(lo <= zj + k * box[2] < hi for k in (-1, 0, 1)), (trial, t, zi, zj, lo, hi)
+
+
+def test_tail_plan_of_the_pair_kernel():
+    """Host-only work plan of the persistent pair grid (cg_tail_plan_probe = kparams.cuh: tail_plan): whole groups fill complete
+    rounds, the groups of a short last round become 2..4 row slices each that fit one round; nothing changes when the groups fit
+    the machine, divide evenly or the last round is more than half full."""
+    lib = _capi.lib
+    out = (C.c_int * 3)()
+    wave = 148 * 12
+    for ng in list(range(0, 4000, 7)) + [wave, wave + 1, 2 * wave - 1, 2 * wave, 4056, 8125, 32500, 10 ** 6]:
+        assert lib.cg_tail_plan_probe(ng, wave, out) == 0
+        n_whole, ts, items = out[0], out[1], out[2]
+        rem = ng - n_whole
+        assert 0 <= n_whole <= ng and 1 <= ts <= 4 and items == n_whole + rem * ts
+        if ts == 1:
+            assert n_whole == ng and (ng <= wave or ng % wave == 0 or wave // (ng % wave) < 2)
+        else:
+            assert n_whole % wave == 0 and n_whole > 0 and rem == ng % wave and rem * ts <= wave and ts == min(4, wave // rem)
+    assert lib.cg_tail_plan_probe(4056, wave, out) == 0 and list(out) == [3552, 3, 3552 + 504 * 3]  # the 1/8 shard of config 2
+    assert lib.cg_tail_plan_probe(10, 0, out) == 0 and list(out) == [10, 1, 10]                    # switched off
