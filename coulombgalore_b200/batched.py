@@ -208,8 +208,7 @@ class BatchedEvaluator:
     def collect_rows_bound(self):
         """Rows a collect_evaluated() output needs after the last (cell-list) evaluation: 32 x the group bound."""
         rb = C.c_int64(0)
-        check(lib.cg_collect_evaluated(self.h, None, 1, 1, (C.c_void_p * 1)(None), (C.c_void_p * 1)(None), C.c_void_p(1), 0, C.byref(rb)),
-              "cg_collect_evaluated", self.h)
+        check(lib.cg_collect_evaluated(self.h, None, 0, 0, None, None, None, 0, C.byref(rb)), "cg_collect_evaluated", self.h)
         return int(rb.value)
 
     def collect_evaluated(self, src, dst, ids_out, ids=None):

@@ -3033,14 +3033,15 @@ int cg_halo_collect_owned(cg_handle *h, const double *ids, const int *n_dev, int
 
 int cg_collect_evaluated(cg_handle *h, const double *ids, int narrays, int width, const double *const *src, double *const *dst,
                          double *ids_out, int64_t cap_rows, int64_t *rows_bound) {
-    if (!h || !src || !dst || !ids_out || narrays < 1 || narrays > 8 || width < 1 || cap_rows < 0) return CG_ERR_INVALID;
+    if (!h || cap_rows < 0) return CG_ERR_INVALID;
     cg_handle *s = h->share_from ? h->share_from : h;
     if (!s->sorted.valid || !s->sorted.has_groups[0]) {
         h->err = "cg_collect_evaluated: the last evaluation did not go through the cell-list kernel (no sorted system)";
         return CG_ERR_STATE;
     }
     if (rows_bound) *rows_bound = 32LL * s->sorted.ng_bound[0];
-    if (cap_rows == 0) return CG_OK;
+    if (cap_rows == 0) return CG_OK; // a query of the bound only
+    if (!src || !dst || !ids_out || narrays < 1 || narrays > 8 || width < 1) return CG_ERR_INVALID;
     cudaSetDevice(h->device);
     CollectArgs a;
     for (int k = 0; k < 8; k++) {

@@ -68,6 +68,15 @@ class BatchedEvaluator {
     void eval_device(int mode, int what, double *force, double *field, double *potential, double *scalars) {
         check(cg_eval_device(h_, mode, what, force, field, potential, scalars), "cg_eval_device");
     }
+    /** the per-particle results this evaluator's shard computed in its last (cell-list) evaluation, compacted for the way back to
+     *  the host: slot g * 32 + l <-> particle l of i-group g, ids_out[slot] = ids[row] (ids == nullptr: the row itself), -1 for
+     *  unused slots; returns the rows dst / ids_out must have (cap_rows = 0 only asks).  Device pointers, one launch. */
+    int64_t collect_evaluated(const double *ids, int narrays, int width, const double *const *src, double *const *dst, double *ids_out,
+                              int64_t cap_rows) {
+        int64_t rows = 0;
+        check(cg_collect_evaluated(h_, ids, narrays, width, src, dst, ids_out, cap_rows, &rows), "cg_collect_evaluated");
+        return rows;
+    }
     /** eval_device + a read of the two scalars (waits for the stream) + one exactly-sized re-evaluation if the first was invalid */
     void eval_device_checked(int mode, int what, double *force, double *field, double *potential, double *scalars, double host_scalars[2]) {
         for (int attempt = 0; attempt < 2; attempt++) {
